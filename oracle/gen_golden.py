@@ -1,0 +1,116 @@
+#!/usr/bin/env python
+"""Generate tests/golden/ from the UNMODIFIED reference compiled in this container.
+
+Test infrastructure.  Run here (needs /root/reference); the outputs are committed
+because /root/reference does not exist on the GPU box.
+
+    python oracle/gen_golden.py            # everything
+    python oracle/gen_golden.py --fast     # skip the high-spp reference images
+
+What is written (all produced by oracle/_ref/libref.so or oracle/_ref/TrimeshTracer,
+i.e. by the reference's own code -- never by oracle.c or by the CUDA path):
+
+  scenes/<name>.npz     triangle array exactly as LoadScene builds it (model + 2 floor
+                        triangles, main.cpp:135-162), model bounds, the main() camera
+  rays/<name>.npz       rays a reference render shoots (primary / bounce / shadow) with
+                        the octree HitScene answer (flag, t, pos, normal) and the
+                        ID-carrying brute-force answer
+  kat.json              RNG / sampler / camera known answers; sha256 + ray counts of the
+                        reference binary's 640x360x4 renders
+  images/<name>_*.png   high-spp reference renders for the statistical image gate
+"""
+from __future__ import annotations
+
+import argparse
+import hashlib
+import json
+import os
+import subprocess
+import sys
+import tempfile
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from oracle.pyoracle import REF_BIN, REF_ROOT, Ref  # noqa: E402
+
+GOLD = os.path.join(ROOT, "tests", "golden")
+SCENES = ["triangle", "cube", "suzanne", "teapot"]
+RAY_STRIDE = {"triangle": 16, "cube": 8, "suzanne": 8, "teapot": 8}
+
+
+def bits(a):
+    return np.ascontiguousarray(a, np.float32).view(np.uint32)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--fast", action="store_true")
+    args = ap.parse_args()
+    from PIL import Image
+
+    R = Ref()
+    for d in ("scenes", "rays", "images"):
+        os.makedirs(os.path.join(GOLD, d), exist_ok=True)
+    kat = {"generator": "oracle/gen_golden.py", "reference_build": "g++ 13.3 -O2 -ffp-contract=off -DNDEBUG + tbb_shim"}
+
+    # --- RNG / samplers (maths.cpp:5-38) ---
+    kat["rng"] = {}
+    for seed in (1, 9782, 0xDEADBEEF, 2463534242):
+        st, fl = R.rng_states(seed, 16)
+        kat["rng"][str(seed)] = {"states": st.tolist(), "float_bits": bits(fl).tolist()}
+    disk, s_end = R.random_in_unit_disk(12345, 64)
+    kat["disk"] = {"seed": 12345, "bits": bits(disk).ravel().tolist(), "end_state": int(s_end)}
+    unit, s_end = R.random_unit_vectors(4321, 64)
+    kat["unit_vector"] = {"seed": 4321, "bits": bits(unit).ravel().tolist(), "end_state": int(s_end)}
+    kat["light_dir_bits"] = bits(R.light_dir()).tolist()
+    cam = R.camera_make([1.5, 2.0, -3.0], [0.1, -0.2, 0.3], [0, 1, 0], 60.0, 16 / 9, 0.03, 4.2)
+    kat["camera_make"] = {"args": [[1.5, 2.0, -3.0], [0.1, -0.2, 0.3], [0, 1, 0], 60.0, 16 / 9, 0.03, 4.2],
+                          "bits": bits(cam).tolist()}
+    st2 = np.stack([np.linspace(0, 1, 32, dtype=np.float32), np.linspace(1, 0, 32, dtype=np.float32)], 1)
+    rays, s_end = R.camera_get_rays(cam, st2, 777)
+    kat["camera_get_rays"] = {"seed": 777, "st_bits": bits(st2).ravel().tolist(), "ray_bits": bits(rays).ravel().tolist(),
+                              "end_state": int(s_end)}
+
+    # --- scenes, ray sets, binary renders ---
+    kat["renders_640x360x4"] = {}
+    for name in SCENES:
+        path = os.path.join(REF_ROOT, "data", f"{name}.obj")
+        h, tris, mn, mx = R.scene_load(path)
+        cam = R.camera_for_scene(h, path, 640, 360)
+        np.savez_compressed(os.path.join(GOLD, "scenes", f"{name}.npz"), tris=tris, bounds_min=mn, bounds_max=mx,
+                            camera_640x360=cam)
+        rays, kind = R.record_path_rays(h, cam, 640, 360, RAY_STRIDE[name], 200000)
+        flag, t, pos, nrm = R.hit_scene(h, rays)
+        bid, bt, bpos, bnrm = R.hit_brute(h, rays)
+        same = ((flag == 1) == (bid >= 0)).all() and (bits(t) == bits(bt)).all() and (bits(pos) == bits(bpos)).all() \
+            and (bits(nrm) == bits(bnrm)).all()
+        print(f"{name}: {tris.shape[0]} tris, {rays.shape[0]} rays, hits {(bid >= 0).sum()}, octree==brute: {same}")
+        assert same, "reference octree HitScene and ID-carrying brute force disagree"
+        np.savez_compressed(os.path.join(GOLD, "rays", f"{name}.npz"), rays=rays, kind=kind.astype(np.int8), flag=flag.astype(np.int8),
+                            id=bid, t=t, pos=pos, normal=nrm)
+        # the reference BINARY, unmodified main(): output.png + its own report lines
+        with tempfile.TemporaryDirectory() as td:
+            out = subprocess.run([REF_BIN, "640", "360", "4", path], cwd=td, check=True, capture_output=True, text=True).stdout
+            img = np.array(Image.open(os.path.join(td, "output.png")).convert("RGBA"))
+        krays = float(out.split("- ")[1].split(" K Rays")[0])
+        rimg, rc = R.render(h, cam, 640, 360, 4)
+        assert (rimg[::-1] == img).all(), "harness render != binary render"
+        kat["renders_640x360x4"][name] = {"sha256_rgba_png_order": hashlib.sha256(img.tobytes()).hexdigest(), "ray_count": int(rc),
+                                          "reported_krays": krays, "mean_rgb": img[..., :3].reshape(-1, 3).mean(0).tolist()}
+        if not args.fast and name in ("cube", "suzanne"):
+            w, hgt, spp = 320, 180, (1024 if name == "cube" else 256)
+            cam_s = R.camera_for_scene(h, path, w, hgt)
+            big, rc = R.render(h, cam_s, w, hgt, spp)
+            Image.fromarray(big[::-1, :, :3].copy()).save(os.path.join(GOLD, "images", f"{name}_{w}x{hgt}_{spp}spp.png"), optimize=True)
+            print(f"  reference image {w}x{hgt}x{spp}: {rc} rays")
+        R.scene_free(h)
+
+    with open(os.path.join(GOLD, "kat.json"), "w") as f:
+        json.dump(kat, f, indent=1)
+    print("wrote", GOLD)
+
+
+if __name__ == "__main__":
+    main()

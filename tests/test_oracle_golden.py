@@ -1,0 +1,103 @@
+"""The CPU restatement (oracle/oracle.c) against the golden vectors the unmodified
+reference produced (tests/golden/, oracle/gen_golden.py).  This is what pins the oracle."""
+import hashlib
+
+import numpy as np
+import pytest
+
+from conftest import bits, from_bits, load_rays, load_scene
+from oracle.pyoracle import RNG_ROW, TRIG_LIBM, TRIG_SPEC
+
+
+def test_xorshift_known_answers(oracle, kat):
+    # from state 1 -> 268476417, 1157628417, ...
+    st, _ = oracle.rng_states(1, 6)
+    assert st.tolist() == [268476417, 1157628417, 1158709409, 269814307, 672445067, 2022772137]
+    st, _ = oracle.rng_states(9782, 3)
+    assert st.tolist() == [1995203669, 2799024486, 2838786458]
+    for seed, g in kat["rng"].items():
+        st, fl = oracle.rng_states(int(seed), 16)
+        assert st.tolist() == g["states"]
+        assert bits(fl).tolist() == g["float_bits"]
+
+
+def test_samplers(oracle, kat):
+    d, s = oracle.random_in_unit_disk(kat["disk"]["seed"], 64)
+    assert bits(d).ravel().tolist() == kat["disk"]["bits"] and s == kat["disk"]["end_state"]
+    u, s = oracle.random_unit_vectors(kat["unit_vector"]["seed"], 64, TRIG_LIBM)
+    assert bits(u).ravel().tolist() == kat["unit_vector"]["bits"] and s == kat["unit_vector"]["end_state"]
+    assert bits(oracle.light_dir()).tolist() == kat["light_dir_bits"]
+
+
+def test_trig_spec_is_accurate(oracle):
+    # the portable sincos must be a faithful sinf/cosf: <= 1 ulp from the float64 truth
+    a = (np.arange(0, 1 << 24, 257, dtype=np.float32) / np.float32(16777216.0)) * np.float32(2.0) * np.float32(3.1415926)
+    s, c = oracle.sincos_spec(a)
+    ts, tc = np.sin(a.astype(np.float64)), np.cos(a.astype(np.float64))
+    assert np.all(np.abs(s - ts) <= np.spacing(np.abs(ts).astype(np.float32)) * 0.5000001 + 1e-45)
+    assert np.all(np.abs(c - tc) <= np.spacing(np.abs(tc).astype(np.float32)) * 0.5000001 + 1e-45)
+
+
+def test_trig_spec_vs_libm_unit_vectors(oracle):
+    a, sa = oracle.random_unit_vectors(99, 20000, TRIG_LIBM)
+    b, sb = oracle.random_unit_vectors(99, 20000, TRIG_SPEC)
+    assert sa == sb
+    assert np.abs(a - b).max() <= 6e-8  # one ulp of a value < 1
+
+
+def test_camera(oracle, kat):
+    g = kat["camera_make"]
+    cam = oracle.camera_make(*g["args"])
+    assert bits(cam).tolist() == g["bits"]
+    g2 = kat["camera_get_rays"]
+    st2 = from_bits(g2["st_bits"], (-1, 2))
+    rays, s = oracle.camera_get_rays(cam, st2, g2["seed"])
+    assert bits(rays).ravel().tolist() == g2["ray_bits"] and s == g2["end_state"]
+
+
+@pytest.mark.parametrize("name", ["triangle", "cube", "suzanne", "teapot"])
+def test_floor_bounds_camera(oracle, name):
+    sc = load_scene(name)
+    out, mn, mx = oracle.add_floor(sc["tris"][:-2])
+    assert (bits(out) == bits(sc["tris"])).all()
+    assert (bits(mn) == bits(sc["bounds_min"])).all() and (bits(mx) == bits(sc["bounds_max"])).all()
+    cam = oracle.camera_for_scene(mn, mx, 640, 360)
+    assert (bits(cam) == bits(sc["camera_640x360"])).all()
+
+
+@pytest.mark.parametrize("name", ["triangle", "cube", "suzanne", "teapot"])
+def test_hit_ids_t_and_payload(oracle, name):
+    """Flag, triangle ID, t bits and the full Hit payload equal the reference's on its own ray set."""
+    sc, g = load_scene(name), load_rays(name)
+    ids, t, pos, nrm = oracle.hit_brute(sc["tris"], g["rays"])
+    hit = g["id"] >= 0
+    assert ((g["flag"] == 1) == hit).all()
+    assert (ids == g["id"]).all()
+    assert (bits(t)[hit] == bits(g["t"])[hit]).all()
+    assert (bits(pos)[hit] == bits(g["pos"])[hit]).all()
+    assert (bits(nrm)[hit] == bits(g["normal"])[hit]).all()
+    # any-hit (shadow semantics, main.cpp:59-60): same boolean
+    aid, *_ = oracle.hit_brute(sc["tris"], g["rays"], any_hit=True)
+    assert ((aid >= 0) == hit).all()
+
+
+@pytest.mark.parametrize("name", ["triangle", "cube", "suzanne"])
+def test_render_row_mode_matches_reference_binary(oracle, kat, name):
+    """oracle (row RNG, libm trig) == the reference binary's output.png bytes and ray count."""
+    sc = load_scene(name)
+    img, rays = oracle.render(sc["tris"], sc["camera_640x360"], 640, 360, 4, RNG_ROW, TRIG_LIBM)
+    g = kat["renders_640x360x4"][name]
+    assert rays == g["ray_count"]
+    assert hashlib.sha256(np.ascontiguousarray(img[::-1]).tobytes()).hexdigest() == g["sha256_rgba_png_order"]
+
+
+def test_render_is_thread_count_independent(oracle):
+    sc = load_scene("cube")
+    a = oracle.render(sc["tris"], sc["camera_640x360"], 160, 90, 2, threads=1)
+    b = oracle.render(sc["tris"], sc["camera_640x360"], 160, 90, 2, threads=5)
+    assert a[1] == b[1] and (a[0] == b[0]).all()
+
+
+def test_pixel_seed_nonzero(oracle):
+    seeds = [oracle.pixel_seed(i) for i in range(0, 1 << 16, 7)]
+    assert all(s != 0 for s in seeds) and len(set(seeds)) == len(seeds)
