@@ -1,0 +1,348 @@
+#!/usr/bin/env python
+"""bench.py -- Mrays/s of the Trace() hot path (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload NAME]
+
+One "step" = one frame of the workload: sponza stand-in (66 452 triangles, tools/gen_sponza.py;
+the reference's own data/sponza.obj is absent from this environment) at 1920x1080, 64 spp --
+the configuration BASELINE.json's metric is quoted on.  A ray is one HitScene-equivalent query
+(primary + bounce + shadow), counted exactly like main.cpp:57, 91.
+
+  value        whole-job Mrays/s, frame left in HBM on rank 0 (device time, max over ranks)
+  e2e          the same through the C-ABI call a user makes (tmpt_render, HOST buffers): the
+               frame's device->host copy is inside the timed region
+  roofline     FP32-issue roofline of the path-tracing kernel (the path is
+               L2-resident tree traversal, neither HBM- nor tensor-bound), with the measured
+               box/triangle tests per ray from an instrumented pass, plus HBM context
+  cpu_baseline the reference's own CPU program (oracle/_ref/TrimeshTracer), all host threads,
+               on a bounded sample of the same workload
+
+`--impl reference` times only the reference's CPU implementation and prints the same line.
+Under torchrun (N > 1) there is one rank per GPU; rows are dealt out in stripes (multigpu.py).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import re
+import statistics
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (scene, width, height, spp)
+    "sponza_1080p_64spp": ("sponza", 1920, 1080, 64),
+    "sponza_640x360_4spp": ("sponza", 640, 360, 4),
+    "teapot_720p_16spp": ("teapot", 1280, 720, 16),
+    "suzanne_640x360_4spp": ("suzanne", 640, 360, 4),
+    "cube_640x360_4spp": ("cube", 640, 360, 4),
+}
+CPU_SAMPLE = {"sponza": (320, 180, 8), "teapot": (320, 180, 8), "suzanne": (640, 360, 4), "cube": (640, 360, 16)}
+REF_BIN = os.path.join(ROOT, "oracle", "_ref", "TrimeshTracer")
+
+
+# ------------------------------------------------------------------------------------------
+# workload files
+# ------------------------------------------------------------------------------------------
+def scene_obj_path(scene: str) -> str:
+    """An .obj file for `scene` in a scratch directory (the CLI and the reference binary take files)."""
+    d = os.path.join(tempfile.gettempdir(), "tmpt_bench_%d" % os.getuid())
+    os.makedirs(d, exist_ok=True)
+    path = os.path.join(d, f"{scene}.obj")
+    if os.path.exists(path):
+        return path
+    if scene == "sponza":
+        real = os.environ.get("TMPT_SPONZA_OBJ")
+        if real and os.path.exists(real):
+            return real
+        from tools.gen_sponza import write_obj
+        write_obj(path)
+        return path
+    z = np.load(os.path.join(ROOT, "tests", "golden", "scenes", f"{scene}.npz"))
+    tris = z["tris"][:-2]  # LoadScene adds the floor itself
+    tmp = path + ".tmp%d" % os.getpid()
+    with open(tmp, "w") as f:
+        f.writelines("v %.9g %.9g %.9g\n" % tuple(float(x) for x in v) for v in tris.reshape(-1, 3))
+        f.writelines("f %d %d %d\n" % (3 * i + 1, 3 * i + 2, 3 * i + 3) for i in range(tris.shape[0]))
+    os.replace(tmp, path)
+    return path
+
+
+def scene_label(scene: str) -> str:
+    if scene == "sponza":
+        return "sponza.obj (real)" if os.environ.get("TMPT_SPONZA_OBJ") else "sponza stand-in (tools/gen_sponza.py, 66452 tris)"
+    return f"{scene}.obj"
+
+
+# ------------------------------------------------------------------------------------------
+# the reference's CPU program on a bounded sample
+# ------------------------------------------------------------------------------------------
+def run_reference_cpu(scene: str, w: int, h: int, spp: int):
+    """-> (Mrays/s, rays, seconds, kind, cores).  oracle/_ref when built, else the C restatement."""
+    cores = os.cpu_count() or 1
+    path = scene_obj_path(scene)
+    if os.path.exists(REF_BIN):
+        with tempfile.TemporaryDirectory() as td:
+            out = subprocess.run([REF_BIN, str(w), str(h), str(spp), path], cwd=td, capture_output=True, text=True, check=True).stdout
+        m = re.search(r"in ([0-9.]+) s\n- ([0-9.]+) K Rays, ([0-9.]+) K Rays/s", out)
+        sec, krays, krate = float(m.group(1)), float(m.group(2)), float(m.group(3))
+        return krate / 1000.0, krays * 1000.0, sec, "reference", cores
+    # fallback: the plain-C restatement (brute force over triangles -> tiny sample)
+    from oracle.pyoracle import RNG_ROW, TRIG_LIBM, Oracle
+    import toymeshpathtracer_b200 as tm
+    tris, mn, mx = tm.load_scene(path)
+    cam = tm.camera_for_scene(path, mn, mx, w, h)
+    orc = Oracle()
+    rows = (0, max(1, h // 16))
+    t0 = time.perf_counter()
+    _, rays = orc.render(tris, cam, w, h, 1, RNG_ROW, TRIG_LIBM, rows=rows)
+    sec = time.perf_counter() - t0
+    return rays / sec / 1e6, rays, sec, "port", orc.threads
+
+
+# ------------------------------------------------------------------------------------------
+# clocks sampling during the timed region
+# ------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap,power.draw"
+
+    def __init__(self, gpu_index: int):
+        self.samples, self.proc, self.thread, self.idx = [], None, None, gpu_index
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.samples.append([x.strip() for x in line.split(",")])
+
+    def __exit__(self, *exc):
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(2)
+            except subprocess.TimeoutExpired:
+                self.proc.kill()
+
+    def summary(self):
+        sm = [float(s[0]) for s in self.samples if s and s[0].replace(".", "").isdigit()]
+        mx = [float(s[1]) for s in self.samples if len(s) > 1 and s[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[k] for s in self.samples if len(s) >= 6 for k in range(4) if s[2 + k].lower().startswith("active")})
+        pw = [float(s[6]) for s in self.samples if len(s) > 6 and re.match(r"^[0-9.]+$", s[6])]
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "power_w_max": max(pw) if pw else None, "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------
+def bench_reference(args, scene, w, h, spp, rank, world):
+    if rank != 0:
+        return 0
+    cw, ch, cspp = CPU_SAMPLE[scene]
+    vals, secs = [], []
+    for i in range(args.warmup + args.steps):
+        mr, rays, sec, kind, cores = run_reference_cpu(scene, cw, ch, cspp)
+        if i >= args.warmup:
+            vals.append(mr)
+            secs.append(sec)
+    value = statistics.mean(vals)
+    sample = f"{scene_label(scene)} {cw}x{ch} {cspp}spp (same scene and camera, reduced pixels/spp), {int(rays)} rays per step"
+    line = {
+        "impl": "reference", "metric": "Mrays/s (primary+bounce+shadow)", "value": value, "unit": "Mrays/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * statistics.mean(secs), "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{scene_label(scene)} {w}x{h} {spp}spp", "cpu_sample": sample},
+        "cpu_baseline": {"value": value, "unit": "Mrays/s", "cores": cores, "kind": kind, "sample": sample},
+        "e2e": {"value": value, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+def bench_b200(args, scene, w, h, spp, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+
+    import toymeshpathtracer_b200 as tm
+    from toymeshpathtracer_b200 import multigpu
+
+    if not torch.cuda.is_available() or tm.device_count() == 0:
+        raise SystemExit("bench.py: no CUDA device -- the product has no CPU path (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+
+    path = scene_obj_path(scene) if rank == 0 else None
+    if world > 1:
+        box = [path]
+        dist.broadcast_object_list(box, src=0)
+        path = box[0]
+    tris, mn, mx = tm.load_scene(path)
+    cam = tm.camera_for_scene(path, mn, mx, w, h)
+    t0 = time.perf_counter()
+    sc = tm.Scene(tris, device=local_rank)
+    build_wall_ms = (time.perf_counter() - t0) * 1e3
+    info = sc.info()
+
+    stream = torch.cuda.Stream(dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+    launches0 = tm.launch_count()
+    step_ms, step_rays = [], []
+    clocks = ClockSampler(local_rank)
+    frame = None
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def one_step():
+        nonlocal frame
+        with torch.cuda.stream(stream):
+            flush.zero_()  # L2 flush between timed iterations (outside the event pair)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            frame, rays = multigpu.render_frame(sc, cam, w, h, spp, rank, world, group=None, device=dev)
+            e1.record(stream)
+        stream.synchronize()
+        return e0.elapsed_time(e1), int(rays.item())
+
+    for _ in range(args.warmup):
+        one_step()
+    barrier()
+    launches1 = tm.launch_count()
+    with clocks:
+        for _ in range(args.steps):
+            ms, rays = one_step()
+            step_ms.append(ms)
+            step_rays.append(rays)
+    barrier()
+    launches2 = tm.launch_count()
+
+    tot_ms = torch.tensor([sum(step_ms)], dtype=torch.float64, device=dev)
+    tot_rays = torch.tensor([sum(step_rays)], dtype=torch.int64, device=dev)
+    if world > 1:
+        dist.all_reduce(tot_ms, op=dist.ReduceOp.MAX)
+        dist.all_reduce(tot_rays, op=dist.ReduceOp.SUM)
+    tot_ms, tot_rays = float(tot_ms.item()), int(tot_rays.item())
+    value = tot_rays / (tot_ms * 1e-3) / 1e6
+
+    # e2e: the user-facing C-ABI call with HOST buffers (single-GPU form; N>1: stripes + gather + D2H of the frame)
+    e2e_ms, e2e_rays = [], []
+    for i in range(1 + min(args.steps, 3)):
+        barrier()
+        t0 = time.perf_counter()
+        if world == 1:
+            img, rays, sec = sc.render(cam, w, h, spp)
+        else:
+            with torch.cuda.stream(stream):
+                fr, rr = multigpu.render_frame(sc, cam, w, h, spp, rank, world, device=dev)
+                img = fr.cpu() if rank == 0 else None
+            stream.synchronize()
+            rays = int(rr.item())
+        barrier()
+        if i > 0:
+            e2e_ms.append((time.perf_counter() - t0) * 1e3)
+            e2e_rays.append(rays)
+    e2e_t = torch.tensor([sum(e2e_ms)], dtype=torch.float64, device=dev)
+    e2e_r = torch.tensor([sum(e2e_rays)], dtype=torch.int64, device=dev)
+    if world > 1:
+        dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(e2e_r, op=dist.ReduceOp.SUM)
+    e2e_value = int(e2e_r.item()) / (float(e2e_t.item()) * 1e-3) / 1e6
+
+    line = None
+    if rank == 0:
+        clk = clocks.summary()
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except OSError:
+            pass
+        sm_count = torch.cuda.get_device_properties(dev).multi_processor_count
+        sm_mhz = clk["sm_mhz"] or peaks.get("sm_max_mhz", 1965.0)
+        fp32_peak = sm_count * 128 * 2 * sm_mhz * 1e6 / 1e12  # TFLOP/s at the clock seen under load
+        stats = sc.traversal_stats(cam, w, h, spp) if hasattr(sc, "traversal_stats") else None
+        flops_per_ray = (stats["box_tests_per_ray"] * 18 + stats["tri_tests_per_ray"] * 46) if stats else None
+        kernel_ms = statistics.mean(step_ms)
+        achieved = (value / world) * 1e6 * flops_per_ray / 1e12 if flops_per_ray else None
+        roofline = {
+            "bound": "fp32_issue (L2-resident traversal; neither hbm nor tensor, SURVEY.md 8(d))",
+            "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s", "frac": (achieved / fp32_peak) if achieved else None,
+            "traffic": None, "per_ray": stats, "flops_per_ray": flops_per_ray,
+            "peak_source": f"{sm_count} SM x 128 lanes x 2 x {sm_mhz:.0f} MHz (median SM clock sampled during the timed region)",
+            "hbm_context": {"algorithmic_bytes_per_frame": int(tris.size * 4 + w * h * 4), "hbm_peak_gbs_measured": peaks.get("hbm_gbs"),
+                            "hbm_frac": (tris.size * 4 + w * h * 4) / (kernel_ms * 1e-3) / 1e9 / peaks["hbm_gbs"] if peaks.get("hbm_gbs") else None},
+            "kernel": "k_render", "kernel_ms": kernel_ms,
+        }
+        cw, ch, cspp = CPU_SAMPLE[scene]
+        try:
+            mr, crays, csec, kind, cores = run_reference_cpu(scene, cw, ch, cspp)
+            cpu = {"value": mr, "unit": "Mrays/s", "cores": cores, "kind": kind,
+                   "sample": f"{scene_label(scene)} {cw}x{ch} {cspp}spp (same scene and camera, reduced pixels/spp), {int(crays)} rays in {csec:.2f} s"}
+        except Exception as e:  # noqa: BLE001
+            cpu = {"value": None, "unit": "Mrays/s", "cores": os.cpu_count(), "kind": "unavailable", "sample": repr(e)}
+        line = {
+            "metric": "Mrays/s (primary+bounce+shadow)", "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": tot_ms / args.steps, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"{scene_label(scene)} {w}x{h} {spp}spp", "rays_per_frame": step_rays[-1] if world == 1 else tot_rays // args.steps,
+                       "parallelism": f"row stripes of {multigpu.DEFAULT_STRIPE_ROWS} over {world} GPU(s), BVH replica per GPU, frame gathered to rank 0",
+                       "l2": "flushed between timed iterations (256 MB write)", "bvh": {k: info[k] for k in ("node_count", "leaf_count", "max_depth", "sah_cost", "build_ms", "device_bytes")},
+                       "scene_build_wall_ms": build_wall_ms},
+            "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": 88, "d2h_bytes_per_step": w * h * 4 + 8,
+                    "ms_per_step": float(e2e_t.item()) / len(e2e_ms)},
+            "gpu_launches": launches2 - launches1,
+            "clocks": clk, "roofline": roofline, "cpu_baseline": cpu,
+        }
+        print(json.dumps(line), flush=True)
+    sc.close()
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="sponza_1080p_64spp", choices=sorted(WORKLOADS))
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world == 1 and args.gpus > 1:
+        # convenience: re-launch under torchrun, one rank per GPU
+        port = 29500 + os.getpid() % 2000
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}", "--master-addr", "127.0.0.1",
+               "--master-port", str(port), os.path.abspath(__file__)] + sys.argv[1:]
+        return subprocess.call(cmd)
+    scene, w, h, spp = WORKLOADS[args.workload]
+    if args.impl == "reference":
+        return bench_reference(args, scene, w, h, spp, rank, world)
+    return bench_b200(args, scene, w, h, spp, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

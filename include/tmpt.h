@@ -1,0 +1,159 @@
+/* include/tmpt.h -- C ABI of the B200-native Trace() hot path ("tmpt" = toy mesh path tracer).
+ *
+ * The reference (pr0g/ToyMeshPathTracer) has no plugin / FFI layer: its seam is the
+ * C++ `Scene` class plus the row functor that main() hands to TBB.  Every entry point
+ * below names the reference interface it stands in for (paths relative to
+ * /root/reference/source).  INTEGRATION.md shows the binding a reference maintainer
+ * would add.  Plain pointers and sizes only; no C++ or torch types cross this line;
+ * nothing throws.  All functions return TMPT_OK (0) or a negative tmpt_status and
+ * leave a message for tmpt_last_error() (thread-local).
+ *
+ * There is NO CPU fallback: without a CUDA device, or if a kernel launch fails, the
+ * compute entry points return TMPT_ERR_CUDA.
+ */
+#ifndef TMPT_H
+#define TMPT_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TMPT_ABI_VERSION 1
+
+typedef enum tmpt_status {
+    TMPT_OK = 0,
+    TMPT_ERR_ARG = -1,   /* bad argument (null pointer, size out of range)            */
+    TMPT_ERR_CUDA = -2,  /* CUDA runtime / launch failure, or no device               */
+    TMPT_ERR_IO = -3,    /* file could not be read / written                          */
+    TMPT_ERR_OOM = -4
+} tmpt_status;
+
+/* Opaque scene: triangle replica + BVH resident on ONE device.
+ * Stands in for `Scene` (scene.h:17-43). */
+typedef struct tmpt_scene tmpt_scene;
+
+/* The reference's Camera fields in declaration order (maths.h:106-111): 22 floats, 88 bytes. */
+typedef struct tmpt_camera {
+    float origin[3];
+    float lowerLeftCorner[3];
+    float horizontal[3];
+    float vertical[3];
+    float u[3], v[3], w[3];
+    float lensRadius;
+} tmpt_camera;
+
+/* Where a caller-supplied buffer lives. */
+typedef enum tmpt_mem { TMPT_HOST = 0, TMPT_DEVICE = 1 } tmpt_mem;
+
+/* tmpt_scene_create flags */
+#define TMPT_BUILD_DEFAULT 0u
+#define TMPT_BUILD_LBVH 1u /* Morton-order Karras hierarchy only (no agglomerative pass) */
+
+/* tmpt_hit_scene modes */
+#define TMPT_HIT_CLOSEST 0 /* nearest hit through the BVH                                  */
+#define TMPT_HIT_ANY 1     /* shadow-ray early out: outID is 1 / -1 (any triangle in range) */
+#define TMPT_HIT_BRUTE 2   /* nearest hit by scanning every triangle on the GPU (upstream's
+                              HitScene); used to cross-check the BVH at sizes the CPU oracle
+                              cannot reach                                                  */
+
+typedef struct tmpt_scene_info {
+    int32_t abi_version;
+    int32_t device;
+    int32_t tri_count;
+    int32_t node_count;      /* wide BVH nodes                                             */
+    int32_t leaf_count;
+    int32_t max_leaf_tris;
+    int32_t max_depth;       /* deepest wide node; the traversal stack is sized from it    */
+    int32_t builder;         /* TMPT_BUILD_* actually used                                 */
+    float bounds_min[3];     /* bounds of all input triangles                              */
+    float bounds_max[3];
+    float sah_cost;          /* SAH cost of the wide tree (Cnode = Ctri = 1, root-relative) */
+    float build_ms;          /* upload + build, device time                                */
+    uint64_t device_bytes;   /* triangles + nodes resident in HBM                          */
+} tmpt_scene_info;
+
+/* ---- scene: Scene::Scene(const Triangle*, int) (scene.h:19, scene.cpp:54-57) followed by
+ * BuildOctree (scene.h:26, scene.cpp:75-83; called from main.cpp:312).  Upstream spells it
+ * InitializeScene(triCount, tris).  tris9 = triCount x 9 floats, AoS v0.xyz v1.xyz v2.xyz,
+ * bit-identical to the reference's Triangle[] (maths.h:56-59).  The input is copied to
+ * `device` and the BVH is built there; the caller keeps ownership of tris9. */
+int tmpt_scene_create(const float* tris9, int triCount, int device, unsigned flags, tmpt_scene** outScene);
+void tmpt_scene_destroy(tmpt_scene* scene); /* Scene::~Scene (scene.cpp:59) */
+int tmpt_scene_get_info(const tmpt_scene* scene, tmpt_scene_info* outInfo);
+
+/* ---- query: int Scene::HitScene(const Ray&, float tMin, float tMax, Hit&) const
+ * (scene.h:36-37, scene.cpp:86-97), batched over nRays.
+ *   rays6      nRays x 6 floats: orig.xyz dir.xyz (Ray, maths.h:31-40; dir assumed unit)
+ *   outID      -1 on a miss; else the ORIGINAL index of the nearest triangle (the contract
+ *              scene.h:35 documents and upstream implements; the fork itself returns 1).
+ *              Tie rule: lowest index among triangles whose t is bit-equal nearest.
+ *              Range rule: tMin <= t <= tMax and t < tMax (maths.cpp:371 + scene.cpp:34, 90).
+ *   outT / outPos3 / outNormal3   Hit fields (maths.h:46-51), written ONLY for hits, may be
+ *              NULL.  pos is the barycentric point (maths.cpp:374), normal the normalised
+ *              e1 x e2 (maths.cpp:375); bit-exact with the reference's arithmetic.
+ *   mem        TMPT_HOST: all pointers are host memory (copies are made inside the call);
+ *              TMPT_DEVICE: all are device pointers on the scene's device.
+ *   stream     a cudaStream_t (NULL = the scene's own stream); with TMPT_DEVICE the call is
+ *              asynchronous on that stream. */
+int tmpt_hit_scene(const tmpt_scene* scene, const float* rays6, int64_t nRays, float tMin, float tMax,
+                   int mode, int mem, int32_t* outID, float* outT, float* outPos3, float* outNormal3,
+                   void* stream);
+
+/* ---- render: the row functor TraceImageBody (main.cpp:180-246) with Trace (:82-119) and
+ * Scatter (:44-73) inside, over image rows [0, height) -- the tbb::parallel_for of
+ * main.cpp:329-331.
+ *   rgba       width*height*4 bytes, row 0 = bottom of the picture (main.cpp:229), A = 255
+ *   rayCount   one count per HitScene-equivalent query (main.cpp:57, 91), 64-bit
+ *   seconds    device time of the render window (main.cpp:319-333): kernel(s) plus, for
+ *              TMPT_HOST, the device-to-host copy of the frame
+ * RNG: one XorShift32 stream (maths.cpp:5-13) per PIXEL, seeded from the pixel index
+ * (DESIGN.md "RNG"); the reference seeds one per row (main.cpp:204). */
+int tmpt_render(const tmpt_scene* scene, const tmpt_camera* camera, int width, int height, int spp,
+                int mem, uint8_t* rgba, uint64_t* rayCount, double* seconds, void* stream);
+
+/* Multi-GPU form: this rank renders only the row stripes it owns -- stripe k (rows
+ * [k*stripeRows, (k+1)*stripeRows)) belongs to rank k % worldSize -- and writes them
+ * packed, stripe after stripe, into outStripes (device memory on the scene's device,
+ * tmpt_stripe_rows(...) * width * 4 bytes).  Asynchronous on `stream`.  rayCountDev is a
+ * device uint64 the kernel adds to.  If peerFrame is non-NULL the pixels are written
+ * straight into that full-size frame (width*height*4, possibly peer / IPC-mapped memory
+ * on another GPU) instead -- the gather fused into the render epilogue. */
+int tmpt_render_stripes(const tmpt_scene* scene, const tmpt_camera* camera, int width, int height, int spp,
+                        int stripeRows, int rank, int worldSize, uint8_t* outStripes, uint8_t* peerFrame,
+                        uint64_t* rayCountDev, void* stream);
+int tmpt_stripe_rows(int height, int stripeRows, int rank, int worldSize); /* rows owned by rank */
+/* Rank 0 after a gather: scatter worldSize packed stripe buffers (each padded to
+ * maxRowsPerRank*width*4 bytes, rank-major) into the final frame.  Device pointers. */
+int tmpt_unpack_stripes(const uint8_t* gathered, int width, int height, int stripeRows, int worldSize,
+                        int device, uint8_t* frame, void* stream);
+
+/* ---- host glue that main() does around the hot path ---- */
+/* LoadScene (main.cpp:122-170): parse the OBJ like external/objparser.cpp, build Triangle[]
+ * plus the two floor triangles, report model bounds.  *outTris9 is malloc'ed; tmpt_free it. */
+int tmpt_load_obj(const char* path, float** outTris9, int* outTriCount, float boundsMin[3], float boundsMax[3]);
+void tmpt_free(void* p);
+/* Camera::Camera (maths.cpp:40-59). */
+void tmpt_camera_make(const float lookFrom[3], const float lookAt[3], const float vup[3], float vfovDeg,
+                      float aspect, float aperture, float focusDist, tmpt_camera* out);
+/* Camera placement of main() (main.cpp:296-307), including the "sponza.obj" special case. */
+void tmpt_camera_for_scene(const char* objPath, const float boundsMin[3], const float boundsMax[3],
+                           int width, int height, tmpt_camera* out);
+/* stbi_write_png + stbi_flip_vertically_on_write (main.cpp:341-342): 8-bit RGBA PNG. */
+int tmpt_write_png(const char* path, int width, int height, const uint8_t* rgba, int flipVertically);
+
+/* The whole CLI (main.cpp:248-345): `<width> <height> <spp> <datafile>` -> output.png and the
+ * three report lines; returns the process exit code. */
+int tmpt_main(int argc, const char** argv);
+
+const char* tmpt_last_error(void);
+int tmpt_device_count(void);
+/* kernels launched by this library since load (bench.py's gpu_launches evidence) */
+uint64_t tmpt_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TMPT_H */

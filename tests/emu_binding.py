@@ -1,0 +1,90 @@
+"""ctypes binding of tests/emu/libemu.so -- TEST INFRASTRUCTURE (see tests/emu/emu.cpp).
+
+The product's __host__ __device__ headers compiled for the host, so the CPU suite can check
+the BVH build, traversal and integrator logic without a GPU.  Never used by the product."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+SRC = os.path.join(HERE, "emu", "emu.cpp")
+SO = os.path.join(HERE, "emu", "libemu.so")
+CSRC = os.path.join(os.path.dirname(HERE), "toymeshpathtracer_b200", "csrc")
+CUDA_INC = os.environ.get("CUDA_INC", "/usr/local/cuda/include")
+
+
+def _stale():
+    if not os.path.exists(SO):
+        return True
+    t = os.path.getmtime(SO)
+    deps = [SRC] + [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".cuh")]
+    return any(os.path.getmtime(d) > t for d in deps)
+
+
+def build():
+    if _stale():
+        subprocess.run(["g++", "-std=c++17", "-O2", "-ffp-contract=off", "-fno-fast-math", "-fopenmp", "-fPIC", "-shared",
+                        "-I" + CUDA_INC, "-o", SO, SRC], check=True)
+    return SO
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+class Emu:
+    def __init__(self):
+        self.L = C.CDLL(build())
+        self.L.emu_scene_create.restype = C.c_void_p
+        self.L.emu_pixel_seed.restype = C.c_uint32
+
+    def scene(self, tris):
+        return EmuScene(self.L, tris)
+
+
+class EmuScene:
+    def __init__(self, L, tris):
+        self.L = L
+        self.tris = np.ascontiguousarray(tris, np.float32).reshape(-1, 9)
+        self.h = C.c_void_p(L.emu_scene_create(_p(self.tris), self.tris.shape[0]))
+
+    def close(self):
+        if self.h:
+            self.L.emu_scene_destroy(self.h)
+            self.h = None
+
+    __del__ = close
+
+    def info(self):
+        out = np.zeros(5, np.uint32)
+        self.L.emu_scene_info(self.h, _p(out))
+        return dict(zip(("nodes", "slots", "leaves", "max_depth", "status"), out.tolist()))
+
+    def nodes(self):
+        n = self.L.emu_nodes(self.h, None)
+        out = np.zeros((n, 8, 4), np.float32)
+        self.L.emu_nodes(self.h, _p(out))
+        return out
+
+    def slots(self):
+        out = np.zeros((self.tris.shape[0], 3, 4), np.float32)
+        self.L.emu_slots(self.h, _p(out))
+        return out
+
+    def hit(self, rays, tmin=0.001, tmax=1.0e7, mode=0):
+        rays = np.ascontiguousarray(rays, np.float32).reshape(-1, 6)
+        n = rays.shape[0]
+        ids = np.full(n, -1, np.int32)
+        t = np.zeros(n, np.float32); pos = np.zeros((n, 3), np.float32); nrm = np.zeros((n, 3), np.float32)
+        self.L.emu_hit_scene(self.h, _p(rays), C.c_long(n), C.c_float(tmin), C.c_float(tmax), mode, _p(ids), _p(t), _p(pos), _p(nrm))
+        return ids, t, pos, nrm
+
+    def render(self, cam22, w, h, spp, rows=None):
+        cam22 = np.ascontiguousarray(cam22, np.float32)
+        img = np.zeros((h, w, 4), np.uint8)
+        rc = C.c_longlong(0)
+        r0, r1 = rows if rows else (0, h)
+        self.L.emu_render(self.h, _p(cam22), w, h, spp, r0, r1, _p(img), None, C.byref(rc))
+        return img, rc.value

@@ -1,0 +1,222 @@
+"""Parity tests proper: the CUDA path, called through the C ABI (libtmpt.so), against the
+golden vectors the reference produced and against the CPU oracle on the same inputs.
+
+Bars (BASELINE.json north_star):
+  * hit flag, ORIGINAL triangle id, t bits and the Hit payload bits: bit-exact;
+  * a frame rendered with the GPU path's RNG layout (one XorShift32 stream per pixel, trig
+    spec): bit-exact against the oracle run in the same mode;
+  * against the reference's OWN image (one stream per row, libm trig) the comparison is
+    statistical at high spp: per-pixel mean absolute error and PSNR, tolerances below.
+"""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import toymeshpathtracer_b200 as tm
+from conftest import GOLD, ROOT, bits, load_rays, load_scene
+
+pytestmark = pytest.mark.gpu
+SCENES = ["triangle", "cube", "suzanne", "teapot"]
+
+
+@pytest.fixture(scope="module")
+def scenes():
+    cache = {}
+
+    def get(name):
+        if name not in cache:
+            cache[name] = tm.Scene(load_scene(name)["tris"])
+        return cache[name]
+    yield get
+    for s in cache.values():
+        s.close()
+
+
+def test_native_library_is_what_runs():
+    assert tm.device_count() >= 1
+    before = tm.launch_count()
+    with tm.Scene(load_scene("cube")["tris"]) as s:
+        s.HitScene(load_rays("cube")["rays"][:100])
+    assert tm.launch_count() > before
+
+
+@pytest.mark.parametrize("name", SCENES)
+def test_hit_ids_t_and_payload_bit_exact(scenes, name):
+    """Config 2 of BASELINE.json (suzanne) and the other reference scenes: every ray a reference render shoots."""
+    g = load_rays(name)
+    s = scenes(name)
+    ids, t, pos, nrm = s.HitScene(g["rays"])
+    hit = g["id"] >= 0
+    assert ((g["flag"] == 1) == (ids >= 0)).all()
+    assert (ids == g["id"]).all()
+    assert (bits(t)[hit] == bits(g["t"])[hit]).all()
+    assert (bits(pos)[hit] == bits(g["pos"])[hit]).all()
+    assert (bits(nrm)[hit] == bits(g["normal"])[hit]).all()
+    # outputs of misses stay untouched (scene.cpp:86-97 writes outHit only on a hit)
+    assert (t[~hit] == 0).all() and (pos[~hit] == 0).all()
+    # any-hit (shadow semantics): same boolean
+    aid, *_ = s.HitScene(g["rays"], mode=tm.HIT_ANY)
+    assert ((aid == 1) == hit).all() and ((aid == -1) == ~hit).all()
+    # brute force on the GPU (upstream's scan) agrees too
+    bid, bt, *_ = s.HitScene(g["rays"], mode=tm.HIT_BRUTE)
+    assert (bid == g["id"]).all() and (bits(bt)[hit] == bits(g["t"])[hit]).all()
+
+
+def _random_rays(sc, n, seed, axis_parallel=True):
+    rng = np.random.default_rng(seed)
+    ext = (sc["bounds_max"] - sc["bounds_min"]) * 0.75
+    o = rng.uniform(sc["bounds_min"] - ext, sc["bounds_max"] + ext, (n, 3)).astype(np.float32)
+    d = rng.normal(size=(n, 3))
+    if axis_parallel:
+        d[: n // 16, 0] = 0.0
+        d[n // 16: n // 8, 1] = 0.0
+        d[n // 8: n // 8 + n // 16, 2] = 0.0
+    d = (d / np.linalg.norm(d, axis=1, keepdims=True)).astype(np.float32)
+    return np.concatenate([o, d], 1)
+
+
+@pytest.mark.parametrize("name,n", [("cube", 200000), ("suzanne", 200000), ("teapot", 60000)])
+def test_random_rays_vs_oracle(scenes, oracle, name, n):
+    sc = load_scene(name)
+    rays = _random_rays(sc, n, 5)
+    ids, t, pos, nrm = scenes(name).HitScene(rays)
+    oid, ot, opos, onrm = oracle.hit_brute(sc["tris"], rays)
+    hit = oid >= 0
+    assert (ids == oid).all()
+    assert (bits(t)[hit] == bits(ot)[hit]).all() and (bits(pos)[hit] == bits(opos)[hit]).all() and (bits(nrm)[hit] == bits(onrm)[hit]).all()
+
+
+@pytest.mark.parametrize("tmin,tmax", [(0.001, 1.0e7), (0.5, 3.0), (0.0, 1.0), (2.0, 2.0)])
+def test_t_range_rules(scenes, oracle, tmin, tmax):
+    """tMin <= t <= tMax and t < tMax (maths.cpp:371, scene.cpp:34, 90)."""
+    sc = load_scene("suzanne")
+    rays = _random_rays(sc, 50000, 9)
+    ids, t, *_ = scenes("suzanne").HitScene(rays, tMin=tmin, tMax=tmax)
+    oid, ot, *_ = oracle.hit_brute(sc["tris"], rays, tmin=tmin, tmax=tmax)
+    assert (ids == oid).all() and (bits(t)[oid >= 0] == bits(ot)[oid >= 0]).all()
+    assert ((t[ids >= 0] >= tmin) & (t[ids >= 0] < tmax)).all()
+
+
+def test_tree_vs_brute_force_at_scale(scenes):
+    """Size-independent property: the BVH answer equals the all-triangle scan on the GPU, at a
+    ray count the CPU oracle cannot reach (conservativeness of the padded boxes)."""
+    sc = load_scene("teapot")
+    s = scenes("teapot")
+    for seed in (1, 2):
+        rays = _random_rays(sc, 2_000_000, seed)
+        a = s.HitScene(rays, payload=True)
+        b = s.HitScene(rays, mode=tm.HIT_BRUTE, payload=True)
+        assert (a[0] == b[0]).all() and (bits(a[1]) == bits(b[1])).all()
+        assert (bits(a[2]) == bits(b[2])).all() and (bits(a[3]) == bits(b[3])).all()
+
+
+def test_edge_cases():
+    ray = np.array([[0.2, 0.2, 1, 0, 0, -1]], np.float32)
+    with tm.Scene(np.zeros((0, 9), np.float32)) as s:  # empty scene: everything misses
+        ids, *_ = s.HitScene(ray)
+        assert ids[0] == -1
+        assert s.HitScene(np.zeros((0, 6), np.float32))[0].shape == (0,)
+    tri = np.array([[0, 0, 0, 1, 0, 0, 0, 1, 0]], np.float32)
+    with tm.Scene(tri) as s:
+        ids, t, pos, nrm = s.HitScene(ray)
+        assert ids[0] == 0 and t[0] == 1.0 and nrm[0].tolist() == [0, 0, 1]
+    with tm.Scene(np.repeat(tri, 100, 0)) as s:  # coincident triangles: lowest index wins the tie
+        assert s.HitScene(ray)[0][0] == 0
+        assert s.info()["tri_count"] == 100
+    degenerate = np.array([[0, 0, 0, 0, 0, 0, 0, 0, 0], [0, 0, 0, 1, 0, 0, 2, 0, 0]], np.float32)  # zero-area
+    with tm.Scene(np.concatenate([degenerate, tri])) as s:
+        assert s.HitScene(ray)[0][0] == 2
+
+
+@pytest.mark.parametrize("name,w,h,spp", [("cube", 160, 90, 4), ("suzanne", 128, 72, 3), ("teapot", 64, 36, 2), ("triangle", 33, 17, 5)])
+def test_frame_bit_exact_vs_oracle_pixel_mode(scenes, oracle, name, w, h, spp):
+    sc = load_scene(name)
+    cam = tm.camera_for_scene(f"{name}.obj", sc["bounds_min"], sc["bounds_max"], w, h)
+    oimg, orays = oracle.render(sc["tris"], cam, w, h, spp)  # per-pixel RNG streams + trig spec
+    img, rays, sec = scenes(name).render(cam, w, h, spp)
+    assert rays == orays
+    assert (img == oimg).all()
+    assert sec > 0
+
+
+def _image_metrics(a, b):
+    a, b = a[..., :3].astype(np.float64), b[..., :3].astype(np.float64)
+    # outlier-robust: the reference poisons a few pixels per frame with NaN -> black
+    bad = (a.sum(-1) == 0) | (b.sum(-1) == 0)
+    d = (a - b)[~bad]
+    mae = np.abs(d).mean()
+    psnr = 10 * np.log10(255.0 ** 2 / (d ** 2).mean())
+    return mae, psnr, int(bad.sum()), np.abs(a[~bad].mean(0) - b[~bad].mean(0)).max()
+
+
+@pytest.mark.parametrize("name,spp,mae_tol,psnr_tol", [("cube", 1024, 0.45, 44.0), ("suzanne", 256, 0.9, 38.0)])
+def test_converged_image_vs_reference_render(scenes, name, spp, mae_tol, psnr_tol):
+    """Statistical gate against the REFERENCE's own render (row RNG, libm trig): two independent
+    reference renders differ by MAE 0.21 / 0.41 at 1024 / 256 spp; the bars are ~2x that."""
+    from PIL import Image
+    w, h = 320, 180
+    ref = np.array(Image.open(os.path.join(GOLD, "images", f"{name}_{w}x{h}_{spp}spp.png")).convert("RGB"))
+    sc = load_scene(name)
+    cam = tm.camera_for_scene(f"{name}.obj", sc["bounds_min"], sc["bounds_max"], w, h)
+    img, rays, _ = scenes(name).render(cam, w, h, spp)
+    mae, psnr, bad, dmean = _image_metrics(img[::-1], ref)
+    print(f"{name}: MAE {mae:.3f} PSNR {psnr:.2f} dB, {bad} masked pixels, max channel-mean diff {dmean:.3f}")
+    assert mae <= mae_tol and psnr >= psnr_tol and bad <= 16 and dmean <= 0.25
+
+
+def test_stripes_compose_to_the_single_gpu_frame(scenes):
+    """Multi-GPU partition, emulated on one GPU: each rank's stripes + unpack == the whole-frame render."""
+    import torch
+    sc = load_scene("suzanne")
+    w, h, spp, stripe, world = 100, 50, 2, 4, 3
+    cam = tm.camera_for_scene("suzanne.obj", sc["bounds_min"], sc["bounds_max"], w, h)
+    s = scenes("suzanne")
+    full, full_rays, _ = s.render(cam, w, h, spp)
+    from toymeshpathtracer_b200 import multigpu
+    rows, max_rows = multigpu.stripe_plan(h, stripe, world)
+    gathered = torch.zeros((world, max_rows, w, 4), dtype=torch.uint8, device="cuda")
+    rays = torch.zeros(world, dtype=torch.int64, device="cuda")
+    st = torch.cuda.Stream()
+    with torch.cuda.stream(st):
+        for r in range(world):
+            s.render_stripes(cam, w, h, spp, stripe, r, world, gathered[r].data_ptr(), rays[r:].data_ptr(), stream=st.cuda_stream)
+        frame = multigpu.gather_frame(gathered[0], w, h, stripe, 0, 1) if world == 1 else None
+        frame = torch.empty((h, w, 4), dtype=torch.uint8, device="cuda")
+        tm._check(tm.lib().tmpt_unpack_stripes(gathered.data_ptr(), w, h, stripe, world, 0, frame.data_ptr(), st.cuda_stream))
+    st.synchronize()
+    assert (frame.cpu().numpy() == full).all()
+    assert int(rays.sum()) == full_rays
+    # peer-frame form: every rank writes straight into one full frame
+    frame2 = torch.zeros((h, w, 4), dtype=torch.uint8, device="cuda")
+    with torch.cuda.stream(st):
+        for r in range(world):
+            s.render_stripes(cam, w, h, spp, stripe, r, world, 0, rays[r:].data_ptr(), peer_frame_ptr=frame2.data_ptr(), stream=st.cuda_stream)
+    st.synchronize()
+    assert (frame2.cpu().numpy() == full).all()
+
+
+def test_cli_end_to_end(tmp_path):
+    """The drop-in command line: `<width> <height> <spp> <datafile>` -> output.png + the three report lines."""
+    from PIL import Image
+    sc = load_scene("cube")
+    obj = tmp_path / "cube.obj"
+    tris = sc["tris"][:-2]  # the loader adds the floor itself
+    with open(obj, "w") as f:
+        for v in tris.reshape(-1, 3):
+            f.write("v %.9g %.9g %.9g\n" % tuple(float(x) for x in v))
+        for i in range(tris.shape[0]):
+            f.write("f %d %d %d\n" % (3 * i + 1, 3 * i + 2, 3 * i + 3))
+    r = subprocess.run([tm.CLI_PATH, "160", "90", "4", str(obj)], cwd=tmp_path, capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    lines = r.stdout.strip().split("\n")
+    assert lines[0].startswith(f"Initialized scene '{obj}' (14 tris) in ")
+    assert lines[1].startswith("Rendered scene at 160x90,4spp in ")
+    assert lines[2].startswith("- ") and lines[2].endswith(" K Rays/s")
+    img = np.array(Image.open(tmp_path / "output.png"))
+    with tm.Scene(sc["tris"]) as s:
+        cam = tm.camera_for_scene(str(obj), sc["bounds_min"], sc["bounds_max"], 160, 90)
+        want, rays, _ = s.render(cam, 160, 90, 4)
+    assert img.shape == (90, 160, 4) and (img == want[::-1]).all()
+    assert abs(float(lines[2].split()[1]) - rays / 1000.0) < 0.06

@@ -1,0 +1,187 @@
+"""Host glue behind the C ABI (csrc/host.cpp) and the library surface -- CPU only.
+No compute call is made here (there is no GPU); the compute entry points must fail loudly."""
+import ctypes as C
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+import toymeshpathtracer_b200 as tm
+from conftest import ROOT, bits, load_scene
+from oracle.pyoracle import REF_ROOT
+
+
+def test_library_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "tmpt.h")).read()
+    declared = set(re.findall(r"\b(tmpt_[a-z_0-9]+)\s*\(", hdr))
+    assert declared == set(tm.ABI_SYMBOLS)
+    L = tm.lib()
+    for name in declared:
+        assert getattr(L, name) is not None
+    out = subprocess.run(["nm", "-D", "--defined-only", tm.LIB_PATH], capture_output=True, text=True, check=True).stdout
+    exported = set(re.findall(r" T (tmpt_[a-z_0-9]+)", out))
+    assert declared <= exported
+
+
+def test_oracle_is_not_linked_into_the_product():
+    out = subprocess.run(["ldd", tm.LIB_PATH], capture_output=True, text=True).stdout
+    assert "oracle" not in out and "libemu" not in out and "libref" not in out
+    syms = subprocess.run(["nm", "-D", tm.LIB_PATH], capture_output=True, text=True).stdout
+    assert "orc_" not in syms and "emu_" not in syms
+
+
+@pytest.mark.skipif(tm.device_count() > 0, reason="a GPU is present")
+def test_compute_fails_loudly_without_a_gpu():
+    tri = np.zeros((1, 9), np.float32)
+    with pytest.raises(tm.TmptError) as e:
+        tm.Scene(tri)
+    assert e.value.status == tm.TMPT_ERR_CUDA and "no CPU path" in str(e.value)
+
+
+OBJ_TEXT = """# comment
+v 0 0 0
+v 1.5 0 0\r
+v 1 1e0 -2.5E-1
+v   0\t1 0.125
+vt 0 0
+vn 0 0 1
+f 1/1/1 2/1/1 3/1/1 4/1/1
+f -4//1 -3//1 -1//1
+f 1 2 3 4 1
+usemtl x
+f 2 3
+"""
+
+
+def test_obj_loader_grammar(tmp_path):
+    p = tmp_path / "t.obj"
+    p.write_bytes(OBJ_TEXT.encode())
+    tris, mn, mx = tm.load_scene(str(p))
+    v = np.array([[0, 0, 0], [1.5, 0, 0], [1, 1, -0.25], [0, 1, 0.125]], np.float32)
+    fan = lambda idx: [[idx[0], idx[k], idx[k + 1]] for k in range(1, len(idx) - 1)]
+    faces = fan([0, 1, 2, 3]) + fan([0, 1, 3]) + fan([0, 1, 2, 3, 0])
+    want = v[np.array(faces)].reshape(-1, 9)
+    assert tris.shape[0] == want.shape[0] + 2
+    assert (bits(tris[:-2]) == bits(want)).all()
+    assert mn.tolist() == [0, 0, -0.25] and mx.tolist() == [1.5, 1, 0.125]
+    # the two floor triangles (main.cpp:153-162)
+    ex, ez = np.float32(1.5) * np.float32(0.7), np.float32(0.375) * np.float32(0.7)
+    x0, x1, z0, z1 = np.float32(0) - ex, np.float32(1.5) + ex, np.float32(-0.25) - ez, np.float32(0.125) + ez
+    floor = np.array([[x0, 0, z0, x0, 0, z1, x1, 0, z0], [x0, 0, z1, x1, 0, z1, x1, 0, z0]], np.float32)
+    assert (bits(tris[-2:]) == bits(floor)).all()
+
+
+def test_obj_loader_errors(tmp_path):
+    with pytest.raises(tm.TmptError) as e:
+        tm.load_scene(str(tmp_path / "missing.obj"))
+    assert e.value.status == tm.TMPT_ERR_IO
+    p = tmp_path / "bad.obj"
+    p.write_text("v 0 0 0\nf 1 2 3\n")
+    with pytest.raises(tm.TmptError):
+        tm.load_scene(str(p))
+    p = tmp_path / "empty.obj"
+    p.write_text("# nothing\n")
+    tris, mn, mx = tm.load_scene(str(p))  # like the reference: just the two floor triangles
+    assert tris.shape == (2, 9)
+
+
+def test_float_parser_matches_reference_semantics(tmp_path):
+    # objparser.cpp:62-131: double mantissa, ONE scaling by an exact power of ten, then float
+    cases = ["0.1", "-0.30000001", "123456789.125", "1e-7", "3.4028234e38", "1.17549435e-38", "+.5", "7.", "0.000000000000000000000001",
+             "12345678901234567890", "-1.5e+3", "2E2"]
+    p = tmp_path / "f.obj"
+    p.write_text("".join(f"v {c} 0 0\n" for c in cases) + "f 1 2 3\n")
+    tris, *_ = tm.load_scene(str(p))
+
+    def ref_parse(s):
+        m = re.match(r"([+-]?)(\d*)(?:\.(\d*))?(?:[eE]([+-]?\d+))?$", s)
+        sign = -1.0 if m.group(1) == "-" else 1.0
+        digits = (m.group(2) or "") + (m.group(3) or "")
+        mant = 0.0
+        for ch in digits:
+            mant = mant * 10.0 + float(int(ch))
+        power = -len(m.group(3) or "") + int(m.group(4) or 0)
+        if -22 <= power <= 0:
+            return np.float32(sign * mant / 10.0 ** (-power))
+        if 0 < power <= 22:
+            return np.float32(sign * mant * 10.0 ** power)
+        return np.float32(sign * mant * np.power(10.0, power))
+
+    got = np.array([tris[0, 0], tris[0, 3], tris[0, 6]], np.float32)
+    want = np.array([ref_parse(c) for c in cases[:3]], np.float32)
+    assert (bits(got) == bits(want)).all()
+    # all of them through single-vertex faces
+    p.write_text("".join(f"v {c} 0 0\n" for c in cases) + "".join(f"f {i+1} {i+1} {i+1}\n" for i in range(len(cases))))
+    tris, *_ = tm.load_scene(str(p))
+    with np.errstate(over="ignore"):
+        want = np.array([ref_parse(c) for c in cases], np.float32)
+    assert (bits(tris[:len(cases), 0]) == bits(want)).all()
+
+
+@pytest.mark.ref
+@pytest.mark.parametrize("name", ["triangle", "cube", "suzanne", "teapot"])
+def test_obj_loader_equals_reference_loadscene(name):
+    path = os.path.join(REF_ROOT, "data", f"{name}.obj")
+    if not os.path.exists(path):
+        pytest.skip("reference data absent")
+    sc = load_scene(name)  # golden: produced by the reference's own LoadScene
+    tris, mn, mx = tm.load_scene(path)
+    assert tris.shape == sc["tris"].shape and (bits(tris) == bits(sc["tris"])).all()
+    assert (bits(mn) == bits(sc["bounds_min"])).all() and (bits(mx) == bits(sc["bounds_max"])).all()
+    cam = tm.camera_for_scene(path, mn, mx, 640, 360)
+    assert (bits(cam) == bits(sc["camera_640x360"])).all()
+
+
+def test_camera_matches_golden(kat):
+    g = kat["camera_make"]
+    cam = tm.camera_make(*g["args"])
+    assert bits(cam).tolist() == g["bits"]
+    for name in ["triangle", "cube", "suzanne", "teapot"]:
+        sc = load_scene(name)
+        cam = tm.camera_for_scene(f"/x/{name}.obj", sc["bounds_min"], sc["bounds_max"], 640, 360)
+        assert (bits(cam) == bits(sc["camera_640x360"])).all()
+
+
+def test_sponza_camera_special_case(oracle):
+    mn, mx = np.array([-18, -0.2, -8], np.float32), np.array([18, 15, 8], np.float32)
+    cam = tm.camera_for_scene("/tmp/gen/sponza.obj", mn, mx, 1920, 1080)
+    assert cam[:3].tolist() == [np.float32(-5.96), np.float32(4.08), np.float32(-1.22)]
+    assert (bits(cam) == bits(oracle.camera_for_scene(mn, mx, 1920, 1080, is_sponza=True))).all()
+    cam2 = tm.camera_for_scene("/tmp/gen/other.obj", mn, mx, 1920, 1080)
+    assert (bits(cam2) == bits(oracle.camera_for_scene(mn, mx, 1920, 1080))).all()
+
+
+def test_png_writer_round_trip(tmp_path):
+    from PIL import Image
+    rng = np.random.default_rng(3)
+    for (w, h) in [(1, 1), (7, 5), (640, 360), (300, 70)]:  # the last two span >1 stored deflate block
+        img = rng.integers(0, 256, (h, w, 4), dtype=np.uint8)
+        p = str(tmp_path / f"o_{w}x{h}.png")
+        tm.write_png(p, img, flip_vertically=True)
+        back = np.array(Image.open(p))
+        assert back.shape == (h, w, 4) and (back == img[::-1]).all()
+        tm.write_png(p, img, flip_vertically=False)
+        assert (np.array(Image.open(p)) == img).all()
+
+
+def test_stripe_rows_partition():
+    for (h, stripe, world) in [(360, 8, 1), (360, 8, 2), (1080, 8, 8), (13, 4, 3), (5, 8, 4), (1080, 4, 8)]:
+        rows = [tm.stripe_rows(h, stripe, r, world) for r in range(world)]
+        assert sum(rows) == h
+        want = [0] * world
+        for y in range(h):
+            want[(y // stripe) % world] += 1
+        assert rows == want
+
+
+def test_cli_argument_errors():
+    def run(*args):
+        r = subprocess.run([tm.CLI_PATH, *args], capture_output=True, text=True)
+        return r.returncode, r.stdout
+    assert run() == (1, "Usage: TrimeshTracer.exe [width] [height] [samplesPerPixel] [objFile]\n")
+    assert run("0", "10", "1", "x.obj") == (1, "ERROR: invalid width argument '0'\n")
+    assert run("10", "10001", "1", "x.obj") == (1, "ERROR: invalid height argument '10001'\n")
+    assert run("10", "10", "1025", "x.obj") == (1, "ERROR: invalid samplesPerPixel argument '1025'\n")
+    assert run("10", "10", "1", "/nonexistent/x.obj") == (1, "ERROR: failed to load .obj file\n")

@@ -1,0 +1,326 @@
+// build_logic.cuh -- per-element logic of the on-device BVH build (K1).
+//
+// Replaces Scene::BuildOctree / OctreeNode::Subdivide / InternalDivide (scene.cpp:75-83,
+// 99-160) and the SAT triangle-box test they rely on (maths.cpp:199-298): the octree is NOT
+// rebuilt.  Pipeline (kernels.cu drives it, one launch per stage):
+//   1 prim_bounds   triangle AABBs + scene bounds (atomic min/max on order-preserving ints)
+//   2 morton_keys   63-bit Morton code of the box centre; padded triangle boxes
+//   3 radix sort    (key, prim) pairs, 8 passes of 8 bits            [kernels.cu]
+//   4 karras_node   binary radix tree over the sorted keys (Karras 2012), index tie-break
+//   5 refit_up      bottom-up boxes, subtree counts, SAH cost and the leaf decision
+//   6 collapse_node top-down: binary tree -> 4-wide nodes + leaf triangle slots
+// Every function here is __host__ __device__ so tests/emu can run the same logic serially
+// on the CPU; the library only runs it inside kernels.
+#pragma once
+#include "bvh.cuh"
+
+namespace bld {
+
+struct Box {
+    float lox, loy, loz, hix, hiy, hiz;
+};
+TMPT_HD Box box_union(const Box& a, const Box& b) {
+    return Box{fminf(a.lox, b.lox), fminf(a.loy, b.loy), fminf(a.loz, b.loz),
+               fmaxf(a.hix, b.hix), fmaxf(a.hiy, b.hiy), fmaxf(a.hiz, b.hiz)};
+}
+TMPT_HD float box_half_area(const Box& b) {
+    float dx = b.hix - b.lox, dy = b.hiy - b.loy, dz = b.hiz - b.loz;
+    return dx * dy + dy * dz + dz * dx;
+}
+
+// Order-preserving float <-> uint map for atomicMin / atomicMax on floats.
+TMPT_HD uint32_t float_to_ordered(float f) {
+    uint32_t u = ex::f2u(f);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+TMPT_HD float ordered_to_float(uint32_t u) {
+    return ex::u2f((u & 0x80000000u) ? (u & 0x7FFFFFFFu) : ~u);
+}
+
+// How far a triangle's box is grown before it enters the tree (DESIGN.md "Conservative
+// boxes").  Two terms: (a) the float slab test and Moller-Trumbore's t each carry a few
+// ulps of the largest coordinate in play -> 64 ulps of the scene's largest |coordinate|;
+// (b) MT accepts points whose computed barycentrics pass although the exact ones are
+// outside by a relative error that grows for grazing rays -> 1e-3 of the triangle's own
+// box diagonal.  Growing boxes can only add work, never change a result.
+TMPT_HD float pad_for(float triDiag, float sceneMaxAbs) {
+    return 1.0e-3f * triDiag + 64.0f * 1.1920929e-7f * sceneMaxAbs;
+}
+
+TMPT_HD Box tri_box(const float* t9) {
+    Box b;
+    b.lox = fminf(fminf(t9[0], t9[3]), t9[6]); b.hix = fmaxf(fmaxf(t9[0], t9[3]), t9[6]);
+    b.loy = fminf(fminf(t9[1], t9[4]), t9[7]); b.hiy = fmaxf(fmaxf(t9[1], t9[4]), t9[7]);
+    b.loz = fminf(fminf(t9[2], t9[5]), t9[8]); b.hiz = fmaxf(fmaxf(t9[2], t9[5]), t9[8]);
+    return b;
+}
+
+TMPT_HD uint64_t expand_bits21(uint64_t v) {  // 21 bits -> every third bit of 63
+    v &= 0x1FFFFFull;
+    v = (v | (v << 32)) & 0x1F00000000FFFFull;
+    v = (v | (v << 16)) & 0x1F0000FF0000FFull;
+    v = (v | (v << 8)) & 0x100F00F00F00F00Full;
+    v = (v | (v << 4)) & 0x10C30C30C30C30C3ull;
+    v = (v | (v << 2)) & 0x1249249249249249ull;
+    return v;
+}
+TMPT_HD uint64_t morton63(float cx, float cy, float cz, const Box& scene) {
+    float ex_ = scene.hix - scene.lox, ey = scene.hiy - scene.loy, ez = scene.hiz - scene.loz;
+    float nx = ex_ > 0.0f ? (cx - scene.lox) / ex_ : 0.0f;
+    float ny = ey > 0.0f ? (cy - scene.loy) / ey : 0.0f;
+    float nz = ez > 0.0f ? (cz - scene.loz) / ez : 0.0f;
+    const float S = 2097151.0f;  // 2^21 - 1
+    uint64_t ix = (uint64_t)fminf(fmaxf(nx * S, 0.0f), S);
+    uint64_t iy = (uint64_t)fminf(fmaxf(ny * S, 0.0f), S);
+    uint64_t iz = (uint64_t)fminf(fmaxf(nz * S, 0.0f), S);
+    return (expand_bits21(ix) << 2) | (expand_bits21(iy) << 1) | expand_bits21(iz);
+}
+
+TMPT_HD int clz64(uint64_t v) {
+#ifdef __CUDA_ARCH__
+    return __clzll((long long)v);
+#else
+    return v ? __builtin_clzll(v) : 64;
+#endif
+}
+TMPT_HD int clz32(uint32_t v) {
+#ifdef __CUDA_ARCH__
+    return __clz((int)v);
+#else
+    return v ? __builtin_clz(v) : 32;
+#endif
+}
+
+// Binary tree over n sorted primitives: inner nodes [0, n-1), leaves [n-1, 2n-1) where leaf
+// n-1+j is sorted position j.
+struct BinTree {
+    int n;
+    const uint64_t* keys;  // sorted
+    int* left;             // [n-1]
+    int* right;            // [n-1]
+    int* parent;           // [2n-1]
+    float4* lo;            // [2n-1] xyz = box min, w = SAH cost of the subtree
+    float4* hi;            // [2n-1] xyz = box max, w = bit-cast int: triangles in the subtree,
+                           //         NEGATIVE when the subtree is to become one leaf
+    uint32_t* visits;      // [n-1] bottom-up arrival counters
+};
+
+// Karras 2012, "Maximizing parallelism in the construction of BVHs, octrees and k-d trees":
+// delta = length of the common prefix of two keys; equal keys fall back to the index bits.
+TMPT_HD int karras_delta(const uint64_t* keys, int n, int i, int j) {
+    if (j < 0 || j >= n) return -1;
+    uint64_t a = keys[i], b = keys[j];
+    if (a == b) return 64 + clz32((uint32_t)i ^ (uint32_t)j);
+    return clz64(a ^ b);
+}
+
+TMPT_HD void karras_node(const BinTree& t, int i) {
+    const int n = t.n;
+    const int d = (karras_delta(t.keys, n, i, i + 1) - karras_delta(t.keys, n, i, i - 1)) >= 0 ? 1 : -1;
+    const int dmin = karras_delta(t.keys, n, i, i - d);
+    int lmax = 2;
+    while (karras_delta(t.keys, n, i, i + lmax * d) > dmin) lmax *= 2;
+    int l = 0;
+    for (int s = lmax / 2; s >= 1; s /= 2)
+        if (karras_delta(t.keys, n, i, i + (l + s) * d) > dmin) l += s;
+    const int j = i + l * d;
+    const int dnode = karras_delta(t.keys, n, i, j);
+    int s = 0;
+    for (int step = (l + 1) / 2;; step = (step + 1) / 2) {
+        if (karras_delta(t.keys, n, i, i + (s + step) * d) > dnode) s += step;
+        if (step == 1) break;
+    }
+    const int gamma = i + s * d + (d < 0 ? -1 : 0);
+    const int lo = i < j ? i : j, hi = i < j ? j : i;
+    const int L = (lo == gamma) ? (n - 1 + gamma) : gamma;
+    const int R = (hi == gamma + 1) ? (n - 1 + gamma + 1) : (gamma + 1);
+    t.left[i] = L;
+    t.right[i] = R;
+    t.parent[L] = i;
+    t.parent[R] = i;
+    if (i == 0) t.parent[0] = -1;
+}
+
+// SAH constants (relative): one 4-wide node visit vs one exact triangle test.  The binary
+// tree charges C_INNER per binary node; a 4-wide node absorbs up to three of them.
+struct SahParams {
+    float cInner;  // per BINARY inner node
+    float cTri;
+    int maxLeaf;
+};
+
+// Combine two finished children into inner node `i` (called by whichever child arrives last).
+TMPT_HD void refit_node(const BinTree& t, int i, const SahParams& sp) {
+    const int L = t.left[i], R = t.right[i];
+    const float4 llo = t.lo[L], lhi = t.hi[L], rlo = t.lo[R], rhi = t.hi[R];
+    Box b = box_union(Box{llo.x, llo.y, llo.z, lhi.x, lhi.y, lhi.z}, Box{rlo.x, rlo.y, rlo.z, rhi.x, rhi.y, rhi.z});
+    int cl = (int)ex::f2u(lhi.w), cr = (int)ex::f2u(rhi.w);
+    int cnt = (cl < 0 ? -cl : cl) + (cr < 0 ? -cr : cr);
+    float area = box_half_area(b);
+    float costSplit = sp.cInner * area + llo.w + rlo.w;
+    float costLeaf = sp.cTri * area * (float)cnt;
+    bool asLeaf = cnt <= sp.maxLeaf && costLeaf <= costSplit;
+    t.lo[i] = make_float4(b.lox, b.loy, b.loz, asLeaf ? costLeaf : costSplit);
+    t.hi[i] = make_float4(b.hix, b.hiy, b.hiz, ex::u2f((uint32_t)(asLeaf ? -cnt : cnt)));
+}
+
+// ---- collapse: binary -> 4-wide ----
+struct WideOut {
+    float4* nodes;         // 8 float4 per wide node
+    float4* tris;          // 3 float4 per slot
+    const float* tris9;    // original triangles
+    const uint32_t* prim;  // sorted position -> original index
+    uint32_t* counters;    // [0] wide nodes allocated, [1] triangle slots allocated, [2] leaves, [3] max depth
+    float* sahAccum;       // [0] sum over inner nodes of half-area, [1] sum over leaves of half-area * count
+};
+struct WorkItem {
+    int bnode;     // binary inner node to expand
+    uint32_t wide; // wide node index it becomes
+    int depth;
+};
+
+TMPT_HD bool subtree_is_leaf(const BinTree& t, int node) {
+    return node >= t.n - 1 || (int)ex::f2u(t.hi[node].w) < 0;
+}
+TMPT_HD int subtree_count(const BinTree& t, int node) {
+    int c = (int)ex::f2u(t.hi[node].w);
+    return c < 0 ? -c : c;
+}
+
+// counter ops: atomic on the device, plain in the serial host emulation
+TMPT_HD uint32_t counter_add(uint32_t* p, uint32_t v) {
+#ifdef __CUDA_ARCH__
+    return atomicAdd(p, v);
+#else
+    uint32_t o = *p; *p += v; return o;
+#endif
+}
+TMPT_HD void counter_max(uint32_t* p, uint32_t v) {
+#ifdef __CUDA_ARCH__
+    atomicMax(p, v);
+#else
+    if (v > *p) *p = v;
+#endif
+}
+TMPT_HD void accum_add(float* p, float v) {
+#ifdef __CUDA_ARCH__
+    atomicAdd(p, v);
+#else
+    *p += v;
+#endif
+}
+
+// Write the triangles of a leaf subtree into consecutive slots, in sorted order.
+TMPT_HD void emit_leaf_tris(const BinTree& t, const WideOut& w, int node, uint32_t firstSlot) {
+    int stack[16];
+    int sp = 0;
+    stack[sp++] = node;
+    uint32_t slot = firstSlot;
+    while (sp > 0) {
+        int nd = stack[--sp];
+        if (nd >= t.n - 1) {
+            const uint32_t id = w.prim[nd - (t.n - 1)];
+            const float* p = w.tris9 + (size_t)id * 9;
+            ex::V3 v0 = ex::v3(p[0], p[1], p[2]), v1 = ex::v3(p[3], p[4], p[5]), v2 = ex::v3(p[6], p[7], p[8]);
+            ex::V3 e1 = ex::sub(v1, v0), e2 = ex::sub(v2, v0);  // maths.cpp:343-344
+            float4* o = w.tris + (size_t)slot * 3;
+            o[0] = make_float4(v0.x, v0.y, v0.z, ex::u2f(id));
+            o[1] = make_float4(e1.x, e1.y, e1.z, 0.0f);
+            o[2] = make_float4(e2.x, e2.y, e2.z, 0.0f);
+            ++slot;
+        } else {
+            stack[sp++] = t.right[nd];  // left first -> ascending sorted position
+            stack[sp++] = t.left[nd];
+        }
+    }
+}
+
+// Expand binary inner node `it.bnode` into wide node `it.wide`: repeatedly open the child
+// with the largest surface area until there are four (or only leaves remain).  Children that
+// stay inner get consecutive wide indices and are appended to `outQueue`.
+TMPT_HD void collapse_node(const BinTree& t, const WideOut& w, const WorkItem& it, WorkItem* outQueue, uint32_t* outCount) {
+    int c[4];
+    int k = 2;
+    c[0] = t.left[it.bnode];
+    c[1] = t.right[it.bnode];
+    while (k < 4) {
+        int pick = -1;
+        float bestArea = -1.0f;
+        for (int j = 0; j < k; ++j) {
+            if (subtree_is_leaf(t, c[j])) continue;
+            const float4 lo = t.lo[c[j]], hi = t.hi[c[j]];
+            float a = box_half_area(Box{lo.x, lo.y, lo.z, hi.x, hi.y, hi.z});
+            if (a > bestArea) { bestArea = a; pick = j; }
+        }
+        if (pick < 0) break;
+        const int open = c[pick];
+        c[pick] = t.left[open];
+        c[k++] = t.right[open];
+    }
+    int nInner = 0;
+    for (int j = 0; j < k; ++j) nInner += subtree_is_leaf(t, c[j]) ? 0 : 1;
+    uint32_t wideBase = nInner ? counter_add(&w.counters[0], (uint32_t)nInner) : 0u;
+    uint32_t qBase = nInner ? counter_add(outCount, (uint32_t)nInner) : 0u;
+
+    float lox[4], loy[4], loz[4], hix[4], hiy[4], hiz[4];
+    uint32_t refs[4];
+    float myArea;
+    {
+        const float4 lo = t.lo[it.bnode], hi = t.hi[it.bnode];
+        myArea = box_half_area(Box{lo.x, lo.y, lo.z, hi.x, hi.y, hi.z});
+    }
+    accum_add(&w.sahAccum[0], myArea);
+    int inner = 0;
+    for (int j = 0; j < 4; ++j) {
+        if (j >= k) {
+            lox[j] = loy[j] = loz[j] = hix[j] = hiy[j] = hiz[j] = 3.0e38f;  // far-away point box
+            refs[j] = bvh::NONE;
+            continue;
+        }
+        const float4 lo = t.lo[c[j]], hi = t.hi[c[j]];
+        lox[j] = lo.x; loy[j] = lo.y; loz[j] = lo.z; hix[j] = hi.x; hiy[j] = hi.y; hiz[j] = hi.z;
+        if (subtree_is_leaf(t, c[j])) {
+            const int cnt = subtree_count(t, c[j]);
+            const uint32_t first = counter_add(&w.counters[1], (uint32_t)cnt);
+            counter_add(&w.counters[2], 1u);
+            emit_leaf_tris(t, w, c[j], first);
+            refs[j] = bvh::make_leaf_ref(first, cnt);
+            accum_add(&w.sahAccum[1], box_half_area(Box{lo.x, lo.y, lo.z, hi.x, hi.y, hi.z}) * (float)cnt);
+        } else {
+            const uint32_t wi = wideBase + (uint32_t)inner;
+            refs[j] = wi;
+            outQueue[qBase + inner] = WorkItem{c[j], wi, it.depth + 1};
+            ++inner;
+        }
+    }
+    counter_max(&w.counters[3], (uint32_t)it.depth);
+    float4* o = w.nodes + (size_t)it.wide * 8;
+    o[0] = make_float4(lox[0], lox[1], lox[2], lox[3]);
+    o[1] = make_float4(hix[0], hix[1], hix[2], hix[3]);
+    o[2] = make_float4(loy[0], loy[1], loy[2], loy[3]);
+    o[3] = make_float4(hiy[0], hiy[1], hiy[2], hiy[3]);
+    o[4] = make_float4(loz[0], loz[1], loz[2], loz[3]);
+    o[5] = make_float4(hiz[0], hiz[1], hiz[2], hiz[3]);
+    o[6] = make_float4(ex::u2f(refs[0]), ex::u2f(refs[1]), ex::u2f(refs[2]), ex::u2f(refs[3]));
+    o[7] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+}
+
+// Root special case: the whole scene is one leaf (n <= maxLeaf and SAH says so, or n == 1).
+// Emits wide node 0 with a single leaf child.
+TMPT_HD void emit_single_leaf_root(const BinTree& t, const WideOut& w, int rootNode) {
+    const int cnt = rootNode >= t.n - 1 ? 1 : subtree_count(t, rootNode);
+    const uint32_t first = counter_add(&w.counters[1], (uint32_t)cnt);
+    counter_add(&w.counters[2], 1u);
+    emit_leaf_tris(t, w, rootNode, first);
+    const float4 lo = t.lo[rootNode], hi = t.hi[rootNode];
+    const float F = 3.0e38f;
+    float4* o = w.nodes;
+    o[0] = make_float4(lo.x, F, F, F); o[1] = make_float4(hi.x, F, F, F);
+    o[2] = make_float4(lo.y, F, F, F); o[3] = make_float4(hi.y, F, F, F);
+    o[4] = make_float4(lo.z, F, F, F); o[5] = make_float4(hi.z, F, F, F);
+    o[6] = make_float4(ex::u2f(bvh::make_leaf_ref(first, cnt)), ex::u2f(bvh::NONE), ex::u2f(bvh::NONE), ex::u2f(bvh::NONE));
+    o[7] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    accum_add(&w.sahAccum[1], box_half_area(Box{lo.x, lo.y, lo.z, hi.x, hi.y, hi.z}) * (float)cnt);
+}
+
+}  // namespace bld

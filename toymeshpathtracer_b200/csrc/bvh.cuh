@@ -1,0 +1,209 @@
+// bvh.cuh -- HBM layout of the scene and the ray traversal (closest-hit and any-hit).
+//
+// Replaces the reference's pointer octree + recursive walk (scene.cpp:7-19, 21-52, 86-97)
+// and its slab test (maths.h:116-134).  Semantics kept exactly (DESIGN.md "HitScene
+// contract"): nearest t over ALL triangles with the reference's own Moller-Trumbore
+// arithmetic (maths.cpp:339-380), range tMin <= t <= tMax and t < tMax, ties on bit-equal
+// t go to the lowest ORIGINAL triangle index, whatever order the tree is walked in.
+//
+// Layout (all 16-byte aligned, read with 128-bit loads, L2-resident at every config):
+//   nodes : 4-wide BVH, one node = one 128-byte line = 8 x float4, children SoA:
+//             [0] lo.x[4] [1] hi.x[4] [2] lo.y[4] [3] hi.y[4] [4] lo.z[4] [5] hi.z[4]
+//             [6] child refs[4] (bit-cast)   [7] reserved
+//           child ref: bit 31 clear -> index of an inner node
+//                      bit 31 set   -> leaf: bits 28..30 = triCount-1, bits 0..27 = first slot
+//           an unused child has ref 0xFFFFFFFF and a far-away point box; it is never entered.
+//   tris  : leaf-ordered triangle slots, 3 x float4 each, precomputed Moller-Trumbore form:
+//             [0] v0.xyz, original index (bit-cast int)   [1] e1 = v1-v0   [2] e2 = v2-v0
+//           (e1, e2 are the same correctly rounded differences maths.cpp:343-344 computes)
+//   tris9 : the caller's AoS array, untouched, indexed by ORIGINAL id -- read once per ray
+//           that hits, to form Hit.pos / Hit.normal with the reference's expression.
+// Child boxes are the union of PADDED triangle boxes (build_logic.cuh: pad_for) so that the
+// float slab test below can never cull a triangle the exact test would accept.
+#pragma once
+#include "exact.cuh"
+
+#ifdef __CUDA_ARCH__
+#define TMPT_LDG4(p) __ldg(p)
+#else
+#define TMPT_LDG4(p) (*(p))
+#endif
+
+namespace bvh {
+
+constexpr uint32_t LEAF_BIT = 0x80000000u;
+constexpr int MAX_LEAF_TRIS = 8;
+constexpr int WIDTH = 4;
+constexpr int STACK_SIZE = 64;         // entries; the builder reports the depth it needs
+constexpr uint32_t NONE = 0xFFFFFFFFu;     // empty child / empty stack; no leaf ref reaches it (slots < 2^28 - 1)
+constexpr uint32_t STACK_OVERFLOW = 1;  // bit in the scene's device status word
+
+TMPT_HD uint32_t make_leaf_ref(uint32_t firstSlot, int count) { return LEAF_BIT | (uint32_t(count - 1) << 28) | firstSlot; }
+TMPT_HD bool ref_is_leaf(uint32_t r) { return (r & LEAF_BIT) != 0; }
+TMPT_HD int leaf_count(uint32_t r) { return int((r >> 28) & 7u) + 1; }
+TMPT_HD uint32_t leaf_first(uint32_t r) { return r & 0x0FFFFFFFu; }
+
+struct SceneView {
+    const float4* nodes;  // 8 float4 per node
+    const float4* tris;   // 3 float4 per slot
+    const float* tris9;   // original triangles
+    uint32_t rootRef;     // may itself be a leaf ref for tiny scenes
+    int triCount;
+    uint32_t* status;     // device status word (STACK_OVERFLOW)
+};
+
+struct HitRec {
+    int id;     // original triangle index, -1 = miss
+    float t;
+    float u, v;  // barycentrics as the exact test computed them
+};
+
+// maths.cpp:339-380 on a precomputed (v0, e1, e2) slot.  Returns true iff the reference's
+// function would return true for [tMin, tMax]; t/u/v get the reference's bits.
+TMPT_HD bool mt_exact(ex::V3 o, ex::V3 d, ex::V3 v0, ex::V3 e1, ex::V3 e2, float tMin, float tMax,
+                      float& t, float& u, float& v) {
+    const float Epsilon = 1e-5f;
+    ex::V3 pvec = ex::cross(d, e2);
+    float det = ex::dot(e1, pvec);
+    if (det > -Epsilon && det < Epsilon) return false;
+    float invDet = ex::rcp(det);
+    ex::V3 tvec = ex::sub(o, v0);
+    u = ex::mul(ex::dot(tvec, pvec), invDet);
+    if (u < 0.0f || u > 1.0f) return false;
+    ex::V3 qvec = ex::cross(tvec, e1);
+    v = ex::mul(ex::dot(d, qvec), invDet);
+    if (v < 0.0f || ex::add(u, v) > 1.0f) return false;
+    t = ex::mul(ex::dot(e2, qvec), invDet);
+    return t >= tMin && t <= tMax;
+}
+
+// Hit.pos / Hit.normal exactly as maths.cpp:374-375 forms them, from the ORIGINAL vertices.
+TMPT_HD void hit_payload(const SceneView& sc, int id, float u, float v, ex::V3& pos, ex::V3& normal) {
+    const float* p = sc.tris9 + (size_t)id * 9;
+    ex::V3 v0 = ex::v3(p[0], p[1], p[2]), v1 = ex::v3(p[3], p[4], p[5]), v2 = ex::v3(p[6], p[7], p[8]);
+    float w = ex::sub(ex::sub(1.0f, u), v);
+    pos = ex::add(ex::add(ex::muls(v0, w), ex::muls(v1, u)), ex::muls(v2, v));
+    normal = ex::normalize(ex::cross(ex::sub(v1, v0), ex::sub(v2, v0)));
+}
+
+TMPT_HD float fmin3(float a, float b, float c) { return fminf(fminf(a, b), c); }
+TMPT_HD float fmax3(float a, float b, float c) { return fmaxf(fmaxf(a, b), c); }
+TMPT_HD float fma_(float a, float b, float c) {
+#ifdef __CUDA_ARCH__
+    return __fmaf_rn(a, b, c);
+#else
+    return a * b + c;  // conservativeness does not depend on fusing
+#endif
+}
+
+// Ray-constant part of the slab test: t = b * idir - o * idir.
+struct RaySlab {
+    float idx, idy, idz;  // 1 / dir
+    float ox, oy, oz;     // orig / dir
+};
+// A zero (or denormal) direction component would make idir infinite and b*inf - o*inf a NaN
+// or a wrongly signed infinity; it is replaced by +-1e-20, for which the slab interval is
+// "everything" when the origin lies between the planes and empty otherwise -- exactly the
+// test an axis-parallel ray needs.
+TMPT_HD float safe_dir(float d) { return fabsf(d) < 1.0e-20f ? copysignf(1.0e-20f, d) : d; }
+TMPT_HD RaySlab make_slab(ex::V3 o, ex::V3 d) {
+    RaySlab r;
+    r.idx = 1.0f / safe_dir(d.x); r.idy = 1.0f / safe_dir(d.y); r.idz = 1.0f / safe_dir(d.z);
+    r.ox = o.x * r.idx; r.oy = o.y * r.idy; r.oz = o.z * r.idz;
+    return r;
+}
+
+// One traversal, closest (ANY=false) or any-hit (ANY=true).
+//
+// Culling keeps a child when tNear <= tFar with tFar clipped to the CURRENT best t -- "<=",
+// not "<", so that a triangle in another leaf with bit-equal t and a lower index is still
+// tested.  The candidate rule is the lexicographic minimum of (t, id).
+template <bool ANY>
+TMPT_HD HitRec traverse(const SceneView& sc, ex::V3 o, ex::V3 d, float tMin, float tMax) {
+    HitRec best;
+    best.id = -1; best.t = tMax; best.u = 0.0f; best.v = 0.0f;
+    const RaySlab rs = make_slab(o, d);
+
+    uint32_t stackRef[STACK_SIZE];
+    float stackT[STACK_SIZE];
+    int sp = 0;
+    uint32_t cur = sc.rootRef;
+
+    while (cur != NONE) {
+        if (!ref_is_leaf(cur)) {
+            const float4* n = sc.nodes + (size_t)cur * 8;
+            const float4 lox = TMPT_LDG4(n + 0), hix = TMPT_LDG4(n + 1);
+            const float4 loy = TMPT_LDG4(n + 2), hiy = TMPT_LDG4(n + 3);
+            const float4 loz = TMPT_LDG4(n + 4), hiz = TMPT_LDG4(n + 5);
+            const float4 refsf = TMPT_LDG4(n + 6);
+            const float lo_x[4] = {lox.x, lox.y, lox.z, lox.w}, hi_x[4] = {hix.x, hix.y, hix.z, hix.w};
+            const float lo_y[4] = {loy.x, loy.y, loy.z, loy.w}, hi_y[4] = {hiy.x, hiy.y, hiy.z, hiy.w};
+            const float lo_z[4] = {loz.x, loz.y, loz.z, loz.w}, hi_z[4] = {hiz.x, hiz.y, hiz.z, hiz.w};
+            const uint32_t refs[4] = {ex::f2u(refsf.x), ex::f2u(refsf.y), ex::f2u(refsf.z), ex::f2u(refsf.w)};
+
+            uint32_t nextRef = NONE;
+            float nextT = 0.0f;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                float tx0 = fma_(lo_x[k], rs.idx, -rs.ox), tx1 = fma_(hi_x[k], rs.idx, -rs.ox);
+                float ty0 = fma_(lo_y[k], rs.idy, -rs.oy), ty1 = fma_(hi_y[k], rs.idy, -rs.oy);
+                float tz0 = fma_(lo_z[k], rs.idz, -rs.oz), tz1 = fma_(hi_z[k], rs.idz, -rs.oz);
+                float tn = fmaxf(fmax3(fminf(tx0, tx1), fminf(ty0, ty1), fminf(tz0, tz1)), tMin);
+                float tf = fminf(fmin3(fmaxf(tx0, tx1), fmaxf(ty0, ty1), fmaxf(tz0, tz1)), best.t);
+                if (tn <= tf && refs[k] != NONE) {
+                    if (nextRef == NONE) {
+                        nextRef = refs[k]; nextT = tn;
+                    } else {
+                        uint32_t pushRef = refs[k]; float pushT = tn;
+                        if (tn < nextT) { pushRef = nextRef; pushT = nextT; nextRef = refs[k]; nextT = tn; }
+                        if (sp < STACK_SIZE) { stackRef[sp] = pushRef; stackT[sp] = pushT; ++sp; }
+                        else if (sc.status) *sc.status |= STACK_OVERFLOW;
+                    }
+                }
+            }
+            cur = nextRef;
+        } else {
+            const uint32_t first = leaf_first(cur);
+            const int cnt = leaf_count(cur);
+            for (int k = 0; k < cnt; ++k) {
+                const float4* tp = sc.tris + (size_t)(first + k) * 3;
+                const float4 a = TMPT_LDG4(tp + 0), b = TMPT_LDG4(tp + 1), c = TMPT_LDG4(tp + 2);
+                float t, u, v;
+                if (mt_exact(o, d, ex::v3(a.x, a.y, a.z), ex::v3(b.x, b.y, b.z), ex::v3(c.x, c.y, c.z), tMin, tMax, t, u, v)) {
+                    const int id = (int)ex::f2u(a.w);
+                    if (t < best.t || (t == best.t && best.id >= 0 && id < best.id)) {
+                        best.t = t; best.id = id; best.u = u; best.v = v;
+                        if (ANY) return best;
+                    }
+                }
+            }
+            cur = NONE;
+        }
+        // pop: skip entries that the shrinking best.t has already culled
+        while (cur == NONE && sp > 0) {
+            --sp;
+            if (stackT[sp] <= best.t) cur = stackRef[sp];
+        }
+    }
+    return best;
+}
+
+// Upstream's HitScene: every triangle, no tree.  Same candidate rule, so it must agree with
+// traverse<false> bit for bit -- the on-GPU cross-check of box conservativeness at sizes the
+// CPU checker cannot reach (TMPT_HIT_BRUTE).
+TMPT_HD HitRec brute_force(const SceneView& sc, ex::V3 o, ex::V3 d, float tMin, float tMax) {
+    HitRec best;
+    best.id = -1; best.t = tMax; best.u = 0.0f; best.v = 0.0f;
+    for (int k = 0; k < sc.triCount; ++k) {
+        const float4* tp = sc.tris + (size_t)k * 3;
+        const float4 a = TMPT_LDG4(tp + 0), b = TMPT_LDG4(tp + 1), c = TMPT_LDG4(tp + 2);
+        float t, u, v;
+        if (mt_exact(o, d, ex::v3(a.x, a.y, a.z), ex::v3(b.x, b.y, b.z), ex::v3(c.x, c.y, c.z), tMin, tMax, t, u, v)) {
+            const int id = (int)ex::f2u(a.w);
+            if (t < best.t || (t == best.t && best.id >= 0 && id < best.id)) { best.t = t; best.id = id; best.u = u; best.v = v; }
+        }
+    }
+    return best;
+}
+
+}  // namespace bvh

@@ -1,0 +1,687 @@
+// kernels.cu -- CUDA kernels (sm_100a) and the compute half of the C ABI (include/tmpt.h).
+//
+//   K1  BVH build      k_prim_bounds, k_morton, k_radix_sort, k_leaf_boxes, k_karras, k_refit, k_collapse
+//                      (replaces Scene::BuildOctree, scene.cpp:75-160)
+//   K2  closest hit    k_hit_scene<CLOSEST>   (Scene::HitScene, scene.cpp:86-97, batched)
+//   K3  any hit        k_hit_scene<ANY>       (the shadow query of Scatter, main.cpp:59)
+//       brute force    k_hit_scene<BRUTE>     (upstream's all-triangle scan; cross-check only)
+//   K4  path tracing   k_render               (TraceImageBody / Trace / Scatter, main.cpp:44-119, 192-238)
+//   K5  stripe gather  k_unpack_stripes       (rank 0 after the multi-GPU gather)
+//
+// There is no CPU fallback in this file: every entry point needs a CUDA device.
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "build_logic.cuh"
+#include "common.h"
+#include "integrator.cuh"
+
+// ------------------------------------------------------------------------------------------
+// error plumbing
+// ------------------------------------------------------------------------------------------
+namespace tmpt {
+static thread_local std::string g_err;
+static std::atomic<uint64_t> g_launches{0};
+int fail(int status, const char* fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return status;
+}
+void count_launch(uint64_t n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+}  // namespace tmpt
+
+extern "C" const char* tmpt_last_error(void) { return tmpt::g_err.c_str(); }
+extern "C" uint64_t tmpt_launch_count(void) { return tmpt::g_launches.load(); }
+extern "C" int tmpt_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+#define CU_TRY(expr)                                                                                       \
+    do {                                                                                                   \
+        cudaError_t e_ = (expr);                                                                           \
+        if (e_ != cudaSuccess) return tmpt::fail(e_ == cudaErrorMemoryAllocation ? TMPT_ERR_OOM : TMPT_ERR_CUDA, \
+                                                 "%s:%d %s: %s", __FILE__, __LINE__, #expr, cudaGetErrorString(e_)); \
+    } while (0)
+#define LAUNCH(kernel, grid, block, smem, stream, ...)      \
+    do {                                                    \
+        kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__); \
+        tmpt::count_launch();                               \
+    } while (0)
+
+static inline int div_up(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+// ------------------------------------------------------------------------------------------
+// the scene object behind tmpt_scene*
+// ------------------------------------------------------------------------------------------
+struct tmpt_scene {
+    int device = 0;
+    int triCount = 0;
+    int smCount = 148;
+    cudaStream_t stream = nullptr;
+    float* d_tris9 = nullptr;      // caller's triangles, original order
+    float4* d_nodes = nullptr;     // wide nodes
+    float4* d_tris = nullptr;      // leaf-ordered MT slots
+    uint32_t* d_status = nullptr;  // [0] status bits
+    // render scratch
+    uint32_t* d_tileCounter = nullptr;
+    unsigned long long* d_rayCount = nullptr;
+    uint8_t* d_frame = nullptr;
+    size_t frameBytes = 0;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    bvh::SceneView view{};
+    tmpt_scene_info info{};
+};
+
+// ------------------------------------------------------------------------------------------
+// K1: BVH build
+// ------------------------------------------------------------------------------------------
+// bounds[0..2] = min, [3..5] = max as order-preserving uints
+__global__ void k_prim_bounds(const float* __restrict__ tris9, int n, uint32_t* __restrict__ bounds) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    bld::Box b{3.0e38f, 3.0e38f, 3.0e38f, -3.0e38f, -3.0e38f, -3.0e38f};
+    if (i < n) b = bld::tri_box(tris9 + (size_t)i * 9);
+    // warp reduce, then one atomic per warp
+    for (int o = 16; o > 0; o >>= 1) {
+        b.lox = fminf(b.lox, __shfl_xor_sync(0xffffffffu, b.lox, o));
+        b.loy = fminf(b.loy, __shfl_xor_sync(0xffffffffu, b.loy, o));
+        b.loz = fminf(b.loz, __shfl_xor_sync(0xffffffffu, b.loz, o));
+        b.hix = fmaxf(b.hix, __shfl_xor_sync(0xffffffffu, b.hix, o));
+        b.hiy = fmaxf(b.hiy, __shfl_xor_sync(0xffffffffu, b.hiy, o));
+        b.hiz = fmaxf(b.hiz, __shfl_xor_sync(0xffffffffu, b.hiz, o));
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicMin(&bounds[0], bld::float_to_ordered(b.lox));
+        atomicMin(&bounds[1], bld::float_to_ordered(b.loy));
+        atomicMin(&bounds[2], bld::float_to_ordered(b.loz));
+        atomicMax(&bounds[3], bld::float_to_ordered(b.hix));
+        atomicMax(&bounds[4], bld::float_to_ordered(b.hiy));
+        atomicMax(&bounds[5], bld::float_to_ordered(b.hiz));
+    }
+}
+
+__device__ __forceinline__ bld::Box load_scene_box(const uint32_t* bounds) {
+    return bld::Box{bld::ordered_to_float(bounds[0]), bld::ordered_to_float(bounds[1]), bld::ordered_to_float(bounds[2]),
+                    bld::ordered_to_float(bounds[3]), bld::ordered_to_float(bounds[4]), bld::ordered_to_float(bounds[5])};
+}
+
+__global__ void k_morton(const float* __restrict__ tris9, int n, const uint32_t* __restrict__ bounds,
+                         uint64_t* __restrict__ keys, uint32_t* __restrict__ prim) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const bld::Box scene = load_scene_box(bounds);
+    const bld::Box b = bld::tri_box(tris9 + (size_t)i * 9);
+    keys[i] = bld::morton63(0.5f * (b.lox + b.hix), 0.5f * (b.loy + b.hiy), 0.5f * (b.loz + b.hiz), scene);
+    prim[i] = (uint32_t)i;
+}
+
+// Stable LSD radix sort of (key, value) pairs by ONE cooperative CTA, 4 bits per pass.
+// Thread t owns the contiguous chunk [t*per, (t+1)*per): it counts its 16 digits, the CTA
+// scans the (digit-major, thread-minor) table in shared memory, and the thread scatters its
+// chunk in order -- stable because chunk order is thread order.  The build is a one-off of
+// <= a few 100k primitives (untimed by the reference, main.cpp:312), so one SM is enough.
+constexpr int SORT_THREADS = 1024;
+__global__ void __launch_bounds__(SORT_THREADS) k_radix_sort(uint64_t* keysA, uint32_t* valsA, uint64_t* keysB, uint32_t* valsB, int n,
+                                                            int passes) {
+    extern __shared__ uint32_t table[];  // 16 * SORT_THREADS entries = 64 KB (dynamic: above the static limit)
+    __shared__ uint32_t warpTotals[32];
+    const int t = threadIdx.x;
+    const int per = (n + SORT_THREADS - 1) / SORT_THREADS;
+    const int b = min(t * per, n), e = min(b + per, n);
+    uint64_t* kin = keysA; uint32_t* vin = valsA; uint64_t* kout = keysB; uint32_t* vout = valsB;
+    for (int pass = 0; pass < passes; ++pass) {
+        const int shift = pass * 4;
+        uint32_t cnt[16];
+#pragma unroll
+        for (int d = 0; d < 16; ++d) cnt[d] = 0;
+        for (int i = b; i < e; ++i) {
+            const int dgt = (int)((kin[i] >> shift) & 15);
+#pragma unroll
+            for (int d = 0; d < 16; ++d) cnt[d] += (d == dgt);
+        }
+#pragma unroll
+        for (int d = 0; d < 16; ++d) table[d * SORT_THREADS + t] = cnt[d];
+        __syncthreads();
+        // exclusive scan of the 16*1024 table: each thread scans 16 consecutive entries
+        uint32_t local[16];
+        uint32_t sum = 0;
+#pragma unroll
+        for (int k = 0; k < 16; ++k) { local[k] = sum; sum += table[t * 16 + k]; }
+        uint32_t incl = sum;
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t y = __shfl_up_sync(0xffffffffu, incl, o);
+            if ((t & 31) >= o) incl += y;
+        }
+        if ((t & 31) == 31) warpTotals[t >> 5] = incl;
+        __syncthreads();
+        if (t < 32) {
+            uint32_t w = warpTotals[t];
+            uint32_t wi = w;
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t y = __shfl_up_sync(0xffffffffu, wi, o);
+                if (t >= o) wi += y;
+            }
+            warpTotals[t] = wi - w;
+        }
+        __syncthreads();
+        const uint32_t base = warpTotals[t >> 5] + incl - sum;
+#pragma unroll
+        for (int k = 0; k < 16; ++k) table[t * 16 + k] = base + local[k];
+        __syncthreads();
+        uint32_t off[16];
+#pragma unroll
+        for (int d = 0; d < 16; ++d) off[d] = table[d * SORT_THREADS + t];
+        for (int i = b; i < e; ++i) {
+            const uint64_t k = kin[i];
+            const int dgt = (int)((k >> shift) & 15);
+            uint32_t dst = 0;
+#pragma unroll
+            for (int d = 0; d < 16; ++d) {
+                if (d == dgt) { dst = off[d]; off[d] = dst + 1; }
+            }
+            kout[dst] = k;
+            vout[dst] = vin[i];
+        }
+        __syncthreads();
+        uint64_t* tk = kin; kin = kout; kout = tk;
+        uint32_t* tv = vin; vin = vout; vout = tv;
+    }
+}
+
+// leaf j of the binary tree = sorted position j: padded box, cost of a 1-triangle leaf, count 1
+__global__ void k_leaf_boxes(const float* __restrict__ tris9, const uint32_t* __restrict__ prim, int n,
+                             const uint32_t* __restrict__ bounds, float cTri, float4* __restrict__ lo, float4* __restrict__ hi) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    const bld::Box scene = load_scene_box(bounds);
+    const float maxAbs = fmaxf(fmaxf(fmaxf(fabsf(scene.lox), fabsf(scene.hix)), fmaxf(fabsf(scene.loy), fabsf(scene.hiy))),
+                               fmaxf(fabsf(scene.loz), fabsf(scene.hiz)));
+    bld::Box b = bld::tri_box(tris9 + (size_t)prim[j] * 9);
+    const float dx = b.hix - b.lox, dy = b.hiy - b.loy, dz = b.hiz - b.loz;
+    const float pad = bld::pad_for(sqrtf(dx * dx + dy * dy + dz * dz), maxAbs);
+    b.lox -= pad; b.loy -= pad; b.loz -= pad; b.hix += pad; b.hiy += pad; b.hiz += pad;
+    lo[n - 1 + j] = make_float4(b.lox, b.loy, b.loz, cTri * bld::box_half_area(b));
+    hi[n - 1 + j] = make_float4(b.hix, b.hiy, b.hiz, ex::u2f(1u));
+}
+
+__global__ void k_karras(bld::BinTree t) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < t.n - 1) bld::karras_node(t, i);
+}
+
+// bottom-up: the second child to arrive at a node combines both (Karras 2012, section 4)
+__global__ void k_refit(bld::BinTree t, bld::SahParams sp) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= t.n) return;
+    int node = t.parent[t.n - 1 + j];
+    while (node >= 0) {
+        __threadfence();
+        if (atomicAdd(&t.visits[node], 1u) == 0u) return;
+        __threadfence();
+        bld::refit_node(t, node, sp);
+        node = t.parent[node];
+    }
+}
+
+__global__ void k_collapse(bld::BinTree t, bld::WideOut w, const bld::WorkItem* __restrict__ inQueue, const uint32_t* __restrict__ inCount,
+                           bld::WorkItem* __restrict__ outQueue, uint32_t* __restrict__ outCount) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= *inCount) return;
+    bld::collapse_node(t, w, inQueue[i], outQueue, outCount);
+}
+__global__ void k_collapse_root_leaf(bld::BinTree t, bld::WideOut w, int rootNode) { bld::emit_single_leaf_root(t, w, rootNode); }
+
+// ------------------------------------------------------------------------------------------
+// K2/K3: batched HitScene
+// ------------------------------------------------------------------------------------------
+template <int MODE>
+__global__ void __launch_bounds__(128) k_hit_scene(bvh::SceneView sc, const float* __restrict__ rays6, long long nRays, float tMin, float tMax,
+                                                    int* __restrict__ outID, float* __restrict__ outT, float* __restrict__ outPos,
+                                                    float* __restrict__ outNormal) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nRays; i += (long long)gridDim.x * blockDim.x) {
+        const float* r = rays6 + i * 6;
+        const ex::V3 o = ex::v3(r[0], r[1], r[2]), d = ex::v3(r[3], r[4], r[5]);
+        bvh::HitRec h;
+        if (MODE == TMPT_HIT_BRUTE) h = bvh::brute_force(sc, o, d, tMin, tMax);
+        else if (MODE == TMPT_HIT_ANY) h = bvh::traverse<true>(sc, o, d, tMin, tMax);
+        else h = bvh::traverse<false>(sc, o, d, tMin, tMax);
+        if (MODE == TMPT_HIT_ANY) { outID[i] = h.id < 0 ? -1 : 1; continue; }
+        outID[i] = h.id;
+        if (h.id >= 0) {
+            if (outT) outT[i] = h.t;
+            if (outPos || outNormal) {
+                ex::V3 pos, nrm;
+                bvh::hit_payload(sc, h.id, h.u, h.v, pos, nrm);
+                if (outPos) { outPos[i * 3] = pos.x; outPos[i * 3 + 1] = pos.y; outPos[i * 3 + 2] = pos.z; }
+                if (outNormal) { outNormal[i * 3] = nrm.x; outNormal[i * 3 + 1] = nrm.y; outNormal[i * 3 + 2] = nrm.z; }
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// K4: path tracing.  Work unit = an 8x4 pixel tile per warp, fetched from a global counter
+// (persistent CTAs); each lane owns one pixel and runs its samples serially because the
+// pixel's XorShift32 stream flows through them (DESIGN.md "RNG").
+// ------------------------------------------------------------------------------------------
+struct RenderParams {
+    bvh::SceneView sc;
+    integ::Camera cam;
+    ex::V3 lightDir;
+    int width, height, spp;
+    int stripeRows, rank, world, ownedRows;
+    int tilesX, numTiles;
+    uchar4* outStripes;  // packed owned rows, or
+    uchar4* frame;       // full frame (possibly peer memory)
+    unsigned long long* rayCount;
+    uint32_t* tileCounter;
+};
+
+__device__ __forceinline__ int owned_row_to_global(int r, int stripeRows, int rank, int world) {
+    const int ls = r / stripeRows;
+    return (ls * world + rank) * stripeRows + (r - ls * stripeRows);
+}
+
+__global__ void __launch_bounds__(256) k_render(const RenderParams p) {
+    const int lane = threadIdx.x & 31;
+    unsigned long long rays = 0;
+    for (;;) {
+        uint32_t tile = 0;
+        if (lane == 0) tile = atomicAdd(p.tileCounter, 1u);
+        tile = __shfl_sync(0xffffffffu, tile, 0);
+        if (tile >= (uint32_t)p.numTiles) break;
+        const int tx = (int)(tile % (uint32_t)p.tilesX), ty = (int)(tile / (uint32_t)p.tilesX);
+        const int x = tx * 8 + (lane & 7), r = ty * 4 + (lane >> 3);
+        if (x < p.width && r < p.ownedRows) {
+            const int y = owned_row_to_global(r, p.stripeRows, p.rank, p.world);
+            const uchar4 px = integ::render_pixel(p.sc, p.cam, x, y, p.width, p.height, p.spp, p.lightDir, rays);
+            if (p.frame) p.frame[(size_t)y * p.width + x] = px;
+            else p.outStripes[(size_t)r * p.width + x] = px;
+        }
+    }
+    for (int o = 16; o > 0; o >>= 1) rays += __shfl_xor_sync(0xffffffffu, rays, o);
+    if (lane == 0 && rays) atomicAdd(p.rayCount, rays);
+}
+
+// K5: rank 0 scatters the gathered, rank-major packed stripes into the frame
+__global__ void k_unpack_stripes(const uchar4* __restrict__ gathered, int width, int height, int stripeRows, int world, int maxRowsPerRank,
+                                 uchar4* __restrict__ frame) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long long)width * height) return;
+    const int y = (int)(i / width), x = (int)(i - (long long)y * width);
+    const int gs = y / stripeRows, rank = gs % world, ls = gs / world;
+    const int r = ls * stripeRows + (y - gs * stripeRows);
+    frame[i] = gathered[((size_t)rank * maxRowsPerRank + r) * width + x];
+}
+
+// ------------------------------------------------------------------------------------------
+// host side of the build
+// ------------------------------------------------------------------------------------------
+namespace {
+template <class T>
+struct DevBuf {
+    T* p = nullptr;
+    ~DevBuf() { if (p) cudaFree(p); }
+    cudaError_t alloc(size_t n) { return cudaMalloc((void**)&p, (n ? n : 1) * sizeof(T)); }
+};
+
+int build_bvh(tmpt_scene* s, unsigned flags) {
+    const int n = s->triCount;
+    cudaStream_t st = s->stream;
+    const float cInner = 1.0f, cTri = 1.0f;
+    (void)flags;
+
+    DevBuf<uint32_t> bounds, primA, primB, visits, counters, qCount;
+    DevBuf<uint64_t> keysA, keysB;
+    DevBuf<int> left, right, parent;
+    DevBuf<float4> lo, hi;
+    DevBuf<float> sah;
+    DevBuf<bld::WorkItem> qA, qB;
+    CU_TRY(bounds.alloc(6)); CU_TRY(primA.alloc(n)); CU_TRY(primB.alloc(n)); CU_TRY(keysA.alloc(n)); CU_TRY(keysB.alloc(n));
+    CU_TRY(visits.alloc(n)); CU_TRY(counters.alloc(4)); CU_TRY(qCount.alloc(2));
+    CU_TRY(left.alloc(n)); CU_TRY(right.alloc(n)); CU_TRY(parent.alloc(2 * (size_t)n));
+    CU_TRY(lo.alloc(2 * (size_t)n)); CU_TRY(hi.alloc(2 * (size_t)n)); CU_TRY(sah.alloc(2));
+    CU_TRY(qA.alloc(n)); CU_TRY(qB.alloc(n));
+    CU_TRY(cudaMalloc((void**)&s->d_nodes, (size_t)n * 8 * sizeof(float4)));
+    CU_TRY(cudaMalloc((void**)&s->d_tris, (size_t)n * 3 * sizeof(float4)));
+
+    const uint32_t initBounds[6] = {0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0u, 0u, 0u};
+    CU_TRY(cudaMemcpyAsync(bounds.p, initBounds, sizeof initBounds, cudaMemcpyHostToDevice, st));
+    CU_TRY(cudaMemsetAsync(visits.p, 0, (size_t)n * sizeof(uint32_t), st));
+    CU_TRY(cudaMemsetAsync(counters.p, 0, 4 * sizeof(uint32_t), st));
+    CU_TRY(cudaMemsetAsync(sah.p, 0, 2 * sizeof(float), st));
+    CU_TRY(cudaMemsetAsync(parent.p, 0xFF, 2 * (size_t)n * sizeof(int), st));
+
+    const int B = 256, G = div_up(n, B);
+    LAUNCH(k_prim_bounds, G, B, 0, st, s->d_tris9, n, bounds.p);
+    LAUNCH(k_morton, G, B, 0, st, s->d_tris9, n, bounds.p, keysA.p, primA.p);
+    const int passes = 16;  // 63-bit keys, 4 bits per pass; an even count leaves the result in A
+    const int sortSmem = 16 * SORT_THREADS * (int)sizeof(uint32_t);
+    CU_TRY(cudaFuncSetAttribute(k_radix_sort, cudaFuncAttributeMaxDynamicSharedMemorySize, sortSmem));
+    LAUNCH(k_radix_sort, 1, SORT_THREADS, sortSmem, st, keysA.p, primA.p, keysB.p, primB.p, n, passes);
+    LAUNCH(k_leaf_boxes, G, B, 0, st, s->d_tris9, primA.p, n, bounds.p, cTri, lo.p, hi.p);
+
+    bld::BinTree t{n, keysA.p, left.p, right.p, parent.p, lo.p, hi.p, visits.p};
+    bld::SahParams sp{cInner, cTri, bvh::MAX_LEAF_TRIS};
+    bld::WideOut w{s->d_nodes, s->d_tris, s->d_tris9, primA.p, counters.p, sah.p};
+    int rootIsLeaf = (n == 1);
+    if (n > 1) {
+        LAUNCH(k_karras, div_up(n - 1, B), B, 0, st, t);
+        LAUNCH(k_refit, G, B, 0, st, t, sp);
+        float4 rootHi;
+        CU_TRY(cudaMemcpyAsync(&rootHi, hi.p, sizeof rootHi, cudaMemcpyDeviceToHost, st));
+        CU_TRY(cudaStreamSynchronize(st));
+        int c; memcpy(&c, &rootHi.w, 4);
+        rootIsLeaf = c < 0;
+    }
+    if (rootIsLeaf) {
+        const uint32_t one = 1;
+        CU_TRY(cudaMemcpyAsync(counters.p, &one, 4, cudaMemcpyHostToDevice, st));
+        LAUNCH(k_collapse_root_leaf, 1, 1, 0, st, t, w, 0);
+    } else {
+        const bld::WorkItem root{0, 0u, 0};
+        const uint32_t one = 1, zero = 0;
+        CU_TRY(cudaMemcpyAsync(qA.p, &root, sizeof root, cudaMemcpyHostToDevice, st));
+        CU_TRY(cudaMemcpyAsync(counters.p, &one, 4, cudaMemcpyHostToDevice, st));   // wide node 0 is taken
+        CU_TRY(cudaMemcpyAsync(qCount.p, &one, 4, cudaMemcpyHostToDevice, st));
+        bld::WorkItem* qin = qA.p; bld::WorkItem* qout = qB.p;
+        int cin = 0;
+        uint32_t count = 1;
+        while (count > 0) {
+            CU_TRY(cudaMemcpyAsync(qCount.p + (1 - cin), &zero, 4, cudaMemcpyHostToDevice, st));
+            LAUNCH(k_collapse, div_up(count, 128), 128, 0, st, t, w, qin, qCount.p + cin, qout, qCount.p + (1 - cin));
+            CU_TRY(cudaMemcpyAsync(&count, qCount.p + (1 - cin), 4, cudaMemcpyDeviceToHost, st));
+            CU_TRY(cudaStreamSynchronize(st));
+            cin = 1 - cin;
+            bld::WorkItem* tq = qin; qin = qout; qout = tq;
+        }
+    }
+    uint32_t hc[4]; float hs[2]; uint32_t hb[6];
+    CU_TRY(cudaMemcpyAsync(hc, counters.p, sizeof hc, cudaMemcpyDeviceToHost, st));
+    CU_TRY(cudaMemcpyAsync(hs, sah.p, sizeof hs, cudaMemcpyDeviceToHost, st));
+    CU_TRY(cudaMemcpyAsync(hb, bounds.p, sizeof hb, cudaMemcpyDeviceToHost, st));
+    CU_TRY(cudaStreamSynchronize(st));
+    CU_TRY(cudaGetLastError());
+    s->info.node_count = (int)hc[0];
+    s->info.leaf_count = (int)hc[2];
+    s->info.max_depth = (int)hc[3] + 1;
+    s->info.max_leaf_tris = bvh::MAX_LEAF_TRIS;
+    s->info.builder = TMPT_BUILD_LBVH;
+    for (int k = 0; k < 3; ++k) {
+        s->info.bounds_min[k] = bld::ordered_to_float(hb[k]);
+        s->info.bounds_max[k] = bld::ordered_to_float(hb[3 + k]);
+    }
+    {
+        const float dx = s->info.bounds_max[0] - s->info.bounds_min[0], dy = s->info.bounds_max[1] - s->info.bounds_min[1],
+                    dz = s->info.bounds_max[2] - s->info.bounds_min[2];
+        const float rootArea = dx * dy + dy * dz + dz * dx;
+        s->info.sah_cost = rootArea > 0.0f ? (cInner * hs[0] + cTri * hs[1]) / rootArea : 0.0f;
+    }
+    if ((int)hc[1] != n) return tmpt::fail(TMPT_ERR_CUDA, "BVH build lost triangles: %u slots for %d triangles", hc[1], n);
+    s->info.device_bytes = (uint64_t)n * 9 * 4 + (uint64_t)hc[0] * 128 + (uint64_t)n * 48;
+    s->view.nodes = s->d_nodes;
+    s->view.tris = s->d_tris;
+    s->view.tris9 = s->d_tris9;
+    s->view.rootRef = 0u;
+    s->view.triCount = n;
+    s->view.status = s->d_status;
+    return TMPT_OK;
+}
+
+struct DeviceGuard {
+    int prev = -1;
+    bool ok = false;
+    explicit DeviceGuard(int dev) { ok = cudaGetDevice(&prev) == cudaSuccess && cudaSetDevice(dev) == cudaSuccess; }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+}  // namespace
+
+// ------------------------------------------------------------------------------------------
+// C ABI: scene
+// ------------------------------------------------------------------------------------------
+extern "C" int tmpt_scene_create(const float* tris9, int triCount, int device, unsigned flags, tmpt_scene** outScene) {
+    if (!outScene) return tmpt::fail(TMPT_ERR_ARG, "tmpt_scene_create: outScene is NULL");
+    *outScene = nullptr;
+    if (triCount < 0 || triCount >= (1 << 28) - 1 || (triCount > 0 && !tris9))
+        return tmpt::fail(TMPT_ERR_ARG, "tmpt_scene_create: bad triangle array (count %d)", triCount);
+    int nDev = 0;
+    if (cudaGetDeviceCount(&nDev) != cudaSuccess || nDev == 0) {
+        cudaGetLastError();
+        return tmpt::fail(TMPT_ERR_CUDA, "tmpt_scene_create: no CUDA device (this library has no CPU path)");
+    }
+    if (device < 0 || device >= nDev) return tmpt::fail(TMPT_ERR_ARG, "tmpt_scene_create: device %d of %d", device, nDev);
+    DeviceGuard guard(device);
+    if (!guard.ok) return tmpt::fail(TMPT_ERR_CUDA, "tmpt_scene_create: cudaSetDevice(%d) failed", device);
+
+    tmpt_scene* s = new (std::nothrow) tmpt_scene();
+    if (!s) return tmpt::fail(TMPT_ERR_OOM, "tmpt_scene_create: out of host memory");
+    s->device = device;
+    s->triCount = triCount;
+    s->info.abi_version = TMPT_ABI_VERSION;
+    s->info.device = device;
+    s->info.tri_count = triCount;
+    int rc = TMPT_OK;
+    auto body = [&]() -> int {
+        cudaDeviceProp prop;
+        CU_TRY(cudaGetDeviceProperties(&prop, device));
+        s->smCount = prop.multiProcessorCount;
+        CU_TRY(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
+        CU_TRY(cudaEventCreate(&s->ev0));
+        CU_TRY(cudaEventCreate(&s->ev1));
+        CU_TRY(cudaMalloc((void**)&s->d_status, 4 * sizeof(uint32_t)));
+        CU_TRY(cudaMemsetAsync(s->d_status, 0, 4 * sizeof(uint32_t), s->stream));
+        CU_TRY(cudaMalloc((void**)&s->d_tileCounter, sizeof(uint32_t)));
+        CU_TRY(cudaMalloc((void**)&s->d_rayCount, sizeof(unsigned long long)));
+        CU_TRY(cudaEventRecord(s->ev0, s->stream));
+        if (triCount > 0) {
+            CU_TRY(cudaMalloc((void**)&s->d_tris9, (size_t)triCount * 9 * sizeof(float)));
+            CU_TRY(cudaMemcpyAsync(s->d_tris9, tris9, (size_t)triCount * 9 * sizeof(float), cudaMemcpyHostToDevice, s->stream));
+            const int brc = build_bvh(s, flags);
+            if (brc != TMPT_OK) return brc;
+        } else {
+            s->view = bvh::SceneView{nullptr, nullptr, nullptr, bvh::NONE, 0, s->d_status};
+        }
+        CU_TRY(cudaEventRecord(s->ev1, s->stream));
+        CU_TRY(cudaStreamSynchronize(s->stream));
+        float ms = 0.0f;
+        CU_TRY(cudaEventElapsedTime(&ms, s->ev0, s->ev1));
+        s->info.build_ms = ms;
+        return TMPT_OK;
+    };
+    rc = body();
+    if (rc != TMPT_OK) { tmpt_scene_destroy(s); return rc; }
+    *outScene = s;
+    return TMPT_OK;
+}
+
+extern "C" void tmpt_scene_destroy(tmpt_scene* s) {
+    if (!s) return;
+    DeviceGuard guard(s->device);
+    if (s->stream) cudaStreamSynchronize(s->stream);
+    cudaFree(s->d_tris9); cudaFree(s->d_nodes); cudaFree(s->d_tris); cudaFree(s->d_status);
+    cudaFree(s->d_tileCounter); cudaFree(s->d_rayCount); cudaFree(s->d_frame);
+    if (s->ev0) cudaEventDestroy(s->ev0);
+    if (s->ev1) cudaEventDestroy(s->ev1);
+    if (s->stream) cudaStreamDestroy(s->stream);
+    delete s;
+}
+
+extern "C" int tmpt_scene_get_info(const tmpt_scene* s, tmpt_scene_info* out) {
+    if (!s || !out) return tmpt::fail(TMPT_ERR_ARG, "tmpt_scene_get_info: NULL argument");
+    *out = s->info;
+    return TMPT_OK;
+}
+
+static int check_status(const tmpt_scene* s, cudaStream_t st) {
+    uint32_t status = 0;
+    CU_TRY(cudaMemcpyAsync(&status, s->d_status, 4, cudaMemcpyDeviceToHost, st));
+    CU_TRY(cudaStreamSynchronize(st));
+    if (status & bvh::STACK_OVERFLOW) return tmpt::fail(TMPT_ERR_CUDA, "traversal stack overflow (BVH depth %d)", s->info.max_depth);
+    return TMPT_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// C ABI: HitScene
+// ------------------------------------------------------------------------------------------
+extern "C" int tmpt_hit_scene(const tmpt_scene* s, const float* rays6, int64_t nRays, float tMin, float tMax, int mode, int mem,
+                              int32_t* outID, float* outT, float* outPos3, float* outNormal3, void* stream) {
+    if (!s || nRays < 0 || (nRays > 0 && (!rays6 || !outID))) return tmpt::fail(TMPT_ERR_ARG, "tmpt_hit_scene: NULL scene / rays / outID");
+    if (mode != TMPT_HIT_CLOSEST && mode != TMPT_HIT_ANY && mode != TMPT_HIT_BRUTE) return tmpt::fail(TMPT_ERR_ARG, "tmpt_hit_scene: mode %d", mode);
+    if (mem != TMPT_HOST && mem != TMPT_DEVICE) return tmpt::fail(TMPT_ERR_ARG, "tmpt_hit_scene: mem %d", mem);
+    if (nRays == 0) return TMPT_OK;
+    DeviceGuard guard(s->device);
+    if (!guard.ok) return tmpt::fail(TMPT_ERR_CUDA, "tmpt_hit_scene: cudaSetDevice(%d) failed", s->device);
+    cudaStream_t st = stream ? (cudaStream_t)stream : s->stream;
+
+    const float* dRays = rays6; int* dID = outID; float* dT = outT; float* dPos = outPos3; float* dNrm = outNormal3;
+    DevBuf<float> bRays, bT, bPos, bNrm;
+    DevBuf<int> bID;
+    if (mem == TMPT_HOST) {
+        CU_TRY(bRays.alloc((size_t)nRays * 6)); CU_TRY(bID.alloc((size_t)nRays));
+        CU_TRY(cudaMemcpyAsync(bRays.p, rays6, (size_t)nRays * 6 * sizeof(float), cudaMemcpyHostToDevice, st));
+        dRays = bRays.p; dID = bID.p;
+        // outputs for misses must stay untouched: start from the caller's contents
+        if (outT) { CU_TRY(bT.alloc((size_t)nRays)); CU_TRY(cudaMemcpyAsync(bT.p, outT, (size_t)nRays * 4, cudaMemcpyHostToDevice, st)); dT = bT.p; }
+        if (outPos3) { CU_TRY(bPos.alloc((size_t)nRays * 3)); CU_TRY(cudaMemcpyAsync(bPos.p, outPos3, (size_t)nRays * 12, cudaMemcpyHostToDevice, st)); dPos = bPos.p; }
+        if (outNormal3) { CU_TRY(bNrm.alloc((size_t)nRays * 3)); CU_TRY(cudaMemcpyAsync(bNrm.p, outNormal3, (size_t)nRays * 12, cudaMemcpyHostToDevice, st)); dNrm = bNrm.p; }
+    }
+    const int B = 128;
+    const int G = (int)std::min<long long>(div_up(nRays, B), (long long)s->smCount * 64);
+    if (mode == TMPT_HIT_CLOSEST) LAUNCH(k_hit_scene<TMPT_HIT_CLOSEST>, G, B, 0, st, s->view, dRays, (long long)nRays, tMin, tMax, dID, dT, dPos, dNrm);
+    else if (mode == TMPT_HIT_ANY) LAUNCH(k_hit_scene<TMPT_HIT_ANY>, G, B, 0, st, s->view, dRays, (long long)nRays, tMin, tMax, dID, dT, dPos, dNrm);
+    else LAUNCH(k_hit_scene<TMPT_HIT_BRUTE>, G, B, 0, st, s->view, dRays, (long long)nRays, tMin, tMax, dID, dT, dPos, dNrm);
+    CU_TRY(cudaGetLastError());
+    if (mem == TMPT_HOST) {
+        CU_TRY(cudaMemcpyAsync(outID, dID, (size_t)nRays * 4, cudaMemcpyDeviceToHost, st));
+        if (outT) CU_TRY(cudaMemcpyAsync(outT, dT, (size_t)nRays * 4, cudaMemcpyDeviceToHost, st));
+        if (outPos3) CU_TRY(cudaMemcpyAsync(outPos3, dPos, (size_t)nRays * 12, cudaMemcpyDeviceToHost, st));
+        if (outNormal3) CU_TRY(cudaMemcpyAsync(outNormal3, dNrm, (size_t)nRays * 12, cudaMemcpyDeviceToHost, st));
+        CU_TRY(cudaStreamSynchronize(st));
+        return check_status(s, st);
+    }
+    return TMPT_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// C ABI: render
+// ------------------------------------------------------------------------------------------
+extern "C" int tmpt_stripe_rows(int height, int stripeRows, int rank, int worldSize) {
+    if (height <= 0 || stripeRows <= 0 || worldSize <= 0 || rank < 0 || rank >= worldSize) return 0;
+    const int stripes = (height + stripeRows - 1) / stripeRows;
+    int rows = 0;
+    for (int k = rank; k < stripes; k += worldSize) rows += std::min(stripeRows, height - k * stripeRows);
+    return rows;
+}
+
+static ex::V3 host_light_dir() { return ex::normalize(ex::v3(-0.7f, 1.0f, 0.5f)); }  // main.cpp:36
+
+static int launch_render(const tmpt_scene* s, const tmpt_camera* camera, int width, int height, int spp, int stripeRows, int rank, int world,
+                         uint8_t* outStripes, uint8_t* frame, unsigned long long* rayCountDev, cudaStream_t st) {
+    RenderParams p;
+    p.sc = s->view;
+    static_assert(sizeof(integ::Camera) == sizeof(tmpt_camera), "camera layout");
+    memcpy(&p.cam, camera, sizeof p.cam);
+    p.lightDir = host_light_dir();
+    p.width = width; p.height = height; p.spp = spp;
+    p.stripeRows = stripeRows; p.rank = rank; p.world = world;
+    p.ownedRows = tmpt_stripe_rows(height, stripeRows, rank, world);
+    p.tilesX = div_up(width, 8);
+    p.numTiles = p.tilesX * div_up(p.ownedRows, 4);
+    p.outStripes = (uchar4*)outStripes;
+    p.frame = (uchar4*)frame;
+    p.rayCount = rayCountDev;
+    p.tileCounter = s->d_tileCounter;
+    if (p.numTiles == 0) return TMPT_OK;
+    CU_TRY(cudaMemsetAsync(s->d_tileCounter, 0, sizeof(uint32_t), st));
+    int perSM = 0;
+    CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, k_render, 256, 0));
+    if (perSM < 1) perSM = 1;
+    const int grid = std::min(s->smCount * perSM, div_up(p.numTiles, 8));
+    LAUNCH(k_render, grid, 256, 0, st, p);
+    CU_TRY(cudaGetLastError());
+    return TMPT_OK;
+}
+
+static int check_render_args(const tmpt_scene* s, const tmpt_camera* camera, int width, int height, int spp) {
+    if (!s || !camera) return tmpt::fail(TMPT_ERR_ARG, "render: NULL scene / camera");
+    // the reference's own ranges (main.cpp:263-279)
+    if (width < 1 || width > 10000 || height < 1 || height > 10000 || spp < 1 || spp > 1024)
+        return tmpt::fail(TMPT_ERR_ARG, "render: width %d height %d spp %d out of range", width, height, spp);
+    return TMPT_OK;
+}
+
+extern "C" int tmpt_render_stripes(const tmpt_scene* s, const tmpt_camera* camera, int width, int height, int spp, int stripeRows, int rank,
+                                   int worldSize, uint8_t* outStripes, uint8_t* peerFrame, uint64_t* rayCountDev, void* stream) {
+    int rc = check_render_args(s, camera, width, height, spp);
+    if (rc != TMPT_OK) return rc;
+    if (stripeRows < 1 || worldSize < 1 || rank < 0 || rank >= worldSize || (!outStripes && !peerFrame) || !rayCountDev)
+        return tmpt::fail(TMPT_ERR_ARG, "tmpt_render_stripes: bad stripe arguments");
+    DeviceGuard guard(s->device);
+    if (!guard.ok) return tmpt::fail(TMPT_ERR_CUDA, "tmpt_render_stripes: cudaSetDevice(%d) failed", s->device);
+    return launch_render(s, camera, width, height, spp, stripeRows, rank, worldSize, outStripes, peerFrame,
+                         (unsigned long long*)rayCountDev, stream ? (cudaStream_t)stream : s->stream);
+}
+
+extern "C" int tmpt_render(const tmpt_scene* cs, const tmpt_camera* camera, int width, int height, int spp, int mem, uint8_t* rgba,
+                           uint64_t* rayCount, double* seconds, void* stream) {
+    int rc = check_render_args(cs, camera, width, height, spp);
+    if (rc != TMPT_OK) return rc;
+    if (!rgba) return tmpt::fail(TMPT_ERR_ARG, "tmpt_render: rgba is NULL");
+    if (mem != TMPT_HOST && mem != TMPT_DEVICE) return tmpt::fail(TMPT_ERR_ARG, "tmpt_render: mem %d", mem);
+    tmpt_scene* s = const_cast<tmpt_scene*>(cs);  // scratch buffers only; the scene data is immutable
+    DeviceGuard guard(s->device);
+    if (!guard.ok) return tmpt::fail(TMPT_ERR_CUDA, "tmpt_render: cudaSetDevice(%d) failed", s->device);
+    cudaStream_t st = stream ? (cudaStream_t)stream : s->stream;
+    const size_t bytes = (size_t)width * height * 4;
+    uint8_t* dFrame = rgba;
+    if (mem == TMPT_HOST) {
+        if (s->frameBytes < bytes) {
+            cudaFree(s->d_frame); s->d_frame = nullptr; s->frameBytes = 0;
+            CU_TRY(cudaMalloc((void**)&s->d_frame, bytes));
+            s->frameBytes = bytes;
+        }
+        dFrame = s->d_frame;
+    }
+    CU_TRY(cudaEventRecord(s->ev0, st));
+    CU_TRY(cudaMemsetAsync(s->d_rayCount, 0, sizeof(unsigned long long), st));
+    rc = launch_render(s, camera, width, height, spp, height, 0, 1, nullptr, dFrame, s->d_rayCount, st);
+    if (rc != TMPT_OK) return rc;
+    if (mem == TMPT_HOST) CU_TRY(cudaMemcpyAsync(rgba, dFrame, bytes, cudaMemcpyDeviceToHost, st));
+    CU_TRY(cudaEventRecord(s->ev1, st));
+    unsigned long long rays = 0;
+    CU_TRY(cudaMemcpyAsync(&rays, s->d_rayCount, sizeof rays, cudaMemcpyDeviceToHost, st));
+    CU_TRY(cudaStreamSynchronize(st));
+    float ms = 0.0f;
+    CU_TRY(cudaEventElapsedTime(&ms, s->ev0, s->ev1));
+    if (rayCount) *rayCount = rays;
+    if (seconds) *seconds = (double)ms * 1.0e-3;
+    return check_status(s, st);
+}
+
+extern "C" int tmpt_unpack_stripes(const uint8_t* gathered, int width, int height, int stripeRows, int worldSize, int device, uint8_t* frame,
+                                   void* stream) {
+    if (!gathered || !frame || width < 1 || height < 1 || stripeRows < 1 || worldSize < 1)
+        return tmpt::fail(TMPT_ERR_ARG, "tmpt_unpack_stripes: bad arguments");
+    DeviceGuard guard(device);
+    if (!guard.ok) return tmpt::fail(TMPT_ERR_CUDA, "tmpt_unpack_stripes: cudaSetDevice(%d) failed", device);
+    int maxRows = 0;
+    for (int r = 0; r < worldSize; ++r) maxRows = std::max(maxRows, tmpt_stripe_rows(height, stripeRows, r, worldSize));
+    const long long n = (long long)width * height;
+    LAUNCH(k_unpack_stripes, div_up(n, 256), 256, 0, (cudaStream_t)stream, (const uchar4*)gathered, width, height, stripeRows, worldSize, maxRows,
+           (uchar4*)frame);
+    CU_TRY(cudaGetLastError());
+    return TMPT_OK;
+}
