@@ -130,6 +130,14 @@ int tmpt_stripe_rows(int height, int stripeRows, int rank, int worldSize); /* ro
 int tmpt_unpack_stripes(const uint8_t* gathered, int width, int height, int stripeRows, int worldSize,
                         int device, uint8_t* frame, void* stream);
 
+/* Instrumented passes: the same kernels compiled with work counters, for the roofline's
+ * per-ray figures (never part of a timed run).  outStats: [0] rays (HitScene-equivalent
+ * queries), [1] wide BVH nodes visited (4 box tests each), [2] exact triangle tests,
+ * [3] hits (tmpt_hit_scene_stats only).  rays6Dev is a DEVICE pointer. */
+int tmpt_render_stats(const tmpt_scene* scene, const tmpt_camera* camera, int width, int height, int spp, uint64_t outStats[4]);
+int tmpt_hit_scene_stats(const tmpt_scene* scene, const float* rays6Dev, int64_t nRays, float tMin, float tMax, int mode,
+                         uint64_t outStats[4]);
+
 /* ---- host glue that main() does around the hot path ---- */
 /* LoadScene (main.cpp:122-170): parse the OBJ like external/objparser.cpp, build Triangle[]
  * plus the two floor triangles, report model bounds.  *outTris9 is malloc'ed; tmpt_free it. */

@@ -36,7 +36,7 @@ ABI_SYMBOLS = [
     "tmpt_scene_create", "tmpt_scene_destroy", "tmpt_scene_get_info", "tmpt_hit_scene", "tmpt_render",
     "tmpt_render_stripes", "tmpt_stripe_rows", "tmpt_unpack_stripes", "tmpt_load_obj", "tmpt_free",
     "tmpt_camera_make", "tmpt_camera_for_scene", "tmpt_write_png", "tmpt_main", "tmpt_last_error",
-    "tmpt_device_count", "tmpt_launch_count",
+    "tmpt_device_count", "tmpt_launch_count", "tmpt_render_stats", "tmpt_hit_scene_stats",
 ]
 
 
@@ -84,6 +84,8 @@ def lib() -> C.CDLL:
     L.tmpt_render_stripes.argtypes = [vp, vp, i32, i32, i32, i32, i32, i32, vp, vp, vp, vp]
     L.tmpt_stripe_rows.argtypes = [i32, i32, i32, i32]
     L.tmpt_unpack_stripes.argtypes = [vp, i32, i32, i32, i32, i32, vp, vp]
+    L.tmpt_render_stats.argtypes = [vp, vp, i32, i32, i32, vp]
+    L.tmpt_hit_scene_stats.argtypes = [vp, vp, i64, f32, f32, i32, vp]
     L.tmpt_load_obj.argtypes = [C.c_char_p, C.POINTER(C.POINTER(C.c_float)), C.POINTER(i32), vp, vp]
     L.tmpt_free.argtypes = [vp]
     L.tmpt_free.restype = None
@@ -220,6 +222,21 @@ class Scene:
         rays, sec = C.c_uint64(0), C.c_double(0.0)
         _check(lib().tmpt_render(self._h, _ptr(cam), width, height, spp, HOST, _ptr(rgba), C.byref(rays), C.byref(sec), None))
         return rgba, rays.value, sec.value
+
+    def traversal_stats(self, camera, width: int, height: int, spp: int) -> dict:
+        """Instrumented render pass -> mean box / triangle tests per ray (bench.py's roofline figures)."""
+        cam = _f32(camera).reshape(22)
+        st = np.zeros(4, np.uint64)
+        _check(lib().tmpt_render_stats(self._h, _ptr(cam), width, height, spp, _ptr(st)))
+        rays = max(int(st[0]), 1)
+        return {"rays": int(st[0]), "node_visits_per_ray": int(st[1]) / rays, "box_tests_per_ray": 4.0 * int(st[1]) / rays,
+                "tri_tests_per_ray": int(st[2]) / rays}
+
+    def hit_scene_stats(self, rays_ptr: int, n: int, mode: int = HIT_CLOSEST, tMin: float = K_MIN_T, tMax: float = K_MAX_T) -> dict:
+        st = np.zeros(4, np.uint64)
+        _check(lib().tmpt_hit_scene_stats(self._h, rays_ptr, n, tMin, tMax, mode, _ptr(st)))
+        rays = max(int(st[0]), 1)
+        return {"rays": int(st[0]), "node_visits_per_ray": int(st[1]) / rays, "tri_tests_per_ray": int(st[2]) / rays, "hit_rate": int(st[3]) / rays}
 
     def render_device(self, camera, width: int, height: int, spp: int, frame_ptr: int, stream: int = 0):
         """One frame into a device buffer (w*h*4 bytes) -> (rayCount, seconds)."""

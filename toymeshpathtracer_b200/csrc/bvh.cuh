@@ -113,13 +113,19 @@ TMPT_HD RaySlab make_slab(ex::V3 o, ex::V3 d) {
     return r;
 }
 
+// Work counters of an instrumented pass (bench.py's roofline: box and triangle tests per ray).
+struct TravStats {
+    unsigned long long nodes = 0;  // wide nodes visited (4 box tests each)
+    unsigned long long tris = 0;   // exact triangle tests
+};
+
 // One traversal, closest (ANY=false) or any-hit (ANY=true).
 //
 // Culling keeps a child when tNear <= tFar with tFar clipped to the CURRENT best t -- "<=",
 // not "<", so that a triangle in another leaf with bit-equal t and a lower index is still
 // tested.  The candidate rule is the lexicographic minimum of (t, id).
-template <bool ANY>
-TMPT_HD HitRec traverse(const SceneView& sc, ex::V3 o, ex::V3 d, float tMin, float tMax) {
+template <bool ANY, bool STATS = false>
+TMPT_HD HitRec traverse(const SceneView& sc, ex::V3 o, ex::V3 d, float tMin, float tMax, TravStats* stats = nullptr) {
     HitRec best;
     best.id = -1; best.t = tMax; best.u = 0.0f; best.v = 0.0f;
     const RaySlab rs = make_slab(o, d);
@@ -131,6 +137,7 @@ TMPT_HD HitRec traverse(const SceneView& sc, ex::V3 o, ex::V3 d, float tMin, flo
 
     while (cur != NONE) {
         if (!ref_is_leaf(cur)) {
+            if (STATS) ++stats->nodes;
             const float4* n = sc.nodes + (size_t)cur * 8;
             const float4 lox = TMPT_LDG4(n + 0), hix = TMPT_LDG4(n + 1);
             const float4 loy = TMPT_LDG4(n + 2), hiy = TMPT_LDG4(n + 3);
@@ -165,6 +172,7 @@ TMPT_HD HitRec traverse(const SceneView& sc, ex::V3 o, ex::V3 d, float tMin, flo
         } else {
             const uint32_t first = leaf_first(cur);
             const int cnt = leaf_count(cur);
+            if (STATS) stats->tris += (unsigned)cnt;
             for (int k = 0; k < cnt; ++k) {
                 const float4* tp = sc.tris + (size_t)(first + k) * 3;
                 const float4 a = TMPT_LDG4(tp + 0), b = TMPT_LDG4(tp + 1), c = TMPT_LDG4(tp + 2);

@@ -81,20 +81,20 @@ TMPT_HD uchar4 resolve_pixel(ex::V3 sum, float sppRecip) {
 // One whole pixel, serially: the straightforward form used by the host emulation and by the
 // first (non-wavefront) render kernel.  kk[] holds the per-bounce sun term (0 for a
 // shadowed bounce).
-template <class Scene>
+template <bool STATS = false, class Scene>
 TMPT_HD ex::V3 trace_path(const Scene& sc, const Camera& cam, ex::V3 o, ex::V3 d, ex::V3 lightDir, uint32_t& rng,
-                          unsigned long long& rays) {
+                          unsigned long long& rays, bvh::TravStats* stats = nullptr) {
     float kk[kMaxDepth];
     int depth = 0;
     ex::V3 color = ex::v3(0.0f, 0.0f, 0.0f);
     while (depth < kMaxDepth) {
         ++rays;
-        const bvh::HitRec h = bvh::traverse<false>(sc, o, d, kMinT, kMaxT);
+        const bvh::HitRec h = bvh::traverse<false, STATS>(sc, o, d, kMinT, kMaxT, stats);
         if (h.id < 0) { color = sky(d); break; }
         ex::V3 pos, normal;
         bvh::hit_payload(sc, h.id, h.u, h.v, pos, normal);
         ++rays;
-        const bvh::HitRec sh = bvh::traverse<true>(sc, pos, lightDir, kMinT, kMaxT);
+        const bvh::HitRec sh = bvh::traverse<true, STATS>(sc, pos, lightDir, kMinT, kMaxT, stats);
         kk[depth] = sh.id < 0 ? sun_term(normal, d, lightDir) : 0.0f;
         d = scatter_dir(pos, normal, rng);
         o = pos;
@@ -104,9 +104,9 @@ TMPT_HD ex::V3 trace_path(const Scene& sc, const Camera& cam, ex::V3 o, ex::V3 d
     return color;
 }
 
-template <class Scene>
+template <bool STATS = false, class Scene>
 TMPT_HD uchar4 render_pixel(const Scene& sc, const Camera& cam, int x, int y, int width, int height, int spp, ex::V3 lightDir,
-                            unsigned long long& rays, ex::V3* outLinear = nullptr) {
+                            unsigned long long& rays, ex::V3* outLinear = nullptr, bvh::TravStats* stats = nullptr) {
     const float invW = ex::divf(1.0f, (float)width), invH = ex::divf(1.0f, (float)height);
     const float sppRecip = ex::divf(1.0f, (float)spp);
     uint32_t rng = ex::pixel_seed((uint32_t)y * (uint32_t)width + (uint32_t)x);
@@ -114,7 +114,7 @@ TMPT_HD uchar4 render_pixel(const Scene& sc, const Camera& cam, int x, int y, in
     for (int s = 0; s < spp; ++s) {
         ex::V3 o, d;
         primary_ray(cam, x, y, invW, invH, rng, o, d);
-        sum = ex::add(sum, trace_path(sc, cam, o, d, lightDir, rng, rays));
+        sum = ex::add(sum, trace_path<STATS>(sc, cam, o, d, lightDir, rng, rays, stats));
     }
     if (outLinear) *outLinear = ex::muls(sum, sppRecip);
     return resolve_pixel(sum, sppRecip);

@@ -247,17 +247,29 @@ __global__ void k_collapse_root_leaf(bld::BinTree t, bld::WideOut w, int rootNod
 // ------------------------------------------------------------------------------------------
 // K2/K3: batched HitScene
 // ------------------------------------------------------------------------------------------
-template <int MODE>
+// stats[0] rays, [1] wide-node visits, [2] triangle tests, [3] hits
+__device__ __forceinline__ void flush_stats(unsigned long long* stats, unsigned long long rays, const bvh::TravStats& ts, unsigned long long hits) {
+    unsigned long long v[4] = {rays, ts.nodes, ts.tris, hits};
+    for (int k = 0; k < 4; ++k) {
+        for (int o = 16; o > 0; o >>= 1) v[k] += __shfl_xor_sync(0xffffffffu, v[k], o);
+        if ((threadIdx.x & 31) == 0 && v[k]) atomicAdd(&stats[k], v[k]);
+    }
+}
+
+template <int MODE, bool STATS>
 __global__ void __launch_bounds__(128) k_hit_scene(bvh::SceneView sc, const float* __restrict__ rays6, long long nRays, float tMin, float tMax,
                                                     int* __restrict__ outID, float* __restrict__ outT, float* __restrict__ outPos,
-                                                    float* __restrict__ outNormal) {
+                                                    float* __restrict__ outNormal, unsigned long long* __restrict__ stats) {
+    bvh::TravStats ts;
+    unsigned long long nr = 0, nh = 0;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nRays; i += (long long)gridDim.x * blockDim.x) {
         const float* r = rays6 + i * 6;
         const ex::V3 o = ex::v3(r[0], r[1], r[2]), d = ex::v3(r[3], r[4], r[5]);
         bvh::HitRec h;
         if (MODE == TMPT_HIT_BRUTE) h = bvh::brute_force(sc, o, d, tMin, tMax);
-        else if (MODE == TMPT_HIT_ANY) h = bvh::traverse<true>(sc, o, d, tMin, tMax);
-        else h = bvh::traverse<false>(sc, o, d, tMin, tMax);
+        else if (MODE == TMPT_HIT_ANY) h = bvh::traverse<true, STATS>(sc, o, d, tMin, tMax, &ts);
+        else h = bvh::traverse<false, STATS>(sc, o, d, tMin, tMax, &ts);
+        if (STATS) { ++nr; nh += h.id >= 0; }
         if (MODE == TMPT_HIT_ANY) { outID[i] = h.id < 0 ? -1 : 1; continue; }
         outID[i] = h.id;
         if (h.id >= 0) {
@@ -270,6 +282,7 @@ __global__ void __launch_bounds__(128) k_hit_scene(bvh::SceneView sc, const floa
             }
         }
     }
+    if (STATS) flush_stats(stats, nr, ts, nh);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -288,6 +301,7 @@ struct RenderParams {
     uchar4* frame;       // full frame (possibly peer memory)
     unsigned long long* rayCount;
     uint32_t* tileCounter;
+    unsigned long long* stats;  // instrumented pass only
 };
 
 __device__ __forceinline__ int owned_row_to_global(int r, int stripeRows, int rank, int world) {
@@ -295,9 +309,11 @@ __device__ __forceinline__ int owned_row_to_global(int r, int stripeRows, int ra
     return (ls * world + rank) * stripeRows + (r - ls * stripeRows);
 }
 
+template <bool STATS>
 __global__ void __launch_bounds__(256) k_render(const RenderParams p) {
     const int lane = threadIdx.x & 31;
     unsigned long long rays = 0;
+    bvh::TravStats ts;
     for (;;) {
         uint32_t tile = 0;
         if (lane == 0) tile = atomicAdd(p.tileCounter, 1u);
@@ -307,11 +323,12 @@ __global__ void __launch_bounds__(256) k_render(const RenderParams p) {
         const int x = tx * 8 + (lane & 7), r = ty * 4 + (lane >> 3);
         if (x < p.width && r < p.ownedRows) {
             const int y = owned_row_to_global(r, p.stripeRows, p.rank, p.world);
-            const uchar4 px = integ::render_pixel(p.sc, p.cam, x, y, p.width, p.height, p.spp, p.lightDir, rays);
+            const uchar4 px = integ::render_pixel<STATS>(p.sc, p.cam, x, y, p.width, p.height, p.spp, p.lightDir, rays, nullptr, &ts);
             if (p.frame) p.frame[(size_t)y * p.width + x] = px;
             else p.outStripes[(size_t)r * p.width + x] = px;
         }
     }
+    if (STATS) flush_stats(p.stats, rays, ts, 0);
     for (int o = 16; o > 0; o >>= 1) rays += __shfl_xor_sync(0xffffffffu, rays, o);
     if (lane == 0 && rays) atomicAdd(p.rayCount, rays);
 }
@@ -560,9 +577,9 @@ extern "C" int tmpt_hit_scene(const tmpt_scene* s, const float* rays6, int64_t n
     }
     const int B = 128;
     const int G = (int)std::min<long long>(div_up(nRays, B), (long long)s->smCount * 64);
-    if (mode == TMPT_HIT_CLOSEST) LAUNCH(k_hit_scene<TMPT_HIT_CLOSEST>, G, B, 0, st, s->view, dRays, (long long)nRays, tMin, tMax, dID, dT, dPos, dNrm);
-    else if (mode == TMPT_HIT_ANY) LAUNCH(k_hit_scene<TMPT_HIT_ANY>, G, B, 0, st, s->view, dRays, (long long)nRays, tMin, tMax, dID, dT, dPos, dNrm);
-    else LAUNCH(k_hit_scene<TMPT_HIT_BRUTE>, G, B, 0, st, s->view, dRays, (long long)nRays, tMin, tMax, dID, dT, dPos, dNrm);
+    if (mode == TMPT_HIT_CLOSEST) LAUNCH((k_hit_scene<TMPT_HIT_CLOSEST, false>), G, B, 0, st, s->view, dRays, (long long)nRays, tMin, tMax, dID, dT, dPos, dNrm, nullptr);
+    else if (mode == TMPT_HIT_ANY) LAUNCH((k_hit_scene<TMPT_HIT_ANY, false>), G, B, 0, st, s->view, dRays, (long long)nRays, tMin, tMax, dID, dT, dPos, dNrm, nullptr);
+    else LAUNCH((k_hit_scene<TMPT_HIT_BRUTE, false>), G, B, 0, st, s->view, dRays, (long long)nRays, tMin, tMax, dID, dT, dPos, dNrm, nullptr);
     CU_TRY(cudaGetLastError());
     if (mem == TMPT_HOST) {
         CU_TRY(cudaMemcpyAsync(outID, dID, (size_t)nRays * 4, cudaMemcpyDeviceToHost, st));
@@ -589,7 +606,8 @@ extern "C" int tmpt_stripe_rows(int height, int stripeRows, int rank, int worldS
 static ex::V3 host_light_dir() { return ex::normalize(ex::v3(-0.7f, 1.0f, 0.5f)); }  // main.cpp:36
 
 static int launch_render(const tmpt_scene* s, const tmpt_camera* camera, int width, int height, int spp, int stripeRows, int rank, int world,
-                         uint8_t* outStripes, uint8_t* frame, unsigned long long* rayCountDev, cudaStream_t st) {
+                         uint8_t* outStripes, uint8_t* frame, unsigned long long* rayCountDev, cudaStream_t st,
+                         unsigned long long* statsDev = nullptr) {
     RenderParams p;
     p.sc = s->view;
     static_assert(sizeof(integ::Camera) == sizeof(tmpt_camera), "camera layout");
@@ -604,13 +622,15 @@ static int launch_render(const tmpt_scene* s, const tmpt_camera* camera, int wid
     p.frame = (uchar4*)frame;
     p.rayCount = rayCountDev;
     p.tileCounter = s->d_tileCounter;
+    p.stats = statsDev;
     if (p.numTiles == 0) return TMPT_OK;
     CU_TRY(cudaMemsetAsync(s->d_tileCounter, 0, sizeof(uint32_t), st));
     int perSM = 0;
-    CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, k_render, 256, 0));
+    CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, k_render<false>, 256, 0));
     if (perSM < 1) perSM = 1;
     const int grid = std::min(s->smCount * perSM, div_up(p.numTiles, 8));
-    LAUNCH(k_render, grid, 256, 0, st, p);
+    if (statsDev) LAUNCH(k_render<true>, grid, 256, 0, st, p);
+    else LAUNCH(k_render<false>, grid, 256, 0, st, p);
     CU_TRY(cudaGetLastError());
     return TMPT_OK;
 }
@@ -669,6 +689,50 @@ extern "C" int tmpt_render(const tmpt_scene* cs, const tmpt_camera* camera, int 
     if (rayCount) *rayCount = rays;
     if (seconds) *seconds = (double)ms * 1.0e-3;
     return check_status(s, st);
+}
+
+// Instrumented passes (same kernels compiled with counters; never part of a timed run).
+extern "C" int tmpt_render_stats(const tmpt_scene* cs, const tmpt_camera* camera, int width, int height, int spp, uint64_t outStats[4]) {
+    int rc = check_render_args(cs, camera, width, height, spp);
+    if (rc != TMPT_OK) return rc;
+    if (!outStats) return tmpt::fail(TMPT_ERR_ARG, "tmpt_render_stats: outStats is NULL");
+    tmpt_scene* s = const_cast<tmpt_scene*>(cs);
+    DeviceGuard guard(s->device);
+    if (!guard.ok) return tmpt::fail(TMPT_ERR_CUDA, "tmpt_render_stats: cudaSetDevice(%d) failed", s->device);
+    cudaStream_t st = s->stream;
+    const size_t bytes = (size_t)width * height * 4;
+    DevBuf<uint8_t> frame;
+    DevBuf<unsigned long long> stats;
+    CU_TRY(frame.alloc(bytes));
+    CU_TRY(stats.alloc(4));
+    CU_TRY(cudaMemsetAsync(stats.p, 0, 4 * sizeof(unsigned long long), st));
+    CU_TRY(cudaMemsetAsync(s->d_rayCount, 0, sizeof(unsigned long long), st));
+    rc = launch_render(s, camera, width, height, spp, height, 0, 1, nullptr, frame.p, s->d_rayCount, st, stats.p);
+    if (rc != TMPT_OK) return rc;
+    CU_TRY(cudaMemcpyAsync(outStats, stats.p, 4 * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+    CU_TRY(cudaStreamSynchronize(st));
+    return TMPT_OK;
+}
+
+extern "C" int tmpt_hit_scene_stats(const tmpt_scene* s, const float* rays6Dev, int64_t nRays, float tMin, float tMax, int mode, uint64_t outStats[4]) {
+    if (!s || !rays6Dev || nRays <= 0 || !outStats || (mode != TMPT_HIT_CLOSEST && mode != TMPT_HIT_ANY))
+        return tmpt::fail(TMPT_ERR_ARG, "tmpt_hit_scene_stats: bad arguments");
+    DeviceGuard guard(s->device);
+    if (!guard.ok) return tmpt::fail(TMPT_ERR_CUDA, "tmpt_hit_scene_stats: cudaSetDevice(%d) failed", s->device);
+    cudaStream_t st = s->stream;
+    DevBuf<unsigned long long> stats;
+    DevBuf<int> ids;
+    CU_TRY(stats.alloc(4));
+    CU_TRY(ids.alloc((size_t)nRays));
+    CU_TRY(cudaMemsetAsync(stats.p, 0, 4 * sizeof(unsigned long long), st));
+    const int B = 128;
+    const int G = (int)std::min<long long>(div_up(nRays, B), (long long)s->smCount * 64);
+    if (mode == TMPT_HIT_CLOSEST) LAUNCH((k_hit_scene<TMPT_HIT_CLOSEST, true>), G, B, 0, st, s->view, rays6Dev, (long long)nRays, tMin, tMax, ids.p, nullptr, nullptr, nullptr, stats.p);
+    else LAUNCH((k_hit_scene<TMPT_HIT_ANY, true>), G, B, 0, st, s->view, rays6Dev, (long long)nRays, tMin, tMax, ids.p, nullptr, nullptr, nullptr, stats.p);
+    CU_TRY(cudaGetLastError());
+    CU_TRY(cudaMemcpyAsync(outStats, stats.p, 4 * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+    CU_TRY(cudaStreamSynchronize(st));
+    return TMPT_OK;
 }
 
 extern "C" int tmpt_unpack_stripes(const uint8_t* gathered, int width, int height, int stripeRows, int worldSize, int device, uint8_t* frame,
