@@ -37,7 +37,7 @@ void* emu_scene_create(const float* tris9, int n) {
     EmuScene* s = new EmuScene();
     s->n = n;
     s->tris9.assign(tris9, tris9 + (size_t)n * 9);
-    s->nodes.assign((size_t)std::max(n, 1) * 8, make_float4(0, 0, 0, 0));
+    s->nodes.assign((size_t)std::max(n, 1) * bvh::NODE_F4, make_float4(0, 0, 0, 0));
     s->tris.assign((size_t)std::max(n, 1) * 3, make_float4(0, 0, 0, 0));
     s->view = bvh::SceneView{s->nodes.data(), s->tris.data(), s->tris9.data(), n ? 0u : bvh::NONE, n, &s->status};
     if (n == 0) return s;
@@ -112,7 +112,7 @@ void emu_scene_info(void* h, uint32_t out[5]) {
 }
 int emu_nodes(void* h, float* out) {
     EmuScene* s = (EmuScene*)h;
-    if (out) memcpy(out, s->nodes.data(), (size_t)s->counters[0] * 128);
+    if (out) memcpy(out, s->nodes.data(), (size_t)s->counters[0] * bvh::NODE_F4 * 16);
     return (int)s->counters[0];
 }
 void emu_slots(void* h, float* out) {

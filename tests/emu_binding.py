@@ -64,7 +64,7 @@ class EmuScene:
 
     def nodes(self):
         n = self.L.emu_nodes(self.h, None)
-        out = np.zeros((n, 8, 4), np.float32)
+        out = np.zeros((n, 7, 4), np.float32)
         self.L.emu_nodes(self.h, _p(out))
         return out
 

@@ -166,7 +166,7 @@ TMPT_HD void refit_node(const BinTree& t, int i, const SahParams& sp) {
 
 // ---- collapse: binary -> 4-wide ----
 struct WideOut {
-    float4* nodes;         // 8 float4 per wide node
+    float4* nodes;         // bvh::NODE_F4 float4 per wide node
     float4* tris;          // 3 float4 per slot
     const float* tris9;    // original triangles
     const uint32_t* prim;  // sorted position -> original index
@@ -294,7 +294,7 @@ TMPT_HD void collapse_node(const BinTree& t, const WideOut& w, const WorkItem& i
         }
     }
     counter_max(&w.counters[3], (uint32_t)it.depth);
-    float4* o = w.nodes + (size_t)it.wide * 8;
+    float4* o = w.nodes + (size_t)it.wide * bvh::NODE_F4;
     o[0] = make_float4(lox[0], lox[1], lox[2], lox[3]);
     o[1] = make_float4(hix[0], hix[1], hix[2], hix[3]);
     o[2] = make_float4(loy[0], loy[1], loy[2], loy[3]);
@@ -302,7 +302,6 @@ TMPT_HD void collapse_node(const BinTree& t, const WideOut& w, const WorkItem& i
     o[4] = make_float4(loz[0], loz[1], loz[2], loz[3]);
     o[5] = make_float4(hiz[0], hiz[1], hiz[2], hiz[3]);
     o[6] = make_float4(ex::u2f(refs[0]), ex::u2f(refs[1]), ex::u2f(refs[2]), ex::u2f(refs[3]));
-    o[7] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
 }
 
 // Root special case: the whole scene is one leaf (n <= maxLeaf and SAH says so, or n == 1).
@@ -319,7 +318,6 @@ TMPT_HD void emit_single_leaf_root(const BinTree& t, const WideOut& w, int rootN
     o[2] = make_float4(lo.y, F, F, F); o[3] = make_float4(hi.y, F, F, F);
     o[4] = make_float4(lo.z, F, F, F); o[5] = make_float4(hi.z, F, F, F);
     o[6] = make_float4(ex::u2f(bvh::make_leaf_ref(first, cnt)), ex::u2f(bvh::NONE), ex::u2f(bvh::NONE), ex::u2f(bvh::NONE));
-    o[7] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
     accum_add(&w.sahAccum[1], box_half_area(Box{lo.x, lo.y, lo.z, hi.x, hi.y, hi.z}) * (float)cnt);
 }
 

@@ -7,9 +7,14 @@
 // t go to the lowest ORIGINAL triangle index, whatever order the tree is walked in.
 //
 // Layout (all 16-byte aligned, read with 128-bit loads, L2-resident at every config):
-//   nodes : 4-wide BVH, one node = one 128-byte line = 8 x float4, children SoA:
+//   nodes : 4-wide BVH, one node = 7 x float4 = 112 bytes, children SoA:
 //             [0] lo.x[4] [1] hi.x[4] [2] lo.y[4] [3] hi.y[4] [4] lo.z[4] [5] hi.z[4]
-//             [6] child refs[4] (bit-cast)   [7] reserved
+//             [6] child refs[4] (bit-cast)
+//           The 112-byte stride is deliberate: every lane of a warp loads the SAME row of a
+//           DIFFERENT node, and with a 128-byte stride all those 16-byte pieces sit at the same
+//           offset of their L1 line -> same data banks -> one L1 wavefront per lane (ncu:
+//           l1tex__data_pipe_lsu_wavefronts at 78 % of peak, profiles/).  At 112 bytes the row
+//           offset rotates with the node index and the lanes spread over the banks.
 //           child ref: bit 31 clear -> index of an inner node
 //                      bit 31 set   -> leaf: bits 28..30 = triCount-1, bits 0..27 = first slot
 //           an unused child has ref 0xFFFFFFFF and a far-away point box; it is never entered.
@@ -34,6 +39,7 @@ namespace bvh {
 constexpr uint32_t LEAF_BIT = 0x80000000u;
 constexpr int MAX_LEAF_TRIS = 8;
 constexpr int WIDTH = 4;
+constexpr int NODE_F4 = 7;              // float4 rows per node (112 bytes)
 constexpr int STACK_SIZE = 64;         // entries; the builder reports the depth it needs
 constexpr uint32_t NONE = 0xFFFFFFFFu;     // empty child / empty stack; no leaf ref reaches it (slots < 2^28 - 1)
 constexpr uint32_t STACK_OVERFLOW = 1;  // bit in the scene's device status word
@@ -44,7 +50,7 @@ TMPT_HD int leaf_count(uint32_t r) { return int((r >> 28) & 7u) + 1; }
 TMPT_HD uint32_t leaf_first(uint32_t r) { return r & 0x0FFFFFFFu; }
 
 struct SceneView {
-    const float4* nodes;  // 8 float4 per node
+    const float4* nodes;  // NODE_F4 float4 per node
     const float4* tris;   // 3 float4 per slot
     const float* tris9;   // original triangles
     uint32_t rootRef;     // may itself be a leaf ref for tiny scenes
@@ -138,7 +144,7 @@ TMPT_HD HitRec traverse(const SceneView& sc, ex::V3 o, ex::V3 d, float tMin, flo
     while (cur != NONE) {
         if (!ref_is_leaf(cur)) {
             if (STATS) ++stats->nodes;
-            const float4* n = sc.nodes + (size_t)cur * 8;
+            const float4* n = sc.nodes + (size_t)cur * NODE_F4;
             const float4 lox = TMPT_LDG4(n + 0), hix = TMPT_LDG4(n + 1);
             const float4 loy = TMPT_LDG4(n + 2), hiy = TMPT_LDG4(n + 3);
             const float4 loz = TMPT_LDG4(n + 4), hiz = TMPT_LDG4(n + 5);

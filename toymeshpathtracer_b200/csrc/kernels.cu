@@ -23,6 +23,8 @@
 #include "build_logic.cuh"
 #include "common.h"
 #include "integrator.cuh"
+#include "trace.cuh"
+#include "warpq.cuh"
 
 // ------------------------------------------------------------------------------------------
 // error plumbing
@@ -79,6 +81,7 @@ struct tmpt_scene {
     // render scratch
     uint32_t* d_tileCounter = nullptr;
     unsigned long long* d_rayCount = nullptr;
+    unsigned long long* d_fetchCounter = nullptr;  // ray queue head of the persistent HitScene kernel
     uint8_t* d_frame = nullptr;
     size_t frameBytes = 0;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -285,6 +288,156 @@ __global__ void __launch_bounds__(128) k_hit_scene(bvh::SceneView sc, const floa
     if (STATS) flush_stats(stats, nr, ts, nh);
 }
 
+// Persistent form of K2/K3: warps stay resident and every lane that finishes its ray is handed
+// the next one from a global counter (warp-aggregated atomic), so lanes do not idle while
+// their neighbours finish long rays.  FETCH_BELOW: refill when fewer lanes than this are busy.
+template <bool STATS, int FETCH_BELOW>
+__global__ void __launch_bounds__(128) k_hit_scene_persist(bvh::SceneView sc, const float* __restrict__ rays6, long long nRays, float tMin, float tMax,
+                                                            int anyHit, int* __restrict__ outID, float* __restrict__ outT, float* __restrict__ outPos,
+                                                            float* __restrict__ outNormal, unsigned long long* __restrict__ counter,
+                                                            unsigned long long* __restrict__ stats) {
+    const unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    uint32_t stackRef[trc::STACK];
+    float stackT[trc::STACK];
+    trc::Lane L;
+    L.id = -1; L.t = tMax; L.u = L.v = 0.0f;
+    long long ray = -1;
+    bool exhausted = false, alive = false;
+    bvh::TravStats ts;
+    unsigned long long nr = 0, nh = 0;
+    for (;;) {
+        const bool need = ray < 0;
+        const unsigned needMask = __ballot_sync(FULL, need);
+        if (needMask && !exhausted) {
+            const int cnt = __popc(needMask);
+            unsigned long long base = 0;
+            if (lane == 0) base = atomicAdd(counter, (unsigned long long)cnt);
+            base = __shfl_sync(FULL, base, 0);
+            if (need) {
+                const long long i = (long long)base + __popc(needMask & ((1u << lane) - 1u));
+                if (i < nRays) {
+                    const float* r = rays6 + i * 6;
+                    alive = trc::lane_start(L, ex::v3(r[0], r[1], r[2]), ex::v3(r[3], r[4], r[5]), tMin, tMax, anyHit != 0, sc.rootRef);
+                    ray = i;
+                }
+            }
+            exhausted = (long long)base + cnt >= nRays;
+        }
+        if (__all_sync(FULL, ray < 0)) break;
+        if (ray >= 0) {
+            while (alive) {
+                alive = trc::lane_step<STATS>(L, sc, stackRef, stackT, &ts);
+                if (!exhausted && __popc(__activemask()) < FETCH_BELOW) break;
+            }
+            if (!alive) {
+                if (STATS) { ++nr; nh += L.id >= 0; }
+                if (anyHit) outID[ray] = L.id < 0 ? -1 : 1;
+                else {
+                    outID[ray] = L.id;
+                    if (L.id >= 0) {
+                        if (outT) outT[ray] = L.t;
+                        if (outPos || outNormal) {
+                            ex::V3 pos, nrm;
+                            bvh::hit_payload(sc, L.id, L.u, L.v, pos, nrm);
+                            if (outPos) { outPos[ray * 3] = pos.x; outPos[ray * 3 + 1] = pos.y; outPos[ray * 3 + 2] = pos.z; }
+                            if (outNormal) { outNormal[ray * 3] = nrm.x; outNormal[ray * 3 + 1] = nrm.y; outNormal[ray * 3 + 2] = nrm.z; }
+                        }
+                    }
+                }
+                ray = -1;
+            }
+        }
+    }
+    if (STATS) flush_stats(stats, nr, ts, nh);
+}
+
+// Warp-queue form of K2/K3 (warpq.cuh): lanes walk inner nodes, triangles are tested 32 pairs
+// at a time by the whole warp, finished lanes are refilled from the global ray counter.
+template <bool STATS, int REFILL_MIN, int NODE_MIN>
+__global__ void __launch_bounds__(128) k_hit_scene_wq(bvh::SceneView sc, const float* __restrict__ rays6, long long nRays, float tMin, float tMax,
+                                                       int anyHit, int* __restrict__ outID, float* __restrict__ outT, float* __restrict__ outPos,
+                                                       float* __restrict__ outNormal, unsigned long long* __restrict__ counter,
+                                                       unsigned long long* __restrict__ stats) {
+    __shared__ wq::WarpShared shared[4];
+    wq::WarpShared& ws = shared[threadIdx.x >> 5];
+    const unsigned FULL = wq::FULL;
+    const int lane = threadIdx.x & 31;
+    uint32_t stackRef[wq::STACK];
+    float stackT[wq::STACK];
+    wq::Lane L;
+    L.cur = bvh::NONE; L.sp = 0; L.lastTail = 0; L.any = anyHit != 0;
+    uint32_t head = 0, tail = 0;  // ring positions (warp-uniform)
+    const unsigned anyMask = anyHit ? FULL : 0u;
+    long long ray = -1;
+    bool exhausted = false;
+    bvh::TravStats ts;
+    unsigned long long nr = 0, nh = 0;
+    for (;;) {
+        // ---- A. retire finished lanes, refill idle ones
+        if (ray >= 0 && L.cur == bvh::NONE && L.sp == 0 && (int)(head - L.lastTail) >= 0) {
+            const unsigned long long key = ws.best[lane];
+            const int id = wq::key_id(key);
+            const bool hit = anyHit ? key == 0ull : id >= 0;
+            if (STATS) { ++nr; nh += hit; }
+            if (anyHit) outID[ray] = hit ? 1 : -1;
+            else {
+                outID[ray] = id;
+                if (hit) {
+                    if (outT) outT[ray] = wq::key_t(key);
+                    if (outPos || outNormal) {
+                        // u, v of the winning triangle: the exact test once more, on the original vertices (same bits)
+                        const float* q = sc.tris9 + (size_t)id * 9;
+                        const ex::V3 v0 = ex::v3(q[0], q[1], q[2]), v1 = ex::v3(q[3], q[4], q[5]), v2 = ex::v3(q[6], q[7], q[8]);
+                        float t, u, v;
+                        bvh::mt_exact(ex::v3(ws.ox[lane], ws.oy[lane], ws.oz[lane]), ex::v3(ws.dx[lane], ws.dy[lane], ws.dz[lane]), v0,
+                                      ex::sub(v1, v0), ex::sub(v2, v0), tMin, tMax, t, u, v);
+                        ex::V3 pos, nrm;
+                        bvh::hit_payload(sc, id, u, v, pos, nrm);
+                        if (outPos) { outPos[ray * 3] = pos.x; outPos[ray * 3 + 1] = pos.y; outPos[ray * 3 + 2] = pos.z; }
+                        if (outNormal) { outNormal[ray * 3] = nrm.x; outNormal[ray * 3 + 1] = nrm.y; outNormal[ray * 3 + 2] = nrm.z; }
+                    }
+                }
+            }
+            ray = -1;
+        }
+        const unsigned idle = __ballot_sync(FULL, ray < 0);
+        if (!exhausted && (__popc(idle) >= REFILL_MIN || idle == FULL)) {
+            const int cnt = __popc(idle);
+            unsigned long long base = 0;
+            if (lane == 0) base = atomicAdd(counter, (unsigned long long)cnt);
+            base = __shfl_sync(FULL, base, 0);
+            if (ray < 0) {
+                const long long i = (long long)base + __popc(idle & ((1u << lane) - 1u));
+                if (i < nRays) {
+                    const float* r = rays6 + i * 6;
+                    wq::lane_start(L, ws, lane, ex::v3(r[0], r[1], r[2]), ex::v3(r[3], r[4], r[5]), tMax, anyHit != 0, sc.rootRef, tail);
+                    ray = i;
+                }
+            }
+            exhausted = (long long)base + cnt >= nRays;
+        }
+        __syncwarp();
+        if (__all_sync(FULL, ray < 0)) break;  // nothing in flight and nothing left to fetch
+        // ---- B. one inner-node step per lane that has one
+        const float bestT = ray >= 0 ? wq::key_t(ws.best[lane]) : 0.0f;
+        if (ray >= 0) {
+            if (L.cur == bvh::NONE) L.cur = wq::pop(L, stackRef, stackT, bestT);
+            if (L.cur != bvh::NONE && !bvh::ref_is_leaf(L.cur)) wq::node_step<STATS>(L, sc, stackRef, stackT, tMin, bestT, &ts);
+        }
+        // ---- C. lanes standing at a leaf queue its triangles and move on
+        const bool atLeaf = ray >= 0 && L.cur != bvh::NONE && bvh::ref_is_leaf(L.cur);
+        if (__any_sync(FULL, atLeaf)) {
+            wq::enqueue_leaves<STATS>(ws, sc, lane, atLeaf, L.cur, head, tail, L.lastTail, tMin, tMax, anyMask, &ts);
+            if (atLeaf) L.cur = bvh::NONE;  // popped at the top of the next iteration, against a fresher best t
+        }
+        // ---- D. exact tests: full passes, or a partial one when too few lanes have node work left
+        const int walkers = __popc(__ballot_sync(FULL, ray >= 0 && (L.cur != bvh::NONE || L.sp > 0)));
+        while (tail - head >= 32u || (tail != head && walkers < NODE_MIN)) wq::tri_pass<STATS>(ws, sc, lane, head, tail, tMin, tMax, anyMask, &ts);
+    }
+    if (STATS) flush_stats(stats, nr, ts, nh);
+}
+
 // ------------------------------------------------------------------------------------------
 // K4: path tracing.  Work unit = an 8x4 pixel tile per warp, fetched from a global counter
 // (persistent CTAs); each lane owns one pixel and runs its samples serially because the
@@ -372,7 +525,7 @@ int build_bvh(tmpt_scene* s, unsigned flags) {
     CU_TRY(left.alloc(n)); CU_TRY(right.alloc(n)); CU_TRY(parent.alloc(2 * (size_t)n));
     CU_TRY(lo.alloc(2 * (size_t)n)); CU_TRY(hi.alloc(2 * (size_t)n)); CU_TRY(sah.alloc(2));
     CU_TRY(qA.alloc(n)); CU_TRY(qB.alloc(n));
-    CU_TRY(cudaMalloc((void**)&s->d_nodes, (size_t)n * 8 * sizeof(float4)));
+    CU_TRY(cudaMalloc((void**)&s->d_nodes, (size_t)n * bvh::NODE_F4 * sizeof(float4)));
     CU_TRY(cudaMalloc((void**)&s->d_tris, (size_t)n * 3 * sizeof(float4)));
 
     const uint32_t initBounds[6] = {0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0u, 0u, 0u};
@@ -448,7 +601,7 @@ int build_bvh(tmpt_scene* s, unsigned flags) {
         s->info.sah_cost = rootArea > 0.0f ? (cInner * hs[0] + cTri * hs[1]) / rootArea : 0.0f;
     }
     if ((int)hc[1] != n) return tmpt::fail(TMPT_ERR_CUDA, "BVH build lost triangles: %u slots for %d triangles", hc[1], n);
-    s->info.device_bytes = (uint64_t)n * 9 * 4 + (uint64_t)hc[0] * 128 + (uint64_t)n * 48;
+    s->info.device_bytes = (uint64_t)n * 9 * 4 + (uint64_t)hc[0] * bvh::NODE_F4 * 16 + (uint64_t)n * 48;
     s->view.nodes = s->d_nodes;
     s->view.tris = s->d_tris;
     s->view.tris9 = s->d_tris9;
@@ -502,6 +655,7 @@ extern "C" int tmpt_scene_create(const float* tris9, int triCount, int device, u
         CU_TRY(cudaMemsetAsync(s->d_status, 0, 4 * sizeof(uint32_t), s->stream));
         CU_TRY(cudaMalloc((void**)&s->d_tileCounter, sizeof(uint32_t)));
         CU_TRY(cudaMalloc((void**)&s->d_rayCount, sizeof(unsigned long long)));
+        CU_TRY(cudaMalloc((void**)&s->d_fetchCounter, sizeof(unsigned long long)));
         CU_TRY(cudaEventRecord(s->ev0, s->stream));
         if (triCount > 0) {
             CU_TRY(cudaMalloc((void**)&s->d_tris9, (size_t)triCount * 9 * sizeof(float)));
@@ -529,7 +683,7 @@ extern "C" void tmpt_scene_destroy(tmpt_scene* s) {
     DeviceGuard guard(s->device);
     if (s->stream) cudaStreamSynchronize(s->stream);
     cudaFree(s->d_tris9); cudaFree(s->d_nodes); cudaFree(s->d_tris); cudaFree(s->d_status);
-    cudaFree(s->d_tileCounter); cudaFree(s->d_rayCount); cudaFree(s->d_frame);
+    cudaFree(s->d_tileCounter); cudaFree(s->d_rayCount); cudaFree(s->d_fetchCounter); cudaFree(s->d_frame);
     if (s->ev0) cudaEventDestroy(s->ev0);
     if (s->ev1) cudaEventDestroy(s->ev1);
     if (s->stream) cudaStreamDestroy(s->stream);
@@ -577,7 +731,37 @@ extern "C" int tmpt_hit_scene(const tmpt_scene* s, const float* rays6, int64_t n
     }
     const int B = 128;
     const int G = (int)std::min<long long>(div_up(nRays, B), (long long)s->smCount * 64);
-    if (mode == TMPT_HIT_CLOSEST) LAUNCH((k_hit_scene<TMPT_HIT_CLOSEST, false>), G, B, 0, st, s->view, dRays, (long long)nRays, tMin, tMax, dID, dT, dPos, dNrm, nullptr);
+    static const int variant = getenv("TMPT_HIT_KERNEL") ? atoi(getenv("TMPT_HIT_KERNEL")) : 0;
+    if (variant > 0 && mode != TMPT_HIT_BRUTE) {
+        int perSM = 0;
+        CU_TRY(cudaMemsetAsync(s->d_fetchCounter, 0, sizeof(unsigned long long), st));
+#define WQ_CASE(V, R, N)                                                                                                        \
+        if (variant == V) {                                                                                                     \
+            CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, k_hit_scene_wq<false, R, N>, B, 0));                       \
+            const int GP = (int)std::min<long long>(div_up(nRays, B), (long long)s->smCount * std::max(perSM, 1));              \
+            LAUNCH((k_hit_scene_wq<false, R, N>), GP, B, 0, st, s->view, dRays, (long long)nRays, tMin, tMax, mode == TMPT_HIT_ANY, dID, dT, \
+                   dPos, dNrm, s->d_fetchCounter, nullptr);                                                                     \
+        } else
+        WQ_CASE(5, 8, 12) WQ_CASE(6, 4, 8) WQ_CASE(7, 8, 20) WQ_CASE(8, 16, 12) WQ_CASE(9, 1, 12)
+#undef WQ_CASE
+        if (variant == 1) {
+            CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, k_hit_scene_persist<false, 24>, B, 0));
+            const int GP = (int)std::min<long long>(div_up(nRays, B), (long long)s->smCount * std::max(perSM, 1));
+            LAUNCH((k_hit_scene_persist<false, 24>), GP, B, 0, st, s->view, dRays, (long long)nRays, tMin, tMax, mode == TMPT_HIT_ANY, dID, dT, dPos, dNrm, s->d_fetchCounter, nullptr);
+        } else if (variant == 2) {
+            CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, k_hit_scene_persist<false, 16>, B, 0));
+            const int GP = (int)std::min<long long>(div_up(nRays, B), (long long)s->smCount * std::max(perSM, 1));
+            LAUNCH((k_hit_scene_persist<false, 16>), GP, B, 0, st, s->view, dRays, (long long)nRays, tMin, tMax, mode == TMPT_HIT_ANY, dID, dT, dPos, dNrm, s->d_fetchCounter, nullptr);
+        } else if (variant == 3) {
+            CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, k_hit_scene_persist<false, 32>, B, 0));
+            const int GP = (int)std::min<long long>(div_up(nRays, B), (long long)s->smCount * std::max(perSM, 1));
+            LAUNCH((k_hit_scene_persist<false, 32>), GP, B, 0, st, s->view, dRays, (long long)nRays, tMin, tMax, mode == TMPT_HIT_ANY, dID, dT, dPos, dNrm, s->d_fetchCounter, nullptr);
+        } else {
+            CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, k_hit_scene_persist<false, 0>, B, 0));
+            const int GP = (int)std::min<long long>(div_up(nRays, B), (long long)s->smCount * std::max(perSM, 1));
+            LAUNCH((k_hit_scene_persist<false, 0>), GP, B, 0, st, s->view, dRays, (long long)nRays, tMin, tMax, mode == TMPT_HIT_ANY, dID, dT, dPos, dNrm, s->d_fetchCounter, nullptr);
+        }
+    } else if (mode == TMPT_HIT_CLOSEST) LAUNCH((k_hit_scene<TMPT_HIT_CLOSEST, false>), G, B, 0, st, s->view, dRays, (long long)nRays, tMin, tMax, dID, dT, dPos, dNrm, nullptr);
     else if (mode == TMPT_HIT_ANY) LAUNCH((k_hit_scene<TMPT_HIT_ANY, false>), G, B, 0, st, s->view, dRays, (long long)nRays, tMin, tMax, dID, dT, dPos, dNrm, nullptr);
     else LAUNCH((k_hit_scene<TMPT_HIT_BRUTE, false>), G, B, 0, st, s->view, dRays, (long long)nRays, tMin, tMax, dID, dT, dPos, dNrm, nullptr);
     CU_TRY(cudaGetLastError());
