@@ -49,8 +49,9 @@ typedef struct tmpt_camera {
 typedef enum tmpt_mem { TMPT_HOST = 0, TMPT_DEVICE = 1 } tmpt_mem;
 
 /* tmpt_scene_create flags */
-#define TMPT_BUILD_DEFAULT 0u
-#define TMPT_BUILD_LBVH 1u /* Morton-order Karras hierarchy only (no agglomerative pass) */
+#define TMPT_BUILD_DEFAULT 0u /* binned-SAH top-down build on the device (16 bins per axis)     */
+#define TMPT_BUILD_LBVH 1u    /* Morton codes + radix sort + Karras hierarchy: faster build,
+                                 ~40 % more node visits per ray                                */
 
 /* tmpt_hit_scene modes */
 #define TMPT_HIT_CLOSEST 0 /* nearest hit through the BVH                                  */

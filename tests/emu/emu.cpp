@@ -33,7 +33,8 @@ struct EmuScene {
 
 extern "C" {
 
-void* emu_scene_create(const float* tris9, int n) {
+// builder: 0 = binned SAH (top-down), 1 = LBVH (Karras)
+void* emu_scene_create2(const float* tris9, int n, int builder, float cInner, float cTri, int maxLeaf) {
     EmuScene* s = new EmuScene();
     s->n = n;
     s->tris9.assign(tris9, tris9 + (size_t)n * 9);
@@ -44,49 +45,113 @@ void* emu_scene_create(const float* tris9, int n) {
     // k_prim_bounds
     bld::Box scene{3.0e38f, 3.0e38f, 3.0e38f, -3.0e38f, -3.0e38f, -3.0e38f};
     for (int i = 0; i < n; ++i) scene = bld::box_union(scene, bld::tri_box(tris9 + (size_t)i * 9));
-    // k_morton
-    std::vector<uint64_t> keys(n);
-    std::vector<uint32_t> prim(n);
-    for (int i = 0; i < n; ++i) {
-        const bld::Box b = bld::tri_box(tris9 + (size_t)i * 9);
-        keys[i] = bld::morton63(0.5f * (b.lox + b.hix), 0.5f * (b.loy + b.hiy), 0.5f * (b.loz + b.hiz), scene);
-        prim[i] = (uint32_t)i;
-    }
-    // k_radix_sort (stable)
-    std::stable_sort(prim.begin(), prim.end(), [&](uint32_t a, uint32_t b) { return keys[a] < keys[b]; });
-    std::vector<uint64_t> skeys(n);
-    for (int j = 0; j < n; ++j) skeys[j] = keys[prim[j]];
-    // k_leaf_boxes
-    std::vector<float4> lo(2 * (size_t)n), hi(2 * (size_t)n);
     const float maxAbs = std::max(std::max(std::max(std::fabs(scene.lox), std::fabs(scene.hix)), std::max(std::fabs(scene.loy), std::fabs(scene.hiy))),
                                   std::max(std::fabs(scene.loz), std::fabs(scene.hiz)));
-    const float cTri = 1.0f, cInner = 1.0f;
-    for (int j = 0; j < n; ++j) {
-        bld::Box b = bld::tri_box(tris9 + (size_t)prim[j] * 9);
+    // padded primitive boxes (k_prim_boxes)
+    std::vector<bld::Box> pbox(n);
+    for (int i = 0; i < n; ++i) {
+        bld::Box b = bld::tri_box(tris9 + (size_t)i * 9);
         const float dx = b.hix - b.lox, dy = b.hiy - b.loy, dz = b.hiz - b.loz;
         const float pad = bld::pad_for(sqrtf(dx * dx + dy * dy + dz * dz), maxAbs);
         b.lox -= pad; b.loy -= pad; b.loz -= pad; b.hix += pad; b.hiy += pad; b.hiz += pad;
-        lo[n - 1 + j] = make_float4(b.lox, b.loy, b.loz, cTri * bld::box_half_area(b));
-        hi[n - 1 + j] = make_float4(b.hix, b.hiy, b.hiz, ex::u2f(1u));
+        pbox[i] = b;
     }
-    std::vector<int> left(n), right(n), parent(2 * (size_t)n, -1);
+    std::vector<uint32_t> prim(n);
+    std::vector<float4> lo(2 * (size_t)n), hi(2 * (size_t)n);
+    std::vector<int> left(2 * (size_t)n), right(2 * (size_t)n), parent(2 * (size_t)n, -1), first(2 * (size_t)n);
     std::vector<uint32_t> visits(n, 0);
-    bld::BinTree t{n, skeys.data(), left.data(), right.data(), parent.data(), lo.data(), hi.data(), visits.data()};
-    bld::SahParams sp{cInner, cTri, bvh::MAX_LEAF_TRIS};
-    bld::WideOut w{s->nodes.data(), s->tris.data(), s->tris9.data(), prim.data(), s->counters, s->sah};
+    std::vector<uint64_t> skeys(n);
+    bld::SahParams sp{cInner, cTri, maxLeaf};
     bool rootIsLeaf = n == 1;
-    if (n > 1) {
-        for (int i = 0; i < n - 1; ++i) bld::karras_node(t, i);  // k_karras
-        for (int j = 0; j < n; ++j) {                              // k_refit
-            int node = parent[n - 1 + j];
-            while (node >= 0) {
-                if (visits[node]++ == 0) break;
-                bld::refit_node(t, node, sp);
-                node = parent[node];
+    if (builder == 1) {
+        // k_morton + k_radix_sort (stable) + k_leaf_boxes
+        std::vector<uint64_t> keys(n);
+        for (int i = 0; i < n; ++i) {
+            const bld::Box b = bld::tri_box(tris9 + (size_t)i * 9);
+            keys[i] = bld::morton63(0.5f * (b.lox + b.hix), 0.5f * (b.loy + b.hiy), 0.5f * (b.loz + b.hiz), scene);
+            prim[i] = (uint32_t)i;
+        }
+        std::stable_sort(prim.begin(), prim.end(), [&](uint32_t a, uint32_t b) { return keys[a] < keys[b]; });
+        for (int j = 0; j < n; ++j) {
+            skeys[j] = keys[prim[j]];
+            const bld::Box& b = pbox[prim[j]];
+            lo[n - 1 + j] = make_float4(b.lox, b.loy, b.loz, cTri * bld::box_half_area(b));
+            hi[n - 1 + j] = make_float4(b.hix, b.hiy, b.hiz, ex::u2f((uint32_t)-1));
+            first[n - 1 + j] = j;
+        }
+    }
+    bld::BinTree t{n, skeys.data(), left.data(), right.data(), parent.data(), lo.data(), hi.data(), first.data(), visits.data()};
+    if (builder == 1) {
+        if (n > 1) {
+            for (int i = 0; i < n - 1; ++i) bld::karras_node(t, i);  // k_karras
+            for (int j = 0; j < n; ++j) {                              // k_refit
+                int node = parent[n - 1 + j];
+                while (node >= 0) {
+                    if (visits[node]++ == 0) break;
+                    bld::refit_node(t, node, sp);
+                    node = parent[node];
+                }
             }
         }
-        rootIsLeaf = (int)ex::f2u(hi[0].w) < 0;
+    } else {
+        // k_sah_level, serially: task = (node, first, count)
+        struct Task { int node, first, count; };
+        for (int i = 0; i < n; ++i) prim[i] = (uint32_t)i;
+        std::vector<Task> q{{0, 0, n}};
+        int nodeCounter = 1;
+        std::vector<uint32_t> tmp(n);
+        while (!q.empty()) {
+            std::vector<Task> next;
+            for (const Task& tk : q) {
+                bld::Box nb = bld::empty_box(), cb = bld::empty_box();
+                for (int i = 0; i < tk.count; ++i) {
+                    const bld::Box& b = pbox[prim[tk.first + i]];
+                    nb = bld::box_union(nb, b);
+                    const float cx = 0.5f * (b.lox + b.hix), cy = 0.5f * (b.loy + b.hiy), cz = 0.5f * (b.loz + b.hiz);
+                    cb = bld::box_union(cb, bld::Box{cx, cy, cz, cx, cy, cz});
+                }
+                const float cmin[3] = {cb.lox, cb.loy, cb.loz}, ext[3] = {cb.hix - cb.lox, cb.hiy - cb.loy, cb.hiz - cb.loz};
+                bld::SahBin bins[3][bld::SAH_BINS];
+                for (int a = 0; a < 3; ++a) for (int b = 0; b < bld::SAH_BINS; ++b) bins[a][b] = bld::SahBin{bld::empty_box(), 0};
+                auto cen = [&](const bld::Box& b, int a) { return a == 0 ? 0.5f * (b.lox + b.hix) : a == 1 ? 0.5f * (b.loy + b.hiy) : 0.5f * (b.loz + b.hiz); };
+                for (int i = 0; i < tk.count; ++i) {
+                    const bld::Box& b = pbox[prim[tk.first + i]];
+                    for (int a = 0; a < 3; ++a) {
+                        bld::SahBin& bn = bins[a][bld::sah_bin_of(cen(b, a), cmin[a], ext[a])];
+                        bn.box = bld::box_union(bn.box, b);
+                        ++bn.count;
+                    }
+                }
+                float costs[3 * (bld::SAH_BINS - 1)];
+                int lcs[3 * (bld::SAH_BINS - 1)];
+                for (int k = 0; k < 3 * (bld::SAH_BINS - 1); ++k) costs[k] = bld::sah_split_cost(bins[k / (bld::SAH_BINS - 1)], k % (bld::SAH_BINS - 1), &lcs[k]);
+                bld::SahDecision d = tk.count == 1 ? bld::SahDecision{-1, 0, 0} : bld::sah_decide(costs, lcs, tk.count, bld::box_half_area(nb), sp);
+                lo[tk.node] = make_float4(nb.lox, nb.loy, nb.loz, 0.0f);
+                first[tk.node] = tk.first;
+                if (d.axis < 0) {
+                    hi[tk.node] = make_float4(nb.hix, nb.hiy, nb.hiz, ex::u2f((uint32_t)(-tk.count)));
+                    continue;
+                }
+                hi[tk.node] = make_float4(nb.hix, nb.hiy, nb.hiz, ex::u2f((uint32_t)tk.count));
+                int nl = 0, nr = 0;
+                for (int i = 0; i < tk.count; ++i) {
+                    const uint32_t id = prim[tk.first + i];
+                    const bool goLeft = d.axis == 3 ? i < d.leftCount : bld::sah_bin_of(cen(pbox[id], d.axis), cmin[d.axis], ext[d.axis]) <= d.split;
+                    if (goLeft) tmp[tk.first + nl++] = id;
+                    else tmp[tk.first + tk.count - 1 - nr++] = id;
+                }
+                for (int i = 0; i < tk.count; ++i) prim[tk.first + i] = tmp[tk.first + i];
+                const int base = nodeCounter; nodeCounter += 2;
+                left[tk.node] = base; right[tk.node] = base + 1;
+                next.push_back({base, tk.first, nl});
+                next.push_back({base + 1, tk.first + nl, nr});
+            }
+            q.swap(next);
+        }
     }
+    rootIsLeaf = (int)ex::f2u(hi[0].w) < 0 || n == 1;
+    if (builder == 1 && n == 1) { /* single leaf n-1+0 == node 0 */ }
+    bld::WideOut w{s->nodes.data(), s->tris.data(), s->tris9.data(), prim.data(), s->counters, s->sah};
     s->counters[0] = 1;
     if (rootIsLeaf) {
         bld::emit_single_leaf_root(t, w, 0);
@@ -103,6 +168,7 @@ void* emu_scene_create(const float* tris9, int n) {
     }
     return s;
 }
+void* emu_scene_create(const float* tris9, int n) { return emu_scene_create2(tris9, n, 1, 1.0f, 1.0f, bvh::MAX_LEAF_TRIS); }
 void emu_scene_destroy(void* h) { delete (EmuScene*)h; }
 // [0] wide nodes [1] slots [2] leaves [3] max depth [4] status
 void emu_scene_info(void* h, uint32_t out[5]) {
@@ -160,6 +226,23 @@ void emu_render(void* h, const float cam22[22], int w, int hgt, int spp, int row
         total += rays;
     }
     if (rayCount) *rayCount = (long long)total;
+}
+
+// work counters of a render: [0] rays [1] wide-node visits [2] triangle tests
+void emu_render_stats(void* h, const float cam22[22], int w, int hgt, int spp, unsigned long long out[3]) {
+    EmuScene* s = (EmuScene*)h;
+    integ::Camera cam;
+    memcpy(&cam, cam22, sizeof cam);
+    const ex::V3 lightDir = ex::normalize(ex::v3(-0.7f, 1.0f, 0.5f));
+    unsigned long long rays = 0, nodes = 0, tris = 0;
+#pragma omp parallel for schedule(dynamic, 1) reduction(+ : rays, nodes, tris)
+    for (int y = 0; y < hgt; ++y) {
+        unsigned long long r = 0;
+        bvh::TravStats ts;
+        for (int x = 0; x < w; ++x) integ::render_pixel<true>(s->view, cam, x, y, w, hgt, spp, lightDir, r, nullptr, &ts);
+        rays += r; nodes += ts.nodes; tris += ts.tris;
+    }
+    out[0] = rays; out[1] = nodes; out[2] = tris;
 }
 
 void emu_sincos(float a, float* s, float* c) { ex::sincos_spec(a, *s, *c); }

@@ -38,17 +38,19 @@ class Emu:
     def __init__(self):
         self.L = C.CDLL(build())
         self.L.emu_scene_create.restype = C.c_void_p
+        self.L.emu_scene_create2.restype = C.c_void_p
         self.L.emu_pixel_seed.restype = C.c_uint32
 
-    def scene(self, tris):
-        return EmuScene(self.L, tris)
+    def scene(self, tris, builder=0, c_inner=1.0, c_tri=1.0, max_leaf=8):
+        """builder 0 = binned SAH (the default of the product), 1 = LBVH"""
+        return EmuScene(self.L, tris, builder, c_inner, c_tri, max_leaf)
 
 
 class EmuScene:
-    def __init__(self, L, tris):
+    def __init__(self, L, tris, builder=0, c_inner=1.0, c_tri=1.0, max_leaf=8):
         self.L = L
         self.tris = np.ascontiguousarray(tris, np.float32).reshape(-1, 9)
-        self.h = C.c_void_p(L.emu_scene_create(_p(self.tris), self.tris.shape[0]))
+        self.h = C.c_void_p(L.emu_scene_create2(_p(self.tris), self.tris.shape[0], builder, C.c_float(c_inner), C.c_float(c_tri), max_leaf))
 
     def close(self):
         if self.h:
@@ -80,6 +82,13 @@ class EmuScene:
         t = np.zeros(n, np.float32); pos = np.zeros((n, 3), np.float32); nrm = np.zeros((n, 3), np.float32)
         self.L.emu_hit_scene(self.h, _p(rays), C.c_long(n), C.c_float(tmin), C.c_float(tmax), mode, _p(ids), _p(t), _p(pos), _p(nrm))
         return ids, t, pos, nrm
+
+    def render_stats(self, cam22, w, h, spp):
+        cam22 = np.ascontiguousarray(cam22, np.float32)
+        out = np.zeros(3, np.uint64)
+        self.L.emu_render_stats(self.h, _p(cam22), w, h, spp, _p(out))
+        rays = max(int(out[0]), 1)
+        return {"rays": int(out[0]), "nodes_per_ray": int(out[1]) / rays, "tris_per_ray": int(out[2]) / rays}
 
     def render(self, cam22, w, h, spp, rows=None):
         cam22 = np.ascontiguousarray(cam22, np.float32)

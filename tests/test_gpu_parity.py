@@ -64,6 +64,18 @@ def test_hit_ids_t_and_payload_bit_exact(scenes, name):
     assert (bid == g["id"]).all() and (bits(bt)[hit] == bits(g["t"])[hit]).all()
 
 
+@pytest.mark.parametrize("name", ["suzanne", "teapot"])
+def test_lbvh_builder_is_exact_too(name):
+    """TMPT_BUILD_LBVH (Morton + radix sort + Karras) gives the same answers as the default binned-SAH tree."""
+    g = load_rays(name)
+    with tm.Scene(load_scene(name)["tris"], flags=tm.BUILD_LBVH) as s:
+        assert s.info()["builder"] == tm.BUILD_LBVH
+        ids, t, pos, nrm = s.HitScene(g["rays"])
+    hit = g["id"] >= 0
+    assert (ids == g["id"]).all() and (bits(t)[hit] == bits(g["t"])[hit]).all()
+    assert (bits(pos)[hit] == bits(g["pos"])[hit]).all() and (bits(nrm)[hit] == bits(g["normal"])[hit]).all()
+
+
 def _random_rays(sc, n, seed, axis_parallel=True):
     rng = np.random.default_rng(seed)
     ext = (sc["bounds_max"] - sc["bounds_min"]) * 0.75

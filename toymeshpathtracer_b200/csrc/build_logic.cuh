@@ -91,18 +91,22 @@ TMPT_HD int clz32(uint32_t v) {
 #endif
 }
 
-// Binary tree over n sorted primitives: inner nodes [0, n-1), leaves [n-1, 2n-1) where leaf
-// n-1+j is sorted position j.
+// Binary tree over n primitives in a pool of 2n-1 nodes, root = node 0.  Every node covers a
+// contiguous range [first, first+count) of the ordered primitive list `prim` (position ->
+// original index).  The LBVH builder (Karras) puts inner nodes at [0, n-1) and the single-
+// primitive leaves at [n-1, 2n-1) (leaf n-1+j = sorted position j); the SAH builder allocates
+// nodes as it goes.  Both hand the same structure to the wide collapse.
 struct BinTree {
     int n;
-    const uint64_t* keys;  // sorted
-    int* left;             // [n-1]
-    int* right;            // [n-1]
-    int* parent;           // [2n-1]
+    const uint64_t* keys;  // sorted Morton codes (LBVH only)
+    int* left;             // [2n-1]
+    int* right;            // [2n-1]
+    int* parent;           // [2n-1] (LBVH only)
     float4* lo;            // [2n-1] xyz = box min, w = SAH cost of the subtree
     float4* hi;            // [2n-1] xyz = box max, w = bit-cast int: triangles in the subtree,
-                           //         NEGATIVE when the subtree is to become one leaf
-    uint32_t* visits;      // [n-1] bottom-up arrival counters
+                           //         NEGATIVE when the node is (to become) one leaf
+    int* first;            // [2n-1] first position of the node's range
+    uint32_t* visits;      // [n-1] bottom-up arrival counters (LBVH only)
 };
 
 // Karras 2012, "Maximizing parallelism in the construction of BVHs, octrees and k-d trees":
@@ -136,6 +140,7 @@ TMPT_HD void karras_node(const BinTree& t, int i) {
     const int R = (hi == gamma + 1) ? (n - 1 + gamma + 1) : (gamma + 1);
     t.left[i] = L;
     t.right[i] = R;
+    t.first[i] = lo;
     t.parent[L] = i;
     t.parent[R] = i;
     if (i == 0) t.parent[0] = -1;
@@ -164,6 +169,58 @@ TMPT_HD void refit_node(const BinTree& t, int i, const SahParams& sp) {
     t.hi[i] = make_float4(b.hix, b.hiy, b.hiz, ex::u2f((uint32_t)(asLeaf ? -cnt : cnt)));
 }
 
+// ---- binned SAH (top-down builder): per-task logic shared by the kernel and the host emulation ----
+constexpr int SAH_BINS = 16;
+struct SahBin {
+    Box box;
+    int count;
+};
+TMPT_HD Box empty_box() { return Box{3.0e38f, 3.0e38f, 3.0e38f, -3.0e38f, -3.0e38f, -3.0e38f}; }
+
+// bin of a centroid coordinate along an axis whose centroid range is [cmin, cmin + extent]
+TMPT_HD int sah_bin_of(float c, float cmin, float extent) {
+    if (!(extent > 0.0f)) return 0;
+    int b = (int)((c - cmin) * ((float)SAH_BINS / extent));
+    return b < 0 ? 0 : (b > SAH_BINS - 1 ? SAH_BINS - 1 : b);
+}
+
+// Cost (areaL*nL + areaR*nR) of splitting after bin `split` (left = bins [0, split]) on one axis;
+// < 0 when one side would be empty.
+TMPT_HD float sah_split_cost(const SahBin* bins, int split, int* outLeftCount) {
+    Box l = empty_box(), r = empty_box();
+    int nl = 0, nr = 0;
+    for (int b = 0; b < SAH_BINS; ++b) {
+        if (bins[b].count == 0) continue;
+        if (b <= split) { l = box_union(l, bins[b].box); nl += bins[b].count; }
+        else { r = box_union(r, bins[b].box); nr += bins[b].count; }
+    }
+    *outLeftCount = nl;
+    if (nl == 0 || nr == 0) return -1.0f;
+    return box_half_area(l) * (float)nl + box_half_area(r) * (float)nr;
+}
+
+struct SahDecision {
+    int axis;       // -1: make a leaf; 3: median split by position (binning found nothing)
+    int split;      // last bin of the left side
+    int leftCount;
+};
+// costs[axis * (SAH_BINS-1) + split] as computed by sah_split_cost; nodeArea = half area of the node box
+TMPT_HD SahDecision sah_decide(const float* costs, const int* leftCounts, int count, float nodeArea, const SahParams& sp) {
+    SahDecision d{-1, 0, 0};
+    float best = 3.0e38f;
+    for (int k = 0; k < 3 * (SAH_BINS - 1); ++k) {
+        if (costs[k] >= 0.0f && costs[k] < best) { best = costs[k]; d.axis = k / (SAH_BINS - 1); d.split = k % (SAH_BINS - 1); d.leftCount = leftCounts[k]; }
+    }
+    const float leafCost = sp.cTri * (float)count * nodeArea;
+    if (d.axis < 0) {  // all centroids coincide
+        if (count <= sp.maxLeaf) return SahDecision{-1, 0, 0};
+        return SahDecision{3, 0, count / 2};
+    }
+    const float splitCost = sp.cInner * nodeArea + sp.cTri * best;
+    if (count <= sp.maxLeaf && leafCost <= splitCost) return SahDecision{-1, 0, 0};
+    return d;
+}
+
 // ---- collapse: binary -> 4-wide ----
 struct WideOut {
     float4* nodes;         // bvh::NODE_F4 float4 per wide node
@@ -179,9 +236,7 @@ struct WorkItem {
     int depth;
 };
 
-TMPT_HD bool subtree_is_leaf(const BinTree& t, int node) {
-    return node >= t.n - 1 || (int)ex::f2u(t.hi[node].w) < 0;
-}
+TMPT_HD bool subtree_is_leaf(const BinTree& t, int node) { return (int)ex::f2u(t.hi[node].w) < 0; }
 TMPT_HD int subtree_count(const BinTree& t, int node) {
     int c = (int)ex::f2u(t.hi[node].w);
     return c < 0 ? -c : c;
@@ -210,28 +265,18 @@ TMPT_HD void accum_add(float* p, float v) {
 #endif
 }
 
-// Write the triangles of a leaf subtree into consecutive slots, in sorted order.
+// Write the triangles of a leaf node (its range of the ordered list) into consecutive slots.
 TMPT_HD void emit_leaf_tris(const BinTree& t, const WideOut& w, int node, uint32_t firstSlot) {
-    int stack[16];
-    int sp = 0;
-    stack[sp++] = node;
-    uint32_t slot = firstSlot;
-    while (sp > 0) {
-        int nd = stack[--sp];
-        if (nd >= t.n - 1) {
-            const uint32_t id = w.prim[nd - (t.n - 1)];
-            const float* p = w.tris9 + (size_t)id * 9;
-            ex::V3 v0 = ex::v3(p[0], p[1], p[2]), v1 = ex::v3(p[3], p[4], p[5]), v2 = ex::v3(p[6], p[7], p[8]);
-            ex::V3 e1 = ex::sub(v1, v0), e2 = ex::sub(v2, v0);  // maths.cpp:343-344
-            float4* o = w.tris + (size_t)slot * 3;
-            o[0] = make_float4(v0.x, v0.y, v0.z, ex::u2f(id));
-            o[1] = make_float4(e1.x, e1.y, e1.z, 0.0f);
-            o[2] = make_float4(e2.x, e2.y, e2.z, 0.0f);
-            ++slot;
-        } else {
-            stack[sp++] = t.right[nd];  // left first -> ascending sorted position
-            stack[sp++] = t.left[nd];
-        }
+    const int first = t.first[node], cnt = subtree_count(t, node);
+    for (int k = 0; k < cnt; ++k) {
+        const uint32_t id = w.prim[first + k];
+        const float* p = w.tris9 + (size_t)id * 9;
+        ex::V3 v0 = ex::v3(p[0], p[1], p[2]), v1 = ex::v3(p[3], p[4], p[5]), v2 = ex::v3(p[6], p[7], p[8]);
+        ex::V3 e1 = ex::sub(v1, v0), e2 = ex::sub(v2, v0);  // maths.cpp:343-344
+        float4* o = w.tris + (size_t)(firstSlot + k) * 3;
+        o[0] = make_float4(v0.x, v0.y, v0.z, ex::u2f(id));
+        o[1] = make_float4(e1.x, e1.y, e1.z, 0.0f);
+        o[2] = make_float4(e2.x, e2.y, e2.z, 0.0f);
     }
 }
 
@@ -307,7 +352,7 @@ TMPT_HD void collapse_node(const BinTree& t, const WideOut& w, const WorkItem& i
 // Root special case: the whole scene is one leaf (n <= maxLeaf and SAH says so, or n == 1).
 // Emits wide node 0 with a single leaf child.
 TMPT_HD void emit_single_leaf_root(const BinTree& t, const WideOut& w, int rootNode) {
-    const int cnt = rootNode >= t.n - 1 ? 1 : subtree_count(t, rootNode);
+    const int cnt = subtree_count(t, rootNode);
     const uint32_t first = counter_add(&w.counters[1], (uint32_t)cnt);
     counter_add(&w.counters[2], 1u);
     emit_leaf_tris(t, w, rootNode, first);

@@ -206,7 +206,8 @@ __global__ void __launch_bounds__(SORT_THREADS) k_radix_sort(uint64_t* keysA, ui
 
 // leaf j of the binary tree = sorted position j: padded box, cost of a 1-triangle leaf, count 1
 __global__ void k_leaf_boxes(const float* __restrict__ tris9, const uint32_t* __restrict__ prim, int n,
-                             const uint32_t* __restrict__ bounds, float cTri, float4* __restrict__ lo, float4* __restrict__ hi) {
+                             const uint32_t* __restrict__ bounds, float cTri, float4* __restrict__ lo, float4* __restrict__ hi,
+                             int* __restrict__ first) {
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= n) return;
     const bld::Box scene = load_scene_box(bounds);
@@ -217,7 +218,8 @@ __global__ void k_leaf_boxes(const float* __restrict__ tris9, const uint32_t* __
     const float pad = bld::pad_for(sqrtf(dx * dx + dy * dy + dz * dz), maxAbs);
     b.lox -= pad; b.loy -= pad; b.loz -= pad; b.hix += pad; b.hiy += pad; b.hiz += pad;
     lo[n - 1 + j] = make_float4(b.lox, b.loy, b.loz, cTri * bld::box_half_area(b));
-    hi[n - 1 + j] = make_float4(b.hix, b.hiy, b.hiz, ex::u2f(1u));
+    hi[n - 1 + j] = make_float4(b.hix, b.hiy, b.hiz, ex::u2f((uint32_t)-1));  // one triangle, a leaf
+    first[n - 1 + j] = j;
 }
 
 __global__ void k_karras(bld::BinTree t) {
@@ -236,6 +238,145 @@ __global__ void k_refit(bld::BinTree t, bld::SahParams sp) {
         __threadfence();
         bld::refit_node(t, node, sp);
         node = t.parent[node];
+    }
+}
+
+// ---- binned-SAH top-down builder (the default): one CTA per (node, range) task per level ----
+__global__ void k_prim_boxes(const float* __restrict__ tris9, int n, const uint32_t* __restrict__ bounds, float4* __restrict__ pLo,
+                             float4* __restrict__ pHi, uint32_t* __restrict__ idx) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const bld::Box scene = load_scene_box(bounds);
+    const float maxAbs = fmaxf(fmaxf(fmaxf(fabsf(scene.lox), fabsf(scene.hix)), fmaxf(fabsf(scene.loy), fabsf(scene.hiy))),
+                               fmaxf(fabsf(scene.loz), fabsf(scene.hiz)));
+    bld::Box b = bld::tri_box(tris9 + (size_t)i * 9);
+    const float dx = b.hix - b.lox, dy = b.hiy - b.loy, dz = b.hiz - b.loz;
+    const float pad = bld::pad_for(sqrtf(dx * dx + dy * dy + dz * dz), maxAbs);
+    pLo[i] = make_float4(b.lox - pad, b.loy - pad, b.loz - pad, 0.0f);
+    pHi[i] = make_float4(b.hix + pad, b.hiy + pad, b.hiz + pad, 0.0f);
+    idx[i] = (uint32_t)i;
+}
+
+struct SahTask {
+    int node, first, count;
+};
+constexpr int SAH_THREADS = 256;
+
+__device__ __forceinline__ void smem_box_grow(uint32_t* b6, float lox, float loy, float loz, float hix, float hiy, float hiz) {
+    atomicMin(&b6[0], bld::float_to_ordered(lox)); atomicMin(&b6[1], bld::float_to_ordered(loy)); atomicMin(&b6[2], bld::float_to_ordered(loz));
+    atomicMax(&b6[3], bld::float_to_ordered(hix)); atomicMax(&b6[4], bld::float_to_ordered(hiy)); atomicMax(&b6[5], bld::float_to_ordered(hiz));
+}
+__device__ __forceinline__ bld::Box smem_box_load(const uint32_t* b6) {
+    return bld::Box{bld::ordered_to_float(b6[0]), bld::ordered_to_float(b6[1]), bld::ordered_to_float(b6[2]),
+                    bld::ordered_to_float(b6[3]), bld::ordered_to_float(b6[4]), bld::ordered_to_float(b6[5])};
+}
+
+__global__ void __launch_bounds__(SAH_THREADS) k_sah_level(bld::BinTree t, const float4* __restrict__ pLo, const float4* __restrict__ pHi,
+                                                           const uint32_t* __restrict__ idxIn, uint32_t* __restrict__ idxOut,
+                                                           uint32_t* __restrict__ primFinal, const SahTask* __restrict__ inQ,
+                                                           SahTask* __restrict__ outQ, uint32_t* __restrict__ outCount,
+                                                           uint32_t* __restrict__ nodeCounter, bld::SahParams sp) {
+    __shared__ uint32_t sNode[6], sCen[6];
+    __shared__ uint32_t sBinBox[3][bld::SAH_BINS][6];
+    __shared__ int sBinCnt[3][bld::SAH_BINS];
+    __shared__ float sCost[3 * (bld::SAH_BINS - 1)];
+    __shared__ int sLeft[3 * (bld::SAH_BINS - 1)];
+    __shared__ bld::SahDecision sDec;
+    __shared__ int sNl, sNr;
+    const SahTask tk = inQ[blockIdx.x];
+    const int tid = threadIdx.x;
+    if (tid < 6) { sNode[tid] = tid < 3 ? 0xFFFFFFFFu : 0u; sCen[tid] = tid < 3 ? 0xFFFFFFFFu : 0u; }
+    for (int k = tid; k < 3 * bld::SAH_BINS; k += SAH_THREADS) {
+        uint32_t* b = &sBinBox[0][0][0] + k * 6;
+        b[0] = b[1] = b[2] = 0xFFFFFFFFu; b[3] = b[4] = b[5] = 0u;
+        (&sBinCnt[0][0])[k] = 0;
+    }
+    if (tid == 0) { sNl = 0; sNr = 0; }
+    __syncthreads();
+    // 1. node box and centroid box: per-thread, then per-warp, then one shared atomic per warp
+    {
+        bld::Box nb = bld::empty_box(), cb = bld::empty_box();
+        for (int i = tid; i < tk.count; i += SAH_THREADS) {
+            const uint32_t id = idxIn[tk.first + i];
+            const float4 lo = pLo[id], hi = pHi[id];
+            nb = bld::box_union(nb, bld::Box{lo.x, lo.y, lo.z, hi.x, hi.y, hi.z});
+            const float cx = 0.5f * (lo.x + hi.x), cy = 0.5f * (lo.y + hi.y), cz = 0.5f * (lo.z + hi.z);
+            cb = bld::box_union(cb, bld::Box{cx, cy, cz, cx, cy, cz});
+        }
+        for (int o = 16; o > 0; o >>= 1) {
+            nb.lox = fminf(nb.lox, __shfl_xor_sync(0xffffffffu, nb.lox, o)); nb.loy = fminf(nb.loy, __shfl_xor_sync(0xffffffffu, nb.loy, o));
+            nb.loz = fminf(nb.loz, __shfl_xor_sync(0xffffffffu, nb.loz, o)); nb.hix = fmaxf(nb.hix, __shfl_xor_sync(0xffffffffu, nb.hix, o));
+            nb.hiy = fmaxf(nb.hiy, __shfl_xor_sync(0xffffffffu, nb.hiy, o)); nb.hiz = fmaxf(nb.hiz, __shfl_xor_sync(0xffffffffu, nb.hiz, o));
+            cb.lox = fminf(cb.lox, __shfl_xor_sync(0xffffffffu, cb.lox, o)); cb.loy = fminf(cb.loy, __shfl_xor_sync(0xffffffffu, cb.loy, o));
+            cb.loz = fminf(cb.loz, __shfl_xor_sync(0xffffffffu, cb.loz, o)); cb.hix = fmaxf(cb.hix, __shfl_xor_sync(0xffffffffu, cb.hix, o));
+            cb.hiy = fmaxf(cb.hiy, __shfl_xor_sync(0xffffffffu, cb.hiy, o)); cb.hiz = fmaxf(cb.hiz, __shfl_xor_sync(0xffffffffu, cb.hiz, o));
+        }
+        if ((tid & 31) == 0) {
+            smem_box_grow(sNode, nb.lox, nb.loy, nb.loz, nb.hix, nb.hiy, nb.hiz);
+            smem_box_grow(sCen, cb.lox, cb.loy, cb.loz, cb.hix, cb.hiy, cb.hiz);
+        }
+    }
+    __syncthreads();
+    const bld::Box nodeBox = smem_box_load(sNode), cenBox = smem_box_load(sCen);
+    const float cmin[3] = {cenBox.lox, cenBox.loy, cenBox.loz};
+    const float ext[3] = {cenBox.hix - cenBox.lox, cenBox.hiy - cenBox.loy, cenBox.hiz - cenBox.loz};
+    // 2. bin the primitives on all three axes
+    if (tk.count > 1) {
+        for (int i = tid; i < tk.count; i += SAH_THREADS) {
+            const uint32_t id = idxIn[tk.first + i];
+            const float4 lo = pLo[id], hi = pHi[id];
+            const float c[3] = {0.5f * (lo.x + hi.x), 0.5f * (lo.y + hi.y), 0.5f * (lo.z + hi.z)};
+#pragma unroll
+            for (int a = 0; a < 3; ++a) {
+                const int b = bld::sah_bin_of(c[a], cmin[a], ext[a]);
+                smem_box_grow(sBinBox[a][b], lo.x, lo.y, lo.z, hi.x, hi.y, hi.z);
+                atomicAdd(&sBinCnt[a][b], 1);
+            }
+        }
+    }
+    __syncthreads();
+    // 3. evaluate the 3 x 15 candidate planes, decide
+    if (tid < 3 * (bld::SAH_BINS - 1) && tk.count > 1) {
+        const int a = tid / (bld::SAH_BINS - 1), sidx = tid % (bld::SAH_BINS - 1);
+        bld::SahBin bins[bld::SAH_BINS];
+        for (int b = 0; b < bld::SAH_BINS; ++b) { bins[b].box = smem_box_load(sBinBox[a][b]); bins[b].count = sBinCnt[a][b]; }
+        int lc;
+        sCost[tid] = bld::sah_split_cost(bins, sidx, &lc);
+        sLeft[tid] = lc;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        const bld::SahDecision d = tk.count == 1 ? bld::SahDecision{-1, 0, 0} : bld::sah_decide(sCost, sLeft, tk.count, bld::box_half_area(nodeBox), sp);
+        sDec = d;
+        t.lo[tk.node] = make_float4(nodeBox.lox, nodeBox.loy, nodeBox.loz, 0.0f);
+        t.first[tk.node] = tk.first;
+        if (d.axis < 0) {
+            t.hi[tk.node] = make_float4(nodeBox.hix, nodeBox.hiy, nodeBox.hiz, ex::u2f((uint32_t)(-tk.count)));
+        } else {
+            t.hi[tk.node] = make_float4(nodeBox.hix, nodeBox.hiy, nodeBox.hiz, ex::u2f((uint32_t)tk.count));
+            const int base = (int)atomicAdd(nodeCounter, 2u);
+            t.left[tk.node] = base;
+            t.right[tk.node] = base + 1;
+            const uint32_t q = atomicAdd(outCount, 2u);
+            outQ[q] = SahTask{base, tk.first, d.leftCount};
+            outQ[q + 1] = SahTask{base + 1, tk.first + d.leftCount, tk.count - d.leftCount};
+        }
+    }
+    __syncthreads();
+    // 4. leaf: the range is final.  split: partition into the other index buffer.
+    const bld::SahDecision d = sDec;
+    for (int i = tid; i < tk.count; i += SAH_THREADS) {
+        const uint32_t id = idxIn[tk.first + i];
+        if (d.axis < 0) { primFinal[tk.first + i] = id; continue; }
+        bool goLeft;
+        if (d.axis == 3) goLeft = i < d.leftCount;
+        else {
+            const float4 lo = pLo[id], hi = pHi[id];
+            const float c = d.axis == 0 ? 0.5f * (lo.x + hi.x) : d.axis == 1 ? 0.5f * (lo.y + hi.y) : 0.5f * (lo.z + hi.z);
+            goLeft = bld::sah_bin_of(c, cmin[d.axis], ext[d.axis]) <= d.split;
+        }
+        if (goLeft) idxOut[tk.first + atomicAdd(&sNl, 1)] = id;
+        else idxOut[tk.first + tk.count - 1 - atomicAdd(&sNr, 1)] = id;
     }
 }
 
@@ -512,17 +653,16 @@ int build_bvh(tmpt_scene* s, unsigned flags) {
     const int n = s->triCount;
     cudaStream_t st = s->stream;
     const float cInner = 1.0f, cTri = 1.0f;
-    (void)flags;
 
     DevBuf<uint32_t> bounds, primA, primB, visits, counters, qCount;
     DevBuf<uint64_t> keysA, keysB;
-    DevBuf<int> left, right, parent;
+    DevBuf<int> left, right, parent, first;
     DevBuf<float4> lo, hi;
     DevBuf<float> sah;
     DevBuf<bld::WorkItem> qA, qB;
     CU_TRY(bounds.alloc(6)); CU_TRY(primA.alloc(n)); CU_TRY(primB.alloc(n)); CU_TRY(keysA.alloc(n)); CU_TRY(keysB.alloc(n));
     CU_TRY(visits.alloc(n)); CU_TRY(counters.alloc(4)); CU_TRY(qCount.alloc(2));
-    CU_TRY(left.alloc(n)); CU_TRY(right.alloc(n)); CU_TRY(parent.alloc(2 * (size_t)n));
+    CU_TRY(left.alloc(2 * (size_t)n)); CU_TRY(right.alloc(2 * (size_t)n)); CU_TRY(parent.alloc(2 * (size_t)n)); CU_TRY(first.alloc(2 * (size_t)n));
     CU_TRY(lo.alloc(2 * (size_t)n)); CU_TRY(hi.alloc(2 * (size_t)n)); CU_TRY(sah.alloc(2));
     CU_TRY(qA.alloc(n)); CU_TRY(qB.alloc(n));
     CU_TRY(cudaMalloc((void**)&s->d_nodes, (size_t)n * bvh::NODE_F4 * sizeof(float4)));
@@ -537,20 +677,54 @@ int build_bvh(tmpt_scene* s, unsigned flags) {
 
     const int B = 256, G = div_up(n, B);
     LAUNCH(k_prim_bounds, G, B, 0, st, s->d_tris9, n, bounds.p);
-    LAUNCH(k_morton, G, B, 0, st, s->d_tris9, n, bounds.p, keysA.p, primA.p);
-    const int passes = 16;  // 63-bit keys, 4 bits per pass; an even count leaves the result in A
-    const int sortSmem = 16 * SORT_THREADS * (int)sizeof(uint32_t);
-    CU_TRY(cudaFuncSetAttribute(k_radix_sort, cudaFuncAttributeMaxDynamicSharedMemorySize, sortSmem));
-    LAUNCH(k_radix_sort, 1, SORT_THREADS, sortSmem, st, keysA.p, primA.p, keysB.p, primB.p, n, passes);
-    LAUNCH(k_leaf_boxes, G, B, 0, st, s->d_tris9, primA.p, n, bounds.p, cTri, lo.p, hi.p);
-
-    bld::BinTree t{n, keysA.p, left.p, right.p, parent.p, lo.p, hi.p, visits.p};
+    bld::BinTree t{n, keysA.p, left.p, right.p, parent.p, lo.p, hi.p, first.p, visits.p};
     bld::SahParams sp{cInner, cTri, bvh::MAX_LEAF_TRIS};
-    bld::WideOut w{s->d_nodes, s->d_tris, s->d_tris9, primA.p, counters.p, sah.p};
+    const uint32_t* primOrder = primA.p;
     int rootIsLeaf = (n == 1);
+    if (flags & TMPT_BUILD_LBVH) {
+        LAUNCH(k_morton, G, B, 0, st, s->d_tris9, n, bounds.p, keysA.p, primA.p);
+        const int passes = 16;  // 63-bit keys, 4 bits per pass; an even count leaves the result in A
+        const int sortSmem = 16 * SORT_THREADS * (int)sizeof(uint32_t);
+        CU_TRY(cudaFuncSetAttribute(k_radix_sort, cudaFuncAttributeMaxDynamicSharedMemorySize, sortSmem));
+        LAUNCH(k_radix_sort, 1, SORT_THREADS, sortSmem, st, keysA.p, primA.p, keysB.p, primB.p, n, passes);
+        LAUNCH(k_leaf_boxes, G, B, 0, st, s->d_tris9, primA.p, n, bounds.p, cTri, lo.p, hi.p, first.p);
+        if (n > 1) {
+            LAUNCH(k_karras, div_up(n - 1, B), B, 0, st, t);
+            LAUNCH(k_refit, G, B, 0, st, t, sp);
+        }
+        s->info.builder = TMPT_BUILD_LBVH;
+    } else {
+        // binned SAH, level by level; tasks double-buffer in the collapse queues' memory
+        DevBuf<float4> pLo, pHi;
+        DevBuf<uint32_t> primFinal, nodeCounter;
+        DevBuf<SahTask> tqA, tqB;
+        CU_TRY(pLo.alloc(n)); CU_TRY(pHi.alloc(n)); CU_TRY(primFinal.alloc(n)); CU_TRY(nodeCounter.alloc(1));
+        CU_TRY(tqA.alloc(n)); CU_TRY(tqB.alloc(n));
+        LAUNCH(k_prim_boxes, G, B, 0, st, s->d_tris9, n, bounds.p, pLo.p, pHi.p, primA.p);
+        const SahTask rootTask{0, 0, n};
+        const uint32_t one = 1, zero = 0;
+        CU_TRY(cudaMemcpyAsync(tqA.p, &rootTask, sizeof rootTask, cudaMemcpyHostToDevice, st));
+        CU_TRY(cudaMemcpyAsync(nodeCounter.p, &one, 4, cudaMemcpyHostToDevice, st));
+        uint32_t* idxIn = primA.p; uint32_t* idxOut = primB.p;
+        SahTask* qin = tqA.p; SahTask* qout = tqB.p;
+        uint32_t count = 1;
+        int levels = 0;
+        while (count > 0) {
+            CU_TRY(cudaMemcpyAsync(qCount.p, &zero, 4, cudaMemcpyHostToDevice, st));
+            LAUNCH(k_sah_level, count, SAH_THREADS, 0, st, t, pLo.p, pHi.p, idxIn, idxOut, primFinal.p, qin, qout, qCount.p, nodeCounter.p, sp);
+            CU_TRY(cudaMemcpyAsync(&count, qCount.p, 4, cudaMemcpyDeviceToHost, st));
+            CU_TRY(cudaStreamSynchronize(st));
+            std::swap(idxIn, idxOut);
+            std::swap(qin, qout);
+            if (++levels > 4096) return tmpt::fail(TMPT_ERR_CUDA, "SAH build did not terminate");
+        }
+        // the final order lives in primFinal; keep it in primA for the collapse (same stream, device copy)
+        CU_TRY(cudaMemcpyAsync(primA.p, primFinal.p, (size_t)n * sizeof(uint32_t), cudaMemcpyDeviceToDevice, st));
+        CU_TRY(cudaStreamSynchronize(st));
+        s->info.builder = TMPT_BUILD_DEFAULT;
+    }
+    bld::WideOut w{s->d_nodes, s->d_tris, s->d_tris9, primOrder, counters.p, sah.p};
     if (n > 1) {
-        LAUNCH(k_karras, div_up(n - 1, B), B, 0, st, t);
-        LAUNCH(k_refit, G, B, 0, st, t, sp);
         float4 rootHi;
         CU_TRY(cudaMemcpyAsync(&rootHi, hi.p, sizeof rootHi, cudaMemcpyDeviceToHost, st));
         CU_TRY(cudaStreamSynchronize(st));
@@ -589,7 +763,6 @@ int build_bvh(tmpt_scene* s, unsigned flags) {
     s->info.leaf_count = (int)hc[2];
     s->info.max_depth = (int)hc[3] + 1;
     s->info.max_leaf_tris = bvh::MAX_LEAF_TRIS;
-    s->info.builder = TMPT_BUILD_LBVH;
     for (int k = 0; k < 3; ++k) {
         s->info.bounds_min[k] = bld::ordered_to_float(hb[k]);
         s->info.bounds_max[k] = bld::ordered_to_float(hb[3 + k]);
