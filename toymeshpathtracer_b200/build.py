@@ -17,7 +17,8 @@ LIB = os.path.join(HERE, "libtmpt.so")
 BIN = os.path.join(HERE, "bin", "TrimeshTracer")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
-CUFLAGS = ["-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC,-ffp-contract=off,-fno-fast-math,-Wall", "-Xptxas", "-v"]
+CUFLAGS = ["-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC,-ffp-contract=off,-fno-fast-math,-Wall", "-Xptxas", "-v"] + \
+    os.environ.get("TMPT_NVCC_EXTRA", "").split()
 CXXFLAGS = ["-O2", "-std=c++17", "-fPIC", "-ffp-contract=off", "-fno-fast-math", "-Wall"]
 
 

@@ -40,7 +40,7 @@ constexpr uint32_t LEAF_BIT = 0x80000000u;
 constexpr int MAX_LEAF_TRIS = 8;
 constexpr int WIDTH = 4;
 constexpr int NODE_F4 = 7;              // float4 rows per node (112 bytes)
-constexpr int STACK_SIZE = 64;         // entries; the builder reports the depth it needs
+constexpr int STACK_SIZE = 48;         // entries; the builder reports the depth it needs
 constexpr uint32_t NONE = 0xFFFFFFFFu;     // empty child / empty stack; no leaf ref reaches it (slots < 2^28 - 1)
 constexpr uint32_t STACK_OVERFLOW = 1;  // bit in the scene's device status word
 
@@ -92,32 +92,11 @@ TMPT_HD void hit_payload(const SceneView& sc, int id, float u, float v, ex::V3& 
     normal = ex::normalize(ex::cross(ex::sub(v1, v0), ex::sub(v2, v0)));
 }
 
-TMPT_HD float fmin3(float a, float b, float c) { return fminf(fminf(a, b), c); }
-TMPT_HD float fmax3(float a, float b, float c) { return fmaxf(fmaxf(a, b), c); }
-TMPT_HD float fma_(float a, float b, float c) {
-#ifdef __CUDA_ARCH__
-    return __fmaf_rn(a, b, c);
-#else
-    return a * b + c;  // conservativeness does not depend on fusing
-#endif
-}
-
-// Ray-constant part of the slab test: t = b * idir - o * idir.
-struct RaySlab {
-    float idx, idy, idz;  // 1 / dir
-    float ox, oy, oz;     // orig / dir
-};
 // A zero (or denormal) direction component would make idir infinite and b*inf - o*inf a NaN
 // or a wrongly signed infinity; it is replaced by +-1e-20, for which the slab interval is
 // "everything" when the origin lies between the planes and empty otherwise -- exactly the
 // test an axis-parallel ray needs.
 TMPT_HD float safe_dir(float d) { return fabsf(d) < 1.0e-20f ? copysignf(1.0e-20f, d) : d; }
-TMPT_HD RaySlab make_slab(ex::V3 o, ex::V3 d) {
-    RaySlab r;
-    r.idx = 1.0f / safe_dir(d.x); r.idy = 1.0f / safe_dir(d.y); r.idz = 1.0f / safe_dir(d.z);
-    r.ox = o.x * r.idx; r.oy = o.y * r.idy; r.oz = o.z * r.idz;
-    return r;
-}
 
 // Work counters of an instrumented pass (bench.py's roofline: box and triangle tests per ray).
 struct TravStats {
@@ -125,8 +104,36 @@ struct TravStats {
     unsigned long long tris = 0;   // exact triangle tests
 };
 
+// 128-bit read-only loads.  On the device they are volatile asm so that the compiler keeps
+// them where they are written: it otherwise SINKS a triangle's v0 row below the determinant
+// test to save a load on the early exit, which turns one L2 round trip per triangle into two
+// dependent ones (ncu source view, profiles/).
+TMPT_HD float4 ld_row(const float4* p) {
+#ifdef __CUDA_ARCH__
+    float4 v;
+    asm volatile("ld.global.nc.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+    return v;
+#else
+    return *p;
+#endif
+}
+TMPT_HD float f4c(const float4& v, int k) { return k == 0 ? v.x : k == 1 ? v.y : k == 2 ? v.z : v.w; }
+TMPT_HD float fmaf_(float a, float b, float c) {
+#ifdef __CUDA_ARCH__
+    return __fmaf_rn(a, b, c);
+#else
+    return a * b + c;  // conservativeness does not depend on fusing
+#endif
+}
+
 // One traversal, closest (ANY=false) or any-hit (ANY=true).
 //
+// Node step: the near / far slab planes are picked by the ray's octant through the LOAD
+// ADDRESS (rows lo/hi of an axis are adjacent), so a child costs 6 FMA + two 3-input min/max
+// (FMNMX3 on sm_100a).  The nearest hit child is found by a 4-way integer min over
+// (entry-distance bits with the child slot in the two low mantissa bits) and entered
+// directly; the other hit children are pushed unsorted, branch-free, as 64-bit
+// (entry distance, ref) pairs and culled against the current best t when popped.
 // Culling keeps a child when tNear <= tFar with tFar clipped to the CURRENT best t -- "<=",
 // not "<", so that a triangle in another leaf with bit-equal t and a lower index is still
 // tested.  The candidate rule is the lexicographic minimum of (t, id).
@@ -134,60 +141,64 @@ template <bool ANY, bool STATS = false>
 TMPT_HD HitRec traverse(const SceneView& sc, ex::V3 o, ex::V3 d, float tMin, float tMax, TravStats* stats = nullptr) {
     HitRec best;
     best.id = -1; best.t = tMax; best.u = 0.0f; best.v = 0.0f;
-    const RaySlab rs = make_slab(o, d);
+    const float sdx = safe_dir(d.x), sdy = safe_dir(d.y), sdz = safe_dir(d.z);
+    const float idx = 1.0f / sdx, idy = 1.0f / sdy, idz = 1.0f / sdz;
+    const float ox = o.x * idx, oy = o.y * idy, oz = o.z * idz;
+    const uint32_t sx = sdx < 0.0f ? 1u : 0u, sy = sdy < 0.0f ? 1u : 0u, sz = sdz < 0.0f ? 1u : 0u;
 
-    uint32_t stackRef[STACK_SIZE];
-    float stackT[STACK_SIZE];
+    unsigned long long stack[STACK_SIZE];  // (entry distance bits << 32) | ref
     int sp = 0;
+    bool overflow = false;
     uint32_t cur = sc.rootRef;
 
     while (cur != NONE) {
         if (!ref_is_leaf(cur)) {
             if (STATS) ++stats->nodes;
             const float4* n = sc.nodes + (size_t)cur * NODE_F4;
-            const float4 lox = TMPT_LDG4(n + 0), hix = TMPT_LDG4(n + 1);
-            const float4 loy = TMPT_LDG4(n + 2), hiy = TMPT_LDG4(n + 3);
-            const float4 loz = TMPT_LDG4(n + 4), hiz = TMPT_LDG4(n + 5);
-            const float4 refsf = TMPT_LDG4(n + 6);
-            const float lo_x[4] = {lox.x, lox.y, lox.z, lox.w}, hi_x[4] = {hix.x, hix.y, hix.z, hix.w};
-            const float lo_y[4] = {loy.x, loy.y, loy.z, loy.w}, hi_y[4] = {hiy.x, hiy.y, hiy.z, hiy.w};
-            const float lo_z[4] = {loz.x, loz.y, loz.z, loz.w}, hi_z[4] = {hiz.x, hiz.y, hiz.z, hiz.w};
-            const uint32_t refs[4] = {ex::f2u(refsf.x), ex::f2u(refsf.y), ex::f2u(refsf.z), ex::f2u(refsf.w)};
-
-            uint32_t nextRef = NONE;
-            float nextT = 0.0f;
+            const float4 nx = ld_row(n + sx), fx = ld_row(n + (sx ^ 1u));
+            const float4 ny = ld_row(n + 2 + sy), fy = ld_row(n + 2 + (sy ^ 1u));
+            const float4 nz = ld_row(n + 4 + sz), fz = ld_row(n + 4 + (sz ^ 1u));
+            const float4 rf = ld_row(n + 6);
+            uint32_t key[4], ref[4];
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
-                float tx0 = fma_(lo_x[k], rs.idx, -rs.ox), tx1 = fma_(hi_x[k], rs.idx, -rs.ox);
-                float ty0 = fma_(lo_y[k], rs.idy, -rs.oy), ty1 = fma_(hi_y[k], rs.idy, -rs.oy);
-                float tz0 = fma_(lo_z[k], rs.idz, -rs.oz), tz1 = fma_(hi_z[k], rs.idz, -rs.oz);
-                float tn = fmaxf(fmax3(fminf(tx0, tx1), fminf(ty0, ty1), fminf(tz0, tz1)), tMin);
-                float tf = fminf(fmin3(fmaxf(tx0, tx1), fmaxf(ty0, ty1), fmaxf(tz0, tz1)), best.t);
-                if (tn <= tf && refs[k] != NONE) {
-                    if (nextRef == NONE) {
-                        nextRef = refs[k]; nextT = tn;
-                    } else {
-                        uint32_t pushRef = refs[k]; float pushT = tn;
-                        if (tn < nextT) { pushRef = nextRef; pushT = nextT; nextRef = refs[k]; nextT = tn; }
-                        if (sp < STACK_SIZE) { stackRef[sp] = pushRef; stackT[sp] = pushT; ++sp; }
-                        else if (sc.status) *sc.status |= STACK_OVERFLOW;
+                const float a = fmaxf(fmaxf(fmaf_(f4c(nx, k), idx, -ox), fmaf_(f4c(ny, k), idy, -oy)), fmaxf(fmaf_(f4c(nz, k), idz, -oz), tMin));
+                const float b = fminf(fminf(fmaf_(f4c(fx, k), idx, -ox), fmaf_(f4c(fy, k), idy, -oy)), fminf(fmaf_(f4c(fz, k), idz, -oz), best.t));
+                ref[k] = ex::f2u(f4c(rf, k));
+                // clearing the two low mantissa bits only lowers the distance: still conservative for the pop-time cull
+                key[k] = (a <= b && ref[k] != NONE) ? ((ex::f2u(a) & ~3u) | (uint32_t)k) : 0xFFFFFFFFu;
+            }
+            const uint32_t k01 = key[0] < key[1] ? key[0] : key[1], k23 = key[2] < key[3] ? key[2] : key[3];
+            const uint32_t kmin = k01 < k23 ? k01 : k23;
+            if (kmin == 0xFFFFFFFFu) {
+                cur = NONE;
+            } else {
+                const uint32_t ks = kmin & 3u;
+                cur = ks == 0 ? ref[0] : ks == 1 ? ref[1] : ks == 2 ? ref[2] : ref[3];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    if (key[k] != 0xFFFFFFFFu && (uint32_t)k != ks) {
+                        if (sp < STACK_SIZE) stack[sp++] = ((unsigned long long)key[k] << 32) | ref[k];
+                        else overflow = true;
                     }
                 }
             }
-            cur = nextRef;
         } else {
             const uint32_t first = leaf_first(cur);
             const int cnt = leaf_count(cur);
             if (STATS) stats->tris += (unsigned)cnt;
             for (int k = 0; k < cnt; ++k) {
                 const float4* tp = sc.tris + (size_t)(first + k) * 3;
-                const float4 a = TMPT_LDG4(tp + 0), b = TMPT_LDG4(tp + 1), c = TMPT_LDG4(tp + 2);
+                const float4 a = ld_row(tp + 0), b = ld_row(tp + 1), c = ld_row(tp + 2);
                 float t, u, v;
                 if (mt_exact(o, d, ex::v3(a.x, a.y, a.z), ex::v3(b.x, b.y, b.z), ex::v3(c.x, c.y, c.z), tMin, tMax, t, u, v)) {
                     const int id = (int)ex::f2u(a.w);
                     if (t < best.t || (t == best.t && best.id >= 0 && id < best.id)) {
                         best.t = t; best.id = id; best.u = u; best.v = v;
-                        if (ANY) return best;
+                        if (ANY) {
+                            if (overflow && sc.status) *sc.status |= STACK_OVERFLOW;
+                            return best;
+                        }
                     }
                 }
             }
@@ -195,10 +206,11 @@ TMPT_HD HitRec traverse(const SceneView& sc, ex::V3 o, ex::V3 d, float tMin, flo
         }
         // pop: skip entries that the shrinking best.t has already culled
         while (cur == NONE && sp > 0) {
-            --sp;
-            if (stackT[sp] <= best.t) cur = stackRef[sp];
+            const unsigned long long e = stack[--sp];
+            if (ex::u2f((uint32_t)(e >> 32)) <= best.t) cur = (uint32_t)e;
         }
     }
+    if (overflow && sc.status) *sc.status |= STACK_OVERFLOW;
     return best;
 }
 

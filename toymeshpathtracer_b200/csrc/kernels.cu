@@ -23,8 +23,8 @@
 #include "build_logic.cuh"
 #include "common.h"
 #include "integrator.cuh"
-#include "trace.cuh"
 #include "warpq.cuh"
+#include "wtrace.cuh"
 
 // ------------------------------------------------------------------------------------------
 // error plumbing
@@ -429,64 +429,32 @@ __global__ void __launch_bounds__(128) k_hit_scene(bvh::SceneView sc, const floa
     if (STATS) flush_stats(stats, nr, ts, nh);
 }
 
-// Persistent form of K2/K3: warps stay resident and every lane that finishes its ray is handed
-// the next one from a global counter (warp-aggregated atomic), so lanes do not idle while
-// their neighbours finish long rays.  FETCH_BELOW: refill when fewer lanes than this are busy.
-template <bool STATS, int FETCH_BELOW>
-__global__ void __launch_bounds__(128) k_hit_scene_persist(bvh::SceneView sc, const float* __restrict__ rays6, long long nRays, float tMin, float tMax,
-                                                            int anyHit, int* __restrict__ outID, float* __restrict__ outT, float* __restrict__ outPos,
-                                                            float* __restrict__ outNormal, unsigned long long* __restrict__ counter,
-                                                            unsigned long long* __restrict__ stats) {
-    const unsigned FULL = 0xffffffffu;
-    const int lane = threadIdx.x & 31;
-    uint32_t stackRef[trc::STACK];
-    float stackT[trc::STACK];
-    trc::Lane L;
-    L.id = -1; L.t = tMax; L.u = L.v = 0.0f;
-    long long ray = -1;
-    bool exhausted = false, alive = false;
+// K2/K3 through the warp-synchronous deferred-triangle traversal (wtrace.cuh)
+template <bool STATS, int TRI_MIN, int WALK_MIN>
+__global__ void __launch_bounds__(128) k_hit_scene_wt(bvh::SceneView sc, const float* __restrict__ rays6, long long nRays, float tMin, float tMax,
+                                                       int anyHit, int* __restrict__ outID, float* __restrict__ outT, float* __restrict__ outPos,
+                                                       float* __restrict__ outNormal, unsigned long long* __restrict__ stats) {
     bvh::TravStats ts;
     unsigned long long nr = 0, nh = 0;
-    for (;;) {
-        const bool need = ray < 0;
-        const unsigned needMask = __ballot_sync(FULL, need);
-        if (needMask && !exhausted) {
-            const int cnt = __popc(needMask);
-            unsigned long long base = 0;
-            if (lane == 0) base = atomicAdd(counter, (unsigned long long)cnt);
-            base = __shfl_sync(FULL, base, 0);
-            if (need) {
-                const long long i = (long long)base + __popc(needMask & ((1u << lane) - 1u));
-                if (i < nRays) {
-                    const float* r = rays6 + i * 6;
-                    alive = trc::lane_start(L, ex::v3(r[0], r[1], r[2]), ex::v3(r[3], r[4], r[5]), tMin, tMax, anyHit != 0, sc.rootRef);
-                    ray = i;
-                }
-            }
-            exhausted = (long long)base + cnt >= nRays;
-        }
-        if (__all_sync(FULL, ray < 0)) break;
-        if (ray >= 0) {
-            while (alive) {
-                alive = trc::lane_step<STATS>(L, sc, stackRef, stackT, &ts);
-                if (!exhausted && __popc(__activemask()) < FETCH_BELOW) break;
-            }
-            if (!alive) {
-                if (STATS) { ++nr; nh += L.id >= 0; }
-                if (anyHit) outID[ray] = L.id < 0 ? -1 : 1;
-                else {
-                    outID[ray] = L.id;
-                    if (L.id >= 0) {
-                        if (outT) outT[ray] = L.t;
-                        if (outPos || outNormal) {
-                            ex::V3 pos, nrm;
-                            bvh::hit_payload(sc, L.id, L.u, L.v, pos, nrm);
-                            if (outPos) { outPos[ray * 3] = pos.x; outPos[ray * 3 + 1] = pos.y; outPos[ray * 3 + 2] = pos.z; }
-                            if (outNormal) { outNormal[ray * 3] = nrm.x; outNormal[ray * 3 + 1] = nrm.y; outNormal[ray * 3 + 2] = nrm.z; }
-                        }
-                    }
-                }
-                ray = -1;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    const long long rounds = (nRays + stride - 1) / stride;
+    for (long long rnd = 0; rnd < rounds; ++rnd) {
+        const long long i = rnd * stride + (long long)blockIdx.x * blockDim.x + threadIdx.x;
+        const bool active = i < nRays;
+        ex::V3 o = ex::v3(0, 0, 0), d = ex::v3(0, 0, 1);
+        if (active) { const float* r = rays6 + i * 6; o = ex::v3(r[0], r[1], r[2]); d = ex::v3(r[3], r[4], r[5]); }
+        const bvh::HitRec h = wt::traverse_warp<STATS, TRI_MIN, WALK_MIN>(sc, o, d, tMin, tMax, anyHit != 0, active, &ts);
+        if (!active) continue;
+        if (STATS) { ++nr; nh += h.id >= 0; }
+        if (anyHit) { outID[i] = h.id < 0 ? -1 : 1; continue; }
+        outID[i] = h.id;
+        if (h.id >= 0) {
+            if (outT) outT[i] = h.t;
+            if (outPos || outNormal) {
+                ex::V3 pos, nrm;
+                bvh::hit_payload(sc, h.id, h.u, h.v, pos, nrm);
+                if (outPos) { outPos[i * 3] = pos.x; outPos[i * 3 + 1] = pos.y; outPos[i * 3 + 2] = pos.z; }
+                if (outNormal) { outNormal[i * 3] = nrm.x; outNormal[i * 3 + 1] = nrm.y; outNormal[i * 3 + 2] = nrm.z; }
             }
         }
     }
@@ -603,8 +571,8 @@ __device__ __forceinline__ int owned_row_to_global(int r, int stripeRows, int ra
     return (ls * world + rank) * stripeRows + (r - ls * stripeRows);
 }
 
-template <bool STATS>
-__global__ void __launch_bounds__(256) k_render(const RenderParams p) {
+template <bool STATS, int THREADS, int MINB>
+__global__ void __launch_bounds__(THREADS, MINB) k_render(const RenderParams p) {
     const int lane = threadIdx.x & 31;
     unsigned long long rays = 0;
     bvh::TravStats ts;
@@ -652,7 +620,9 @@ struct DevBuf {
 int build_bvh(tmpt_scene* s, unsigned flags) {
     const int n = s->triCount;
     cudaStream_t st = s->stream;
-    const float cInner = 1.0f, cTri = 1.0f;
+    // SAH constants: one binary inner node vs one exact triangle test (TMPT_SAH_CI / TMPT_SAH_MAXLEAF: tuning overrides)
+    const float cInner = getenv("TMPT_SAH_CI") ? (float)atof(getenv("TMPT_SAH_CI")) : 1.0f, cTri = 1.0f;
+    const int maxLeaf = getenv("TMPT_SAH_MAXLEAF") ? std::max(1, std::min(bvh::MAX_LEAF_TRIS, atoi(getenv("TMPT_SAH_MAXLEAF")))) : bvh::MAX_LEAF_TRIS;
 
     DevBuf<uint32_t> bounds, primA, primB, visits, counters, qCount;
     DevBuf<uint64_t> keysA, keysB;
@@ -678,7 +648,7 @@ int build_bvh(tmpt_scene* s, unsigned flags) {
     const int B = 256, G = div_up(n, B);
     LAUNCH(k_prim_bounds, G, B, 0, st, s->d_tris9, n, bounds.p);
     bld::BinTree t{n, keysA.p, left.p, right.p, parent.p, lo.p, hi.p, first.p, visits.p};
-    bld::SahParams sp{cInner, cTri, bvh::MAX_LEAF_TRIS};
+    bld::SahParams sp{cInner, cTri, maxLeaf};
     const uint32_t* primOrder = primA.p;
     int rootIsLeaf = (n == 1);
     if (flags & TMPT_BUILD_LBVH) {
@@ -904,6 +874,8 @@ extern "C" int tmpt_hit_scene(const tmpt_scene* s, const float* rays6, int64_t n
     }
     const int B = 128;
     const int G = (int)std::min<long long>(div_up(nRays, B), (long long)s->smCount * 64);
+    // Experimental traversal engines kept for A/B runs (tools/exp_traverse.py; results in profiles/ and DESIGN.md 5):
+    // 5 = warp queue (warpq.cuh), 10/11 = warp-synchronous deferred triangle tests (wtrace.cuh).  Default 0.
     static const int variant = getenv("TMPT_HIT_KERNEL") ? atoi(getenv("TMPT_HIT_KERNEL")) : 0;
     if (variant > 0 && mode != TMPT_HIT_BRUTE) {
         int perSM = 0;
@@ -915,25 +887,16 @@ extern "C" int tmpt_hit_scene(const tmpt_scene* s, const float* rays6, int64_t n
             LAUNCH((k_hit_scene_wq<false, R, N>), GP, B, 0, st, s->view, dRays, (long long)nRays, tMin, tMax, mode == TMPT_HIT_ANY, dID, dT, \
                    dPos, dNrm, s->d_fetchCounter, nullptr);                                                                     \
         } else
-        WQ_CASE(5, 8, 12) WQ_CASE(6, 4, 8) WQ_CASE(7, 8, 20) WQ_CASE(8, 16, 12) WQ_CASE(9, 1, 12)
+        WQ_CASE(5, 8, 12)
 #undef WQ_CASE
-        if (variant == 1) {
-            CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, k_hit_scene_persist<false, 24>, B, 0));
-            const int GP = (int)std::min<long long>(div_up(nRays, B), (long long)s->smCount * std::max(perSM, 1));
-            LAUNCH((k_hit_scene_persist<false, 24>), GP, B, 0, st, s->view, dRays, (long long)nRays, tMin, tMax, mode == TMPT_HIT_ANY, dID, dT, dPos, dNrm, s->d_fetchCounter, nullptr);
-        } else if (variant == 2) {
-            CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, k_hit_scene_persist<false, 16>, B, 0));
-            const int GP = (int)std::min<long long>(div_up(nRays, B), (long long)s->smCount * std::max(perSM, 1));
-            LAUNCH((k_hit_scene_persist<false, 16>), GP, B, 0, st, s->view, dRays, (long long)nRays, tMin, tMax, mode == TMPT_HIT_ANY, dID, dT, dPos, dNrm, s->d_fetchCounter, nullptr);
-        } else if (variant == 3) {
-            CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, k_hit_scene_persist<false, 32>, B, 0));
-            const int GP = (int)std::min<long long>(div_up(nRays, B), (long long)s->smCount * std::max(perSM, 1));
-            LAUNCH((k_hit_scene_persist<false, 32>), GP, B, 0, st, s->view, dRays, (long long)nRays, tMin, tMax, mode == TMPT_HIT_ANY, dID, dT, dPos, dNrm, s->d_fetchCounter, nullptr);
-        } else {
-            CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, k_hit_scene_persist<false, 0>, B, 0));
-            const int GP = (int)std::min<long long>(div_up(nRays, B), (long long)s->smCount * std::max(perSM, 1));
-            LAUNCH((k_hit_scene_persist<false, 0>), GP, B, 0, st, s->view, dRays, (long long)nRays, tMin, tMax, mode == TMPT_HIT_ANY, dID, dT, dPos, dNrm, s->d_fetchCounter, nullptr);
-        }
+#define WT_CASE(V, T, W)                                                                                                        \
+        if (variant == V) {                                                                                                     \
+            LAUNCH((k_hit_scene_wt<false, T, W>), G, B, 0, st, s->view, dRays, (long long)nRays, tMin, tMax, mode == TMPT_HIT_ANY, dID, dT, dPos, \
+                   dNrm, nullptr);                                                                                              \
+        } else
+        WT_CASE(10, 16, 8) WT_CASE(11, 8, 8)
+#undef WT_CASE
+        return tmpt::fail(TMPT_ERR_ARG, "TMPT_HIT_KERNEL=%d: no such traversal variant", variant);
     } else if (mode == TMPT_HIT_CLOSEST) LAUNCH((k_hit_scene<TMPT_HIT_CLOSEST, false>), G, B, 0, st, s->view, dRays, (long long)nRays, tMin, tMax, dID, dT, dPos, dNrm, nullptr);
     else if (mode == TMPT_HIT_ANY) LAUNCH((k_hit_scene<TMPT_HIT_ANY, false>), G, B, 0, st, s->view, dRays, (long long)nRays, tMin, tMax, dID, dT, dPos, dNrm, nullptr);
     else LAUNCH((k_hit_scene<TMPT_HIT_BRUTE, false>), G, B, 0, st, s->view, dRays, (long long)nRays, tMin, tMax, dID, dT, dPos, dNrm, nullptr);
@@ -982,12 +945,26 @@ static int launch_render(const tmpt_scene* s, const tmpt_camera* camera, int wid
     p.stats = statsDev;
     if (p.numTiles == 0) return TMPT_OK;
     CU_TRY(cudaMemsetAsync(s->d_tileCounter, 0, sizeof(uint32_t), st));
+    static const int cfg = getenv("TMPT_RENDER_CFG") ? atoi(getenv("TMPT_RENDER_CFG")) : 0;
     int perSM = 0;
-    CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, k_render<false>, 256, 0));
-    if (perSM < 1) perSM = 1;
-    const int grid = std::min(s->smCount * perSM, div_up(p.numTiles, 8));
-    if (statsDev) LAUNCH(k_render<true>, grid, 256, 0, st, p);
-    else LAUNCH(k_render<false>, grid, 256, 0, st, p);
+#define RENDER_CASE(C, T, M)                                                                              \
+    if (cfg == C && !statsDev) {                                                                          \
+        CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, k_render<false, T, M>, T, 0));       \
+        const int grid = std::min(s->smCount * std::max(perSM, 1), div_up(p.numTiles, T / 32));           \
+        LAUNCH((k_render<false, T, M>), grid, T, 0, st, p);                                               \
+    } else
+    RENDER_CASE(1, 256, 3) RENDER_CASE(2, 128, 6) RENDER_CASE(3, 128, 8) RENDER_CASE(4, 128, 4) RENDER_CASE(5, 64, 12) RENDER_CASE(6, 512, 2) RENDER_CASE(7, 256, 1) RENDER_CASE(8, 256, 2)
+    RENDER_CASE(9, 256, 5) RENDER_CASE(10, 256, 6) RENDER_CASE(11, 128, 10) RENDER_CASE(12, 128, 12) RENDER_CASE(13, 512, 3) RENDER_CASE(14, 1024, 1)
+    RENDER_CASE(15, 128, 16) RENDER_CASE(16, 64, 20)
+#undef RENDER_CASE
+    {
+        // default: 256 threads x 4 CTAs/SM = 32 warps/SM at 64 registers (sweep in profiles/r1_tuning_sweeps.txt:
+        // 24 warps at 77 registers is 10 % slower, 40 warps at 48 registers spills and is 3 % slower)
+        CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, k_render<false, 256, 4>, 256, 0));
+        const int grid = std::min(s->smCount * std::max(perSM, 1), div_up(p.numTiles, 8));
+        if (statsDev) LAUNCH((k_render<true, 256, 4>), grid, 256, 0, st, p);
+        else LAUNCH((k_render<false, 256, 4>), grid, 256, 0, st, p);
+    }
     CU_TRY(cudaGetLastError());
     return TMPT_OK;
 }
