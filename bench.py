@@ -204,6 +204,21 @@ def bench_b200(args, scene, w, h, spp, rank, world, local_rank):
     info = sc.info()
 
     stream = torch.cuda.Stream(dev)
+    peer = None
+    if world > 1 and args.gather == "peer":
+        # every rank must agree: fall back to the NCCL gather if the IPC mapping fails anywhere
+        try:
+            peer = multigpu.PeerFrame(w, h, rank, world, local_rank)
+            ok = torch.ones(1, dtype=torch.int32, device=dev)
+        except Exception as e:  # noqa: BLE001
+            sys.stderr.write(f"[rank {rank}] peer frame unavailable ({e}); using the NCCL gather\n")
+            ok = torch.zeros(1, dtype=torch.int32, device=dev)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if int(ok.item()) == 0 and peer is not None:
+            peer.close()
+            peer = None
+        elif int(ok.item()) == 0:
+            peer = None
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
     launches0 = tm.launch_count()
     step_ms, step_rays = [], []
@@ -221,7 +236,7 @@ def bench_b200(args, scene, w, h, spp, rank, world, local_rank):
             flush.zero_()  # L2 flush between timed iterations (outside the event pair)
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record(stream)
-            frame, rays = multigpu.render_frame(sc, cam, w, h, spp, rank, world, group=None, device=dev)
+            frame, rays = multigpu.render_frame(sc, cam, w, h, spp, rank, world, group=None, device=dev, peer=peer)
             e1.record(stream)
         stream.synchronize()
         return e0.elapsed_time(e1), int(rays.item())
@@ -255,7 +270,7 @@ def bench_b200(args, scene, w, h, spp, rank, world, local_rank):
             img, rays, sec = sc.render(cam, w, h, spp)
         else:
             with torch.cuda.stream(stream):
-                fr, rr = multigpu.render_frame(sc, cam, w, h, spp, rank, world, device=dev)
+                fr, rr = multigpu.render_frame(sc, cam, w, h, spp, rank, world, device=dev, peer=peer)
                 img = fr.cpu() if rank == 0 else None
             stream.synchronize()
             rays = int(rr.item())
@@ -306,7 +321,8 @@ def bench_b200(args, scene, w, h, spp, rank, world, local_rank):
             "warmup": args.warmup, "ms_per_step": tot_ms / args.steps, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": f"{scene_label(scene)} {w}x{h} {spp}spp", "rays_per_frame": step_rays[-1] if world == 1 else tot_rays // args.steps,
-                       "parallelism": f"row stripes of {multigpu.DEFAULT_STRIPE_ROWS} over {world} GPU(s), BVH replica per GPU, frame gathered to rank 0",
+                       "parallelism": f"row stripes of {multigpu.DEFAULT_STRIPE_ROWS} over {world} GPU(s), BVH replica per GPU, " + (
+                           "pixels stored straight into rank 0's frame over NVLink (CUDA IPC peer memory)" if peer else "frame gathered to rank 0 (NCCL)"),
                        "l2": "flushed between timed iterations (256 MB write)", "bvh": {k: info[k] for k in ("node_count", "leaf_count", "max_depth", "sah_cost", "build_ms", "device_bytes")},
                        "scene_build_wall_ms": build_wall_ms},
             "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": 88, "d2h_bytes_per_step": w * h * 4 + 8,
@@ -317,6 +333,9 @@ def bench_b200(args, scene, w, h, spp, rank, world, local_rank):
         print(json.dumps(line), flush=True)
     sc.close()
     if world > 1:
+        dist.barrier()
+        if peer:
+            peer.close()
         dist.destroy_process_group()
     return 0
 
@@ -328,6 +347,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="sponza_1080p_64spp", choices=sorted(WORKLOADS))
+    ap.add_argument("--gather", default="peer", choices=["nccl", "peer"], help="N>1: how the frame reaches rank 0")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

@@ -131,6 +131,15 @@ int tmpt_stripe_rows(int height, int stripeRows, int rank, int worldSize); /* ro
 int tmpt_unpack_stripes(const uint8_t* gathered, int width, int height, int stripeRows, int worldSize,
                         int device, uint8_t* frame, void* stream);
 
+/* Frame memory that other ranks (processes) on the same node can write: rank 0 allocates
+ * the full-size frame and exports a 64-byte CUDA IPC handle; every other rank opens it and
+ * passes the mapped pointer as `peerFrame` to tmpt_render_stripes, so its pixels travel over
+ * NVLink / NVSwitch as plain stores in the render kernel's epilogue -- no gather step, no copy. */
+int tmpt_frame_alloc(int device, size_t bytes, void** outPtr, unsigned char outHandle[64]);
+int tmpt_frame_open(int device, const unsigned char handle[64], void** outPtr);
+int tmpt_frame_close(int device, void* ptr);   /* for pointers from tmpt_frame_open  */
+int tmpt_frame_free(int device, void* ptr);    /* for pointers from tmpt_frame_alloc */
+
 /* Instrumented passes: the same kernels compiled with work counters, for the roofline's
  * per-ray figures (never part of a timed run).  outStats: [0] rays (HitScene-equivalent
  * queries), [1] wide BVH nodes visited (4 box tests each), [2] exact triangle tests,

@@ -232,3 +232,47 @@ def test_cli_end_to_end(tmp_path):
         want, rays, _ = s.render(cam, 160, 90, 4)
     assert img.shape == (90, 160, 4) and (img == want[::-1]).all()
     assert abs(float(lines[2].split()[1]) - rays / 1000.0) < 0.06
+
+
+def _peer_worker(rank, world, port, w, h, spp, stripe, out):
+    import torch
+    import torch.distributed as dist
+    from toymeshpathtracer_b200 import multigpu
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)  # two ranks share the one GPU of this box: no NCCL
+    try:
+        sc = load_scene("suzanne")
+        cam = tm.camera_for_scene("suzanne.obj", sc["bounds_min"], sc["bounds_max"], w, h)
+        with tm.Scene(sc["tris"], device=0) as s:
+            peer = multigpu.PeerFrame(w, h, rank, world, 0)
+            st = torch.cuda.Stream()
+            with torch.cuda.stream(st):
+                frame, rays = multigpu.render_frame(s, cam, w, h, spp, rank, world, stripe=stripe, peer=peer)
+            st.synchronize()
+            total = rays.cpu()
+            dist.all_reduce(total)
+            if rank == 0:
+                full, full_rays, _ = s.render(cam, w, h, spp)
+                out.put(bool((frame.cpu().numpy() == full).all()) and int(total) == full_rays)
+            dist.barrier()
+            peer.close()
+    finally:
+        dist.destroy_process_group()
+
+
+def test_peer_frame_across_processes():
+    """The fused gather: two ranks (processes) write their stripes straight into rank 0's frame through CUDA IPC."""
+    import socket
+    import torch.multiprocessing as mp
+    with socket.socket() as sk:
+        sk.bind(("127.0.0.1", 0))
+        port = sk.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    out = ctx.SimpleQueue()
+    procs = [ctx.Process(target=_peer_worker, args=(r, 2, port, 96, 50, 2, 4, out)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(180)
+        assert p.exitcode == 0
+    assert out.get() is True

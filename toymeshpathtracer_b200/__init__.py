@@ -37,6 +37,7 @@ ABI_SYMBOLS = [
     "tmpt_render_stripes", "tmpt_stripe_rows", "tmpt_unpack_stripes", "tmpt_load_obj", "tmpt_free",
     "tmpt_camera_make", "tmpt_camera_for_scene", "tmpt_write_png", "tmpt_main", "tmpt_last_error",
     "tmpt_device_count", "tmpt_launch_count", "tmpt_render_stats", "tmpt_hit_scene_stats",
+    "tmpt_frame_alloc", "tmpt_frame_open", "tmpt_frame_close", "tmpt_frame_free",
 ]
 
 
@@ -86,6 +87,10 @@ def lib() -> C.CDLL:
     L.tmpt_unpack_stripes.argtypes = [vp, i32, i32, i32, i32, i32, vp, vp]
     L.tmpt_render_stats.argtypes = [vp, vp, i32, i32, i32, vp]
     L.tmpt_hit_scene_stats.argtypes = [vp, vp, i64, f32, f32, i32, vp]
+    L.tmpt_frame_alloc.argtypes = [i32, C.c_size_t, C.POINTER(vp), vp]
+    L.tmpt_frame_open.argtypes = [i32, vp, C.POINTER(vp)]
+    L.tmpt_frame_close.argtypes = [i32, vp]
+    L.tmpt_frame_free.argtypes = [i32, vp]
     L.tmpt_load_obj.argtypes = [C.c_char_p, C.POINTER(C.POINTER(C.c_float)), C.POINTER(i32), vp, vp]
     L.tmpt_free.argtypes = [vp]
     L.tmpt_free.restype = None

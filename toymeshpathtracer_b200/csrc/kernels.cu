@@ -1025,6 +1025,45 @@ extern "C" int tmpt_render(const tmpt_scene* cs, const tmpt_camera* camera, int 
     return check_status(s, st);
 }
 
+// ------------------------------------------------------------------------------------------
+// C ABI: peer-writable frame (CUDA IPC)
+// ------------------------------------------------------------------------------------------
+extern "C" int tmpt_frame_alloc(int device, size_t bytes, void** outPtr, unsigned char outHandle[64]) {
+    if (!outPtr || !outHandle || bytes == 0) return tmpt::fail(TMPT_ERR_ARG, "tmpt_frame_alloc: bad arguments");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    DeviceGuard guard(device);
+    if (!guard.ok) return tmpt::fail(TMPT_ERR_CUDA, "tmpt_frame_alloc: cudaSetDevice(%d) failed", device);
+    void* p = nullptr;
+    CU_TRY(cudaMalloc(&p, bytes));
+    cudaIpcMemHandle_t h;
+    cudaError_t e = cudaIpcGetMemHandle(&h, p);
+    if (e != cudaSuccess) { cudaFree(p); return tmpt::fail(TMPT_ERR_CUDA, "cudaIpcGetMemHandle: %s", cudaGetErrorString(e)); }
+    memcpy(outHandle, &h, 64);
+    *outPtr = p;
+    return TMPT_OK;
+}
+extern "C" int tmpt_frame_open(int device, const unsigned char handle[64], void** outPtr) {
+    if (!handle || !outPtr) return tmpt::fail(TMPT_ERR_ARG, "tmpt_frame_open: bad arguments");
+    DeviceGuard guard(device);
+    if (!guard.ok) return tmpt::fail(TMPT_ERR_CUDA, "tmpt_frame_open: cudaSetDevice(%d) failed", device);
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, 64);
+    CU_TRY(cudaIpcOpenMemHandle(outPtr, h, cudaIpcMemLazyEnablePeerAccess));
+    return TMPT_OK;
+}
+extern "C" int tmpt_frame_close(int device, void* ptr) {
+    if (!ptr) return TMPT_OK;
+    DeviceGuard guard(device);
+    CU_TRY(cudaIpcCloseMemHandle(ptr));
+    return TMPT_OK;
+}
+extern "C" int tmpt_frame_free(int device, void* ptr) {
+    if (!ptr) return TMPT_OK;
+    DeviceGuard guard(device);
+    CU_TRY(cudaFree(ptr));
+    return TMPT_OK;
+}
+
 // Instrumented passes (same kernels compiled with counters; never part of a timed run).
 extern "C" int tmpt_render_stats(const tmpt_scene* cs, const tmpt_camera* camera, int width, int height, int spp, uint64_t outStats[4]) {
     int rc = check_render_args(cs, camera, width, height, spp);

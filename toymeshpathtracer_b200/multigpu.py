@@ -67,15 +67,70 @@ def gather_frame(packed, width: int, height: int, stripe: int, rank: int, world:
     return frame
 
 
+class _DevArray:
+    """Zero-copy view of library-owned device memory for torch (``__cuda_array_interface__``)."""
+
+    def __init__(self, ptr: int, shape):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": "|u1", "data": (int(ptr), False), "version": 3, "strides": None}
+
+
+class PeerFrame:
+    """Rank 0's full-size frame, mapped into every rank through CUDA IPC (tmpt_frame_alloc / tmpt_frame_open).
+
+    With it the gather is fused into the render kernel: each rank's pixels are plain stores to
+    rank 0's HBM over NVLink / NVSwitch (`peerFrame` of tmpt_render_stripes); what remains of
+    the exchange step is the 8-byte ray-count all-reduce, which also orders the frame."""
+
+    def __init__(self, width: int, height: int, rank: int, world: int, device_index: int, group=None):
+        import ctypes as C
+
+        import torch
+        import torch.distributed as dist
+
+        from . import _check, lib
+        self.rank, self.world, self.dev = rank, world, device_index
+        self.shape = (height, width, 4)
+        self.ptr = C.c_void_p()
+        handle = (C.c_ubyte * 64)()
+        if rank == 0:
+            _check(lib().tmpt_frame_alloc(device_index, width * height * 4, C.byref(self.ptr), handle))
+        box = [bytes(handle)]
+        if world > 1:
+            dist.broadcast_object_list(box, src=0, group=group)
+        if rank != 0:
+            h = (C.c_ubyte * 64).from_buffer_copy(box[0])
+            _check(lib().tmpt_frame_open(device_index, h, C.byref(self.ptr)))
+        self.tensor = torch.as_tensor(_DevArray(self.ptr.value, self.shape), device=torch.device("cuda", device_index)) if rank == 0 else None
+
+    def close(self):
+        from . import lib
+        if self.ptr:
+            (lib().tmpt_frame_free if self.rank == 0 else lib().tmpt_frame_close)(self.dev, self.ptr)
+            self.ptr = None
+
+
 def render_frame(scene, camera, width: int, height: int, spp: int, rank: int, world: int, stripe: int = DEFAULT_STRIPE_ROWS,
-                 group=None, device=None):
+                 group=None, device=None, peer: "PeerFrame | None" = None):
     """One frame across `world` ranks.  Returns (frame uint8 CUDA tensor on rank 0 else None, local ray count tensor).
 
     Asynchronous on torch's current stream of `device` apart from the collective's own
-    synchronisation; the caller brackets it with CUDA events."""
+    synchronisation; the caller brackets it with CUDA events.  With `peer` the pixels go
+    straight into rank 0's frame (no gather); a one-element all-reduce enqueued behind every
+    rank's render kernel orders the frame on rank 0."""
     import torch
 
     device = device or torch.device("cuda", scene.device)
+    if peer is not None:
+        import torch.distributed as dist
+        rays = torch.zeros(1, dtype=torch.int64, device=device)
+        stream = torch.cuda.current_stream(device).cuda_stream
+        if stream == 0:
+            raise RuntimeError("render_frame: run inside `with torch.cuda.stream(torch.cuda.Stream())` (non-default stream)")
+        scene.render_stripes(camera, width, height, spp, stripe, rank, world, 0, rays.data_ptr(), peer_frame_ptr=peer.ptr.value, stream=stream)
+        if world > 1:
+            token = torch.ones(1, dtype=torch.int32, device=device)
+            dist.all_reduce(token, group=group)  # enqueued behind the render kernel on every rank
+        return peer.tensor, rays
     rows, max_rows = stripe_plan(height, stripe, world)
     packed = torch.empty((max_rows, width, 4), dtype=torch.uint8, device=device)
     rays = torch.zeros(1, dtype=torch.int64, device=device)
