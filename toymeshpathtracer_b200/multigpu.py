@@ -92,11 +92,19 @@ class PeerFrame:
         self.shape = (height, width, 4)
         self.ptr = C.c_void_p()
         handle = (C.c_ubyte * 64)()
+        err = None
         if rank == 0:
-            _check(lib().tmpt_frame_alloc(device_index, width * height * 4, C.byref(self.ptr), handle))
-        box = [bytes(handle)]
+            try:
+                _check(lib().tmpt_frame_alloc(device_index, width * height * 4, C.byref(self.ptr), handle))
+            except Exception as e:  # noqa: BLE001 -- still reach the broadcast so the other ranks do not hang
+                err = e
+        box = [bytes(handle) if err is None else b""]
         if world > 1:
             dist.broadcast_object_list(box, src=0, group=group)
+        if err is not None:
+            raise err
+        if not box[0]:
+            raise RuntimeError("rank 0 could not allocate the shared frame")
         if rank != 0:
             h = (C.c_ubyte * 64).from_buffer_copy(box[0])
             _check(lib().tmpt_frame_open(device_index, h, C.byref(self.ptr)))
