@@ -372,14 +372,24 @@ static void render_row(render_job* j, int y, int64_t* rayCount) { /* main.cpp:20
     const float sppRecip = 1.0f / (float)j->spp;
     uint32_t rng = (uint32_t)y * 9781u + 1u; /* main.cpp:204 */
     for (int x = 0; x < j->w; ++x) {
-        if (j->rngMode == ORC_RNG_PIXEL) rng = orc_pixel_seed((uint32_t)y * (uint32_t)j->w + (uint32_t)x);
         v3 col = V(0.0f, 0.0f, 0.0f);
-        for (int s = 0; s < j->spp; ++s) {
-            /* GetRay(argU, argV, rng): g++ evaluates argV (second) first */
-            float fv = ((float)y + random_float01(&rng)) * invHeight;
-            float fu = ((float)x + random_float01(&rng)) * invWidth;
-            ray_t ray = camera_get_ray(&j->cam, fu, fv, &rng);
-            col = add(col, trace(&j->sc, ray, &rng, rayCount));
+        /* ORC_RNG_ROW: one chunk holding every sample, the row's stream flowing on (the reference).
+         * ORC_RNG_PIXEL: chunks of ORC_CHUNK_SAMPLES samples, each with its own stream seeded from
+         * (chunk, pixel); chunk sums are added in chunk order (DESIGN.md "RNG"). */
+        const int chunkLen = j->rngMode == ORC_RNG_PIXEL ? ORC_CHUNK_SAMPLES : j->spp;
+        for (int s0 = 0, c = 0; s0 < j->spp; s0 += chunkLen, ++c) {
+            if (j->rngMode == ORC_RNG_PIXEL)
+                rng = orc_pixel_seed((uint32_t)c * ((uint32_t)j->w * (uint32_t)j->h) + (uint32_t)y * (uint32_t)j->w + (uint32_t)x);
+            v3 chunk = V(0.0f, 0.0f, 0.0f);
+            const int s1 = s0 + chunkLen < j->spp ? s0 + chunkLen : j->spp;
+            for (int s = s0; s < s1; ++s) {
+                /* GetRay(argU, argV, rng): g++ evaluates argV (second) first */
+                float fv = ((float)y + random_float01(&rng)) * invHeight;
+                float fu = ((float)x + random_float01(&rng)) * invWidth;
+                ray_t ray = camera_get_ray(&j->cam, fu, fv, &rng);
+                chunk = add(chunk, trace(&j->sc, ray, &rng, rayCount));
+            }
+            col = j->rngMode == ORC_RNG_PIXEL ? add(col, chunk) : chunk;
         }
         col = muls(col, sppRecip);
         size_t p = (size_t)y * (size_t)j->w + (size_t)x;

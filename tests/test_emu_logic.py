@@ -91,7 +91,7 @@ def test_tree_equals_brute_force_on_random_rays(emu):
     assert (c[0] == d2[0]).all() and (c[1][c[0] >= 0] < tcut).all()
 
 
-@pytest.mark.parametrize("name,w,h,spp", [("cube", 96, 54, 3), ("suzanne", 64, 36, 2), ("teapot", 32, 18, 1)])
+@pytest.mark.parametrize("name,w,h,spp", [("cube", 96, 54, 3), ("suzanne", 64, 36, 2), ("teapot", 32, 18, 1), ("cube", 40, 24, 20)])
 def test_integrator_equals_oracle_pixel_mode(emu, oracle, name, w, h, spp):
     sc = load_scene(name)
     cam = oracle.camera_for_scene(sc["bounds_min"], sc["bounds_max"], w, h)

@@ -142,7 +142,8 @@ def test_edge_cases():
         assert s.HitScene(ray)[0][0] == 2
 
 
-@pytest.mark.parametrize("name,w,h,spp", [("cube", 160, 90, 4), ("suzanne", 128, 72, 3), ("teapot", 64, 36, 2), ("triangle", 33, 17, 5)])
+@pytest.mark.parametrize("name,w,h,spp", [("cube", 160, 90, 4), ("suzanne", 128, 72, 3), ("teapot", 64, 36, 2), ("triangle", 33, 17, 5),
+                                          ("cube", 70, 41, 20), ("suzanne", 48, 28, 9)])  # the last two: several 8-sample chunks per pixel
 def test_frame_bit_exact_vs_oracle_pixel_mode(scenes, oracle, name, w, h, spp):
     sc = load_scene(name)
     cam = tm.camera_for_scene(f"{name}.obj", sc["bounds_min"], sc["bounds_max"], w, h)

@@ -104,18 +104,35 @@ TMPT_HD ex::V3 trace_path(const Scene& sc, const Camera& cam, ex::V3 o, ex::V3 d
     return color;
 }
 
+// The unit of parallel work: one CHUNK of a pixel's samples.  A chunk owns an XorShift32 stream
+// seeded from (chunk, pixel) and adds its samples in order; a pixel is the in-order sum of its
+// chunk sums (DESIGN.md "RNG").  With spp <= kChunkSamples there is one chunk per pixel and the
+// result equals a single per-pixel stream.
+constexpr int kChunkSamples = 8;
+TMPT_HD int chunk_count(int spp) { return (spp + kChunkSamples - 1) / kChunkSamples; }
+
 template <bool STATS = false, class Scene>
-TMPT_HD uchar4 render_pixel(const Scene& sc, const Camera& cam, int x, int y, int width, int height, int spp, ex::V3 lightDir,
-                            unsigned long long& rays, ex::V3* outLinear = nullptr, bvh::TravStats* stats = nullptr) {
+TMPT_HD ex::V3 render_chunk(const Scene& sc, const Camera& cam, int x, int y, int chunk, int width, int height, int spp, ex::V3 lightDir,
+                            unsigned long long& rays, bvh::TravStats* stats = nullptr) {
     const float invW = ex::divf(1.0f, (float)width), invH = ex::divf(1.0f, (float)height);
-    const float sppRecip = ex::divf(1.0f, (float)spp);
-    uint32_t rng = ex::pixel_seed((uint32_t)y * (uint32_t)width + (uint32_t)x);
+    uint32_t rng = ex::pixel_seed((uint32_t)chunk * ((uint32_t)width * (uint32_t)height) + (uint32_t)y * (uint32_t)width + (uint32_t)x);
     ex::V3 sum = ex::v3(0.0f, 0.0f, 0.0f);
-    for (int s = 0; s < spp; ++s) {
+    const int s0 = chunk * kChunkSamples, s1 = s0 + kChunkSamples < spp ? s0 + kChunkSamples : spp;
+    for (int s = s0; s < s1; ++s) {
         ex::V3 o, d;
         primary_ray(cam, x, y, invW, invH, rng, o, d);
         sum = ex::add(sum, trace_path<STATS>(sc, cam, o, d, lightDir, rng, rays, stats));
     }
+    return sum;
+}
+
+// One whole pixel, serially (host emulation; the kernels spread the chunks over lanes).
+template <bool STATS = false, class Scene>
+TMPT_HD uchar4 render_pixel(const Scene& sc, const Camera& cam, int x, int y, int width, int height, int spp, ex::V3 lightDir,
+                            unsigned long long& rays, ex::V3* outLinear = nullptr, bvh::TravStats* stats = nullptr) {
+    const float sppRecip = ex::divf(1.0f, (float)spp);
+    ex::V3 sum = ex::v3(0.0f, 0.0f, 0.0f);
+    for (int c = 0; c < chunk_count(spp); ++c) sum = ex::add(sum, render_chunk<STATS>(sc, cam, x, y, c, width, height, spp, lightDir, rays, stats));
     if (outLinear) *outLinear = ex::muls(sum, sppRecip);
     return resolve_pixel(sum, sppRecip);
 }

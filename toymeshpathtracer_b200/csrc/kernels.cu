@@ -84,6 +84,8 @@ struct tmpt_scene {
     unsigned long long* d_fetchCounter = nullptr;  // ray queue head of the persistent HitScene kernel
     uint8_t* d_frame = nullptr;
     size_t frameBytes = 0;
+    float4* d_accum = nullptr;     // chunk sums of the band being rendered
+    size_t accumBytes = 0;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     bvh::SceneView view{};
     tmpt_scene_info info{};
@@ -461,6 +463,43 @@ __global__ void __launch_bounds__(128) k_hit_scene_wt(bvh::SceneView sc, const f
     if (STATS) flush_stats(stats, nr, ts, nh);
 }
 
+// K2/K3 with the cooperative leaf phase (wtrace.cuh: traverse_warp8)
+template <bool STATS>
+__global__ void __launch_bounds__(128) k_hit_scene_w8(bvh::SceneView sc, const float* __restrict__ rays6, long long nRays, float tMin, float tMax,
+                                                       int anyHit, int* __restrict__ outID, float* __restrict__ outT, float* __restrict__ outPos,
+                                                       float* __restrict__ outNormal, unsigned long long* __restrict__ stats) {
+    bvh::TravStats ts;
+    unsigned long long nr = 0, nh = 0;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    const long long rounds = (nRays + stride - 1) / stride;
+    for (long long rnd = 0; rnd < rounds; ++rnd) {
+        const long long i = rnd * stride + (long long)blockIdx.x * blockDim.x + threadIdx.x;
+        const bool active = i < nRays;
+        ex::V3 o = ex::v3(0, 0, 0), d = ex::v3(0, 0, 1);
+        if (active) { const float* r = rays6 + i * 6; o = ex::v3(r[0], r[1], r[2]); d = ex::v3(r[3], r[4], r[5]); }
+        const unsigned long long key = wt::traverse_warp8<STATS>(sc, o, d, tMin, tMax, anyHit != 0, active, &ts);
+        if (!active) continue;
+        const int id = (int)(uint32_t)key;
+        if (STATS) { ++nr; nh += id >= 0; }
+        if (anyHit) { outID[i] = id < 0 ? -1 : 1; continue; }
+        outID[i] = id;
+        if (id >= 0) {
+            if (outT) outT[i] = wt::key_t(key);
+            if (outPos || outNormal) {
+                const float* q = sc.tris9 + (size_t)id * 9;
+                const ex::V3 v0 = ex::v3(q[0], q[1], q[2]), v1 = ex::v3(q[3], q[4], q[5]), v2 = ex::v3(q[6], q[7], q[8]);
+                float t, u, v;
+                bvh::mt_exact(o, d, v0, ex::sub(v1, v0), ex::sub(v2, v0), tMin, tMax, t, u, v);
+                ex::V3 pos, nrm;
+                bvh::hit_payload(sc, id, u, v, pos, nrm);
+                if (outPos) { outPos[i * 3] = pos.x; outPos[i * 3 + 1] = pos.y; outPos[i * 3 + 2] = pos.z; }
+                if (outNormal) { outNormal[i * 3] = nrm.x; outNormal[i * 3 + 1] = nrm.y; outNormal[i * 3 + 2] = nrm.z; }
+            }
+        }
+    }
+    if (STATS) flush_stats(stats, nr, ts, nh);
+}
+
 // Warp-queue form of K2/K3 (warpq.cuh): lanes walk inner nodes, triangles are tested 32 pairs
 // at a time by the whole warp, finished lanes are refilled from the global ray counter.
 template <bool STATS, int REFILL_MIN, int NODE_MIN>
@@ -548,9 +587,12 @@ __global__ void __launch_bounds__(128) k_hit_scene_wq(bvh::SceneView sc, const f
 }
 
 // ------------------------------------------------------------------------------------------
-// K4: path tracing.  Work unit = an 8x4 pixel tile per warp, fetched from a global counter
-// (persistent CTAs); each lane owns one pixel and runs its samples serially because the
-// pixel's XorShift32 stream flows through them (DESIGN.md "RNG").
+// K4: path tracing.  Work unit = (8x4 pixel tile, chunk of 8 samples) per warp, fetched from a
+// global counter (persistent CTAs); a lane runs the samples of its pixel's chunk serially
+// because the chunk's XorShift32 stream flows through them (DESIGN.md "RNG").  With more than
+// one chunk per pixel the chunk sums go to an accumulation buffer and k_resolve adds them in
+// chunk order; this keeps ~10x more work items than resident lanes even when a 1080p frame is
+// split over 8 GPUs.
 // ------------------------------------------------------------------------------------------
 struct RenderParams {
     bvh::SceneView sc;
@@ -559,6 +601,9 @@ struct RenderParams {
     int width, height, spp;
     int stripeRows, rank, world, ownedRows;
     int tilesX, numTiles;
+    int chunks;          // sample chunks per pixel
+    int bandRow0;        // first owned row of the band being rendered (the accumulation buffer covers one band)
+    float4* accum;       // [bandRows][width][chunks] chunk sums, when chunks > 1
     uchar4* outStripes;  // packed owned rows, or
     uchar4* frame;       // full frame (possibly peer memory)
     unsigned long long* rayCount;
@@ -580,19 +625,39 @@ __global__ void __launch_bounds__(THREADS, MINB) k_render(const RenderParams p) 
         uint32_t tile = 0;
         if (lane == 0) tile = atomicAdd(p.tileCounter, 1u);
         tile = __shfl_sync(0xffffffffu, tile, 0);
-        if (tile >= (uint32_t)p.numTiles) break;
+        if (tile >= (uint32_t)p.numTiles * (uint32_t)p.chunks) break;
+        const int chunk = (int)(tile / (uint32_t)p.numTiles);
+        tile -= (uint32_t)chunk * (uint32_t)p.numTiles;
         const int tx = (int)(tile % (uint32_t)p.tilesX), ty = (int)(tile / (uint32_t)p.tilesX);
-        const int x = tx * 8 + (lane & 7), r = ty * 4 + (lane >> 3);
+        const int x = tx * 8 + (lane & 7), rb = ty * 4 + (lane >> 3), r = p.bandRow0 + rb;
         if (x < p.width && r < p.ownedRows) {
             const int y = owned_row_to_global(r, p.stripeRows, p.rank, p.world);
-            const uchar4 px = integ::render_pixel<STATS>(p.sc, p.cam, x, y, p.width, p.height, p.spp, p.lightDir, rays, nullptr, &ts);
-            if (p.frame) p.frame[(size_t)y * p.width + x] = px;
-            else p.outStripes[(size_t)r * p.width + x] = px;
+            const ex::V3 sum = integ::render_chunk<STATS>(p.sc, p.cam, x, y, chunk, p.width, p.height, p.spp, p.lightDir, rays, &ts);
+            if (p.chunks > 1) {
+                p.accum[((size_t)rb * p.width + x) * p.chunks + chunk] = make_float4(sum.x, sum.y, sum.z, 0.0f);
+            } else {
+                const uchar4 px = integ::resolve_pixel(sum, ex::divf(1.0f, (float)p.spp));
+                if (p.frame) p.frame[(size_t)y * p.width + x] = px;
+                else p.outStripes[(size_t)r * p.width + x] = px;
+            }
         }
     }
     if (STATS) flush_stats(p.stats, rays, ts, 0);
     for (int o = 16; o > 0; o >>= 1) rays += __shfl_xor_sync(0xffffffffu, rays, o);
     if (lane == 0 && rays) atomicAdd(p.rayCount, rays);
+}
+
+// pixel = in-order sum of its chunk sums, then mean / sqrt / quantise (main.cpp:221-233)
+__global__ void k_resolve(const RenderParams p, int bandRows) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long long)bandRows * p.width) return;
+    const int rb = (int)(i / p.width), x = (int)(i - (long long)rb * p.width), r = p.bandRow0 + rb;
+    const float4* a = p.accum + (size_t)i * p.chunks;
+    ex::V3 sum = ex::v3(0.0f, 0.0f, 0.0f);
+    for (int c = 0; c < p.chunks; ++c) { const float4 v = a[c]; sum = ex::add(sum, ex::v3(v.x, v.y, v.z)); }
+    const uchar4 px = integ::resolve_pixel(sum, ex::divf(1.0f, (float)p.spp));
+    if (p.frame) p.frame[(size_t)owned_row_to_global(r, p.stripeRows, p.rank, p.world) * p.width + x] = px;
+    else p.outStripes[(size_t)r * p.width + x] = px;
 }
 
 // K5: rank 0 scatters the gathered, rank-major packed stripes into the frame
@@ -826,7 +891,7 @@ extern "C" void tmpt_scene_destroy(tmpt_scene* s) {
     DeviceGuard guard(s->device);
     if (s->stream) cudaStreamSynchronize(s->stream);
     cudaFree(s->d_tris9); cudaFree(s->d_nodes); cudaFree(s->d_tris); cudaFree(s->d_status);
-    cudaFree(s->d_tileCounter); cudaFree(s->d_rayCount); cudaFree(s->d_fetchCounter); cudaFree(s->d_frame);
+    cudaFree(s->d_tileCounter); cudaFree(s->d_rayCount); cudaFree(s->d_fetchCounter); cudaFree(s->d_frame); cudaFree(s->d_accum);
     if (s->ev0) cudaEventDestroy(s->ev0);
     if (s->ev1) cudaEventDestroy(s->ev1);
     if (s->stream) cudaStreamDestroy(s->stream);
@@ -875,7 +940,7 @@ extern "C" int tmpt_hit_scene(const tmpt_scene* s, const float* rays6, int64_t n
     const int B = 128;
     const int G = (int)std::min<long long>(div_up(nRays, B), (long long)s->smCount * 64);
     // Experimental traversal engines kept for A/B runs (tools/exp_traverse.py; results in profiles/ and DESIGN.md 5):
-    // 5 = warp queue (warpq.cuh), 10/11 = warp-synchronous deferred triangle tests (wtrace.cuh).  Default 0.
+    // 5 = warp queue (warpq.cuh), 10/11 = warp-synchronous deferred triangle tests, 20 = cooperative leaf phase (wtrace.cuh).
     static const int variant = getenv("TMPT_HIT_KERNEL") ? atoi(getenv("TMPT_HIT_KERNEL")) : 0;
     if (variant > 0 && mode != TMPT_HIT_BRUTE) {
         int perSM = 0;
@@ -896,6 +961,9 @@ extern "C" int tmpt_hit_scene(const tmpt_scene* s, const float* rays6, int64_t n
         } else
         WT_CASE(10, 16, 8) WT_CASE(11, 8, 8)
 #undef WT_CASE
+        if (variant == 20) {
+            LAUNCH((k_hit_scene_w8<false>), G, B, 0, st, s->view, dRays, (long long)nRays, tMin, tMax, mode == TMPT_HIT_ANY, dID, dT, dPos, dNrm, nullptr);
+        } else
         return tmpt::fail(TMPT_ERR_ARG, "TMPT_HIT_KERNEL=%d: no such traversal variant", variant);
     } else if (mode == TMPT_HIT_CLOSEST) LAUNCH((k_hit_scene<TMPT_HIT_CLOSEST, false>), G, B, 0, st, s->view, dRays, (long long)nRays, tMin, tMax, dID, dT, dPos, dNrm, nullptr);
     else if (mode == TMPT_HIT_ANY) LAUNCH((k_hit_scene<TMPT_HIT_ANY, false>), G, B, 0, st, s->view, dRays, (long long)nRays, tMin, tMax, dID, dT, dPos, dNrm, nullptr);
@@ -925,9 +993,10 @@ extern "C" int tmpt_stripe_rows(int height, int stripeRows, int rank, int worldS
 
 static ex::V3 host_light_dir() { return ex::normalize(ex::v3(-0.7f, 1.0f, 0.5f)); }  // main.cpp:36
 
-static int launch_render(const tmpt_scene* s, const tmpt_camera* camera, int width, int height, int spp, int stripeRows, int rank, int world,
+static int launch_render(const tmpt_scene* cs, const tmpt_camera* camera, int width, int height, int spp, int stripeRows, int rank, int world,
                          uint8_t* outStripes, uint8_t* frame, unsigned long long* rayCountDev, cudaStream_t st,
                          unsigned long long* statsDev = nullptr) {
+    tmpt_scene* s = const_cast<tmpt_scene*>(cs);  // scratch buffers only; the scene data is immutable
     RenderParams p;
     p.sc = s->view;
     static_assert(sizeof(integ::Camera) == sizeof(tmpt_camera), "camera layout");
@@ -937,33 +1006,42 @@ static int launch_render(const tmpt_scene* s, const tmpt_camera* camera, int wid
     p.stripeRows = stripeRows; p.rank = rank; p.world = world;
     p.ownedRows = tmpt_stripe_rows(height, stripeRows, rank, world);
     p.tilesX = div_up(width, 8);
-    p.numTiles = p.tilesX * div_up(p.ownedRows, 4);
+    p.chunks = integ::chunk_count(spp);
     p.outStripes = (uchar4*)outStripes;
     p.frame = (uchar4*)frame;
     p.rayCount = rayCountDev;
     p.tileCounter = s->d_tileCounter;
     p.stats = statsDev;
-    if (p.numTiles == 0) return TMPT_OK;
-    CU_TRY(cudaMemsetAsync(s->d_tileCounter, 0, sizeof(uint32_t), st));
-    static const int cfg = getenv("TMPT_RENDER_CFG") ? atoi(getenv("TMPT_RENDER_CFG")) : 0;
+    p.accum = nullptr;
+    if (p.ownedRows == 0) return TMPT_OK;
+    // bands of owned rows so that the chunk-sum buffer stays within a fixed budget (a whole 1080p x 64 spp frame is 265 MB)
+    int bandRows = p.ownedRows;
+    if (p.chunks > 1) {
+        const size_t rowBytes = (size_t)width * p.chunks * sizeof(float4), budget = (size_t)1 << 30;
+        bandRows = (int)std::min<size_t>((size_t)p.ownedRows, std::max<size_t>(4, (budget / rowBytes) & ~(size_t)3));
+        const size_t need = (size_t)bandRows * rowBytes;
+        if (s->accumBytes < need) {
+            CU_TRY(cudaStreamSynchronize(st));
+            cudaFree(s->d_accum); s->d_accum = nullptr; s->accumBytes = 0;
+            CU_TRY(cudaMalloc((void**)&s->d_accum, need));
+            s->accumBytes = need;
+        }
+        p.accum = s->d_accum;
+    }
+    // 256 threads x 4 CTAs/SM = 32 warps/SM at 64 registers (sweep in profiles/r1_tuning_sweeps.txt: 24 warps at
+    // 77 registers is 10 % slower, 40 warps at 48 registers spills and is 3 % slower)
     int perSM = 0;
-#define RENDER_CASE(C, T, M)                                                                              \
-    if (cfg == C && !statsDev) {                                                                          \
-        CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, k_render<false, T, M>, T, 0));       \
-        const int grid = std::min(s->smCount * std::max(perSM, 1), div_up(p.numTiles, T / 32));           \
-        LAUNCH((k_render<false, T, M>), grid, T, 0, st, p);                                               \
-    } else
-    RENDER_CASE(1, 256, 3) RENDER_CASE(2, 128, 6) RENDER_CASE(3, 128, 8) RENDER_CASE(4, 128, 4) RENDER_CASE(5, 64, 12) RENDER_CASE(6, 512, 2) RENDER_CASE(7, 256, 1) RENDER_CASE(8, 256, 2)
-    RENDER_CASE(9, 256, 5) RENDER_CASE(10, 256, 6) RENDER_CASE(11, 128, 10) RENDER_CASE(12, 128, 12) RENDER_CASE(13, 512, 3) RENDER_CASE(14, 1024, 1)
-    RENDER_CASE(15, 128, 16) RENDER_CASE(16, 64, 20)
-#undef RENDER_CASE
-    {
-        // default: 256 threads x 4 CTAs/SM = 32 warps/SM at 64 registers (sweep in profiles/r1_tuning_sweeps.txt:
-        // 24 warps at 77 registers is 10 % slower, 40 warps at 48 registers spills and is 3 % slower)
-        CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, k_render<false, 256, 4>, 256, 0));
-        const int grid = std::min(s->smCount * std::max(perSM, 1), div_up(p.numTiles, 8));
+    CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, k_render<false, 256, 4>, 256, 0));
+    for (p.bandRow0 = 0; p.bandRow0 < p.ownedRows; p.bandRow0 += bandRows) {
+        const int rowsHere = std::min(bandRows, p.ownedRows - p.bandRow0);
+        p.numTiles = p.tilesX * div_up(rowsHere, 4);
+        const long long items = (long long)p.numTiles * p.chunks;
+        if (items >= 0xFFFFFFFFll) return tmpt::fail(TMPT_ERR_ARG, "render: too many work items in one band");
+        CU_TRY(cudaMemsetAsync(s->d_tileCounter, 0, sizeof(uint32_t), st));
+        const int grid = (int)std::min<long long>((long long)s->smCount * std::max(perSM, 1), (items + 7) / 8);
         if (statsDev) LAUNCH((k_render<true, 256, 4>), grid, 256, 0, st, p);
         else LAUNCH((k_render<false, 256, 4>), grid, 256, 0, st, p);
+        if (p.chunks > 1) LAUNCH(k_resolve, div_up((long long)rowsHere * width, 256), 256, 0, st, p, rowsHere);
     }
     CU_TRY(cudaGetLastError());
     return TMPT_OK;
