@@ -100,6 +100,15 @@ def test_integrator_equals_oracle_pixel_mode(emu, oracle, name, w, h, spp):
     assert rays == orays and (img == oimg).all()
 
 
+def test_nan_rays_are_misses(emu):
+    sc = load_scene("suzanne")
+    s = emu.scene(sc["tris"])
+    rays = np.array([[0, 0, 5, np.nan, np.nan, np.nan], [np.nan, 0, 5, 0, 0, -1], [0, 0, 5, 0, np.nan, -1], [0, 0.2, 5, 0, 0, -1]], np.float32)
+    for mode in (0, 1, 2):
+        ids, *_ = s.hit(rays, mode=mode)
+        assert (ids[:3] == -1).all() and ids[3] != -1
+
+
 def test_degenerate_inputs(emu):
     # one triangle; duplicate triangles (equal Morton keys, equal t -> lowest index wins)
     tri = np.array([[0, 0, 0, 1, 0, 0, 0, 1, 0]], np.float32)

@@ -124,6 +124,24 @@ def test_tree_vs_brute_force_at_scale(scenes):
         assert (bits(a[2]) == bits(b[2])).all() and (bits(a[3]) == bits(b[3])).all()
 
 
+def test_nan_rays_miss_quickly(scenes, oracle):
+    """NaN rays (the reference's normalize(0) scatter makes them) are misses for the exact test; the tree must say
+    so too, and without walking every node (fmin/fmax drop NaN operands)."""
+    sc = load_scene("teapot")
+    rays = _random_rays(sc, 4096, 3, axis_parallel=False)
+    rays[::7, 3:] = np.nan
+    rays[3::11, 0] = np.nan
+    rays[5::13, 4] = np.nan
+    for mode in (tm.HIT_CLOSEST, tm.HIT_BRUTE):
+        ids, *_ = scenes("teapot").HitScene(rays, mode=mode)
+        oid, *_ = oracle.hit_brute(sc["tris"], rays)
+        assert (ids == oid).all()
+    bad = np.isnan(rays).any(1)
+    assert (ids[bad] == -1).all()
+    aid, *_ = scenes("teapot").HitScene(rays, mode=tm.HIT_ANY)
+    assert ((aid == 1) == (oid >= 0)).all()
+
+
 def test_edge_cases():
     ray = np.array([[0.2, 0.2, 1, 0, 0, -1]], np.float32)
     with tm.Scene(np.zeros((0, 9), np.float32)) as s:  # empty scene: everything misses

@@ -181,8 +181,8 @@ class Scene:
         _check(lib().tmpt_scene_create(_ptr(tris), tris.shape[0], device, flags, C.byref(self._h)))
 
     def close(self):
-        if getattr(self, "_h", None):
-            lib().tmpt_scene_destroy(self._h)
+        if getattr(self, "_h", None) and _lib is not None:  # (module globals may be gone at interpreter exit)
+            _lib.tmpt_scene_destroy(self._h)
             self._h = None
 
     __del__ = close

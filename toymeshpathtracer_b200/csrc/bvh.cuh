@@ -126,6 +126,13 @@ TMPT_HD float fmaf_(float a, float b, float c) {
 #endif
 }
 
+// A ray with a NaN component can never be accepted by the exact test (det, u, v or t is NaN and
+// the last comparison t >= tMin fails), so it is a miss by definition -- but fminf/fmaxf DROP
+// NaN operands, which would make every slab test pass and the walk visit the whole tree
+// (measured: one such ray = 37 ms; the reference's own normalize(0) scatter, SURVEY.md 0.7,
+// produces them).  Traversal starts from an empty root for these rays.
+TMPT_HD bool ray_has_nan(ex::V3 o, ex::V3 d) { return o.x != o.x || o.y != o.y || o.z != o.z || d.x != d.x || d.y != d.y || d.z != d.z; }
+
 // One traversal, closest (ANY=false) or any-hit (ANY=true).
 //
 // Node step: the near / far slab planes are picked by the ray's octant through the LOAD
@@ -149,7 +156,7 @@ TMPT_HD HitRec traverse(const SceneView& sc, ex::V3 o, ex::V3 d, float tMin, flo
     unsigned long long stack[STACK_SIZE];  // (entry distance bits << 32) | ref
     int sp = 0;
     bool overflow = false;
-    uint32_t cur = sc.rootRef;
+    uint32_t cur = ray_has_nan(o, d) ? NONE : sc.rootRef;
 
     while (cur != NONE) {
         if (!ref_is_leaf(cur)) {

@@ -57,7 +57,7 @@ __device__ __forceinline__ void lane_start(Lane& L, WarpShared& ws, int lane, ex
     L.idx = 1.0f / dx; L.idy = 1.0f / dy; L.idz = 1.0f / dz;
     L.ox = o.x * L.idx; L.oy = o.y * L.idy; L.oz = o.z * L.idz;
     L.sx = dx < 0.0f; L.sy = dy < 0.0f; L.sz = dz < 0.0f;
-    L.cur = rootRef;
+    L.cur = bvh::ray_has_nan(o, d) ? bvh::NONE : rootRef;
     L.sp = 0;
     L.lastTail = tail;
     L.any = any;

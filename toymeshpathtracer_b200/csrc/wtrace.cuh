@@ -31,7 +31,7 @@ __device__ __forceinline__ bvh::HitRec traverse_warp(const bvh::SceneView& sc, e
     uint32_t stackRef[STACK];
     float stackT[STACK];
     int sp = 0;
-    uint32_t cur = active ? sc.rootRef : bvh::NONE;
+    uint32_t cur = active && !bvh::ray_has_nan(o, d) ? sc.rootRef : bvh::NONE;
     uint32_t triPos = 0, triEnd = 0;
 
     auto pop = [&]() -> uint32_t {
@@ -183,7 +183,7 @@ __device__ __forceinline__ unsigned long long traverse_warp8(const bvh::SceneVie
     unsigned long long stack[STACK];
     int sp = 0;
     bool overflow = false;
-    uint32_t cur = active ? sc.rootRef : bvh::NONE;
+    uint32_t cur = active && !bvh::ray_has_nan(o, d) ? sc.rootRef : bvh::NONE;
 
     for (;;) {
         if (cur != bvh::NONE && !bvh::ref_is_leaf(cur)) {
