@@ -295,3 +295,114 @@ def test_peer_frame_across_processes():
         p.join(180)
         assert p.exitcode == 0
     assert out.get() is True
+
+
+# ---- BASELINE.json configurations at their full sizes, through size-independent properties ----------------------
+
+def _sponza_tris():
+    from tools.gen_sponza import triangles
+    from oracle.pyoracle import Oracle
+    return Oracle().add_floor(triangles())  # (tris incl. the two floor triangles, boundsMin, boundsMax) like LoadScene
+
+
+def test_config3_teapot_720p_16spp_properties(scenes):
+    """teapot.obj 1280x720 16 spp, 1 GPU: deterministic, and the 8-way stripe partition composes to the same frame
+    (two 8-sample chunks per pixel, so the accumulate + resolve path is exercised at full size)."""
+    import torch
+    from toymeshpathtracer_b200 import multigpu
+    sc = load_scene("teapot")
+    w, h, spp = 1280, 720, 16
+    cam = tm.camera_for_scene("teapot.obj", sc["bounds_min"], sc["bounds_max"], w, h)
+    s = scenes("teapot")
+    a, ra, _ = s.render(cam, w, h, spp)
+    b, rb, _ = s.render(cam, w, h, spp)
+    assert ra == rb and (a == b).all()
+    assert 30e6 < ra < 50e6  # the reference counts 38.2 M rays at this configuration (SURVEY.md 6); streams differ
+    assert a[..., 3].min() == 255 and a[..., :3].std() > 10
+    frame = torch.zeros((h, w, 4), dtype=torch.uint8, device="cuda")
+    rays = torch.zeros(8, dtype=torch.int64, device="cuda")
+    st = torch.cuda.Stream()
+    with torch.cuda.stream(st):
+        for r in range(8):
+            s.render_stripes(cam, w, h, spp, multigpu.DEFAULT_STRIPE_ROWS, r, 8, 0, rays[r:].data_ptr(), peer_frame_ptr=frame.data_ptr(), stream=st.cuda_stream)
+    st.synchronize()
+    assert int(rays.sum()) == ra and (frame.cpu().numpy() == a).all()
+
+
+def test_config4_sponza_tree_vs_brute_force():
+    """sponza (66 452 triangles): nearest-hit ids / t / payload of the SAH tree == the all-triangle scan, on primary,
+    bounce and shadow rays of the Sponza camera (the rays configs 4 and 5 shoot)."""
+    tris, mn, mx = _sponza_tris()
+    assert tris.shape[0] == 66452
+    w, h = 320, 180
+    cam = tm.camera_for_scene("x/sponza.obj", mn, mx, w, h)
+    ys, xs = np.meshgrid(np.arange(h), np.arange(w), indexing="ij")
+    o = np.broadcast_to(cam[0:3], (h * w, 3))
+    d = cam[3:6] + ((xs.ravel() + 0.5) / w)[:, None] * cam[6:9] + ((ys.ravel() + 0.5) / h)[:, None] * cam[9:12] - cam[0:3]
+    d = d / np.linalg.norm(d, axis=1, keepdims=True)
+    rays = np.concatenate([o, d], 1).astype(np.float32)
+    rng = np.random.default_rng(4)
+    light = np.array([-0.7, 1.0, 0.5]); light /= np.linalg.norm(light)
+    with tm.Scene(tris) as s:
+        assert s.info()["builder"] == tm.BUILD_DEFAULT
+        for bounce in range(3):
+            a = s.HitScene(rays)
+            b = s.HitScene(rays, mode=tm.HIT_BRUTE)
+            hit = a[0] >= 0
+            assert (a[0] == b[0]).all() and (bits(a[1])[hit] == bits(b[1])[hit]).all()
+            assert (bits(a[2])[hit] == bits(b[2])[hit]).all() and (bits(a[3])[hit] == bits(b[3])[hit]).all()
+            pos, nrm = a[2][hit], a[3][hit]
+            shadow = np.concatenate([pos, np.broadcast_to(light, pos.shape)], 1).astype(np.float32)
+            sa = s.HitScene(shadow, mode=tm.HIT_ANY)[0]
+            sb = s.HitScene(shadow, mode=tm.HIT_BRUTE)[0]
+            assert ((sa == 1) == (sb >= 0)).all()
+            r = rng.normal(size=pos.shape); r /= np.linalg.norm(r, axis=1, keepdims=True)
+            nd = nrm + r; nd /= np.maximum(np.linalg.norm(nd, axis=1, keepdims=True), 1e-20)
+            rays = np.concatenate([pos, nd], 1).astype(np.float32)
+
+
+def test_config4_sponza_640x360_4spp_partitions():
+    """sponza 640x360 4 spp: the frame is the same for 1, 2, 4 and 8 ranks (emulated on this GPU), and so is the ray count."""
+    import torch
+    from toymeshpathtracer_b200 import multigpu
+    tris, mn, mx = _sponza_tris()
+    w, h, spp = 640, 360, 4
+    cam = tm.camera_for_scene("x/sponza.obj", mn, mx, w, h)
+    with tm.Scene(tris) as s:
+        full, full_rays, _ = s.render(cam, w, h, spp)
+        assert 8e6 < full_rays < 20e6
+        st = torch.cuda.Stream()
+        for world in (2, 4, 8):
+            frame = torch.zeros((h, w, 4), dtype=torch.uint8, device="cuda")
+            rays = torch.zeros(world, dtype=torch.int64, device="cuda")
+            with torch.cuda.stream(st):
+                for r in range(world):
+                    s.render_stripes(cam, w, h, spp, multigpu.DEFAULT_STRIPE_ROWS, r, world, 0, rays[r:].data_ptr(), peer_frame_ptr=frame.data_ptr(), stream=st.cuda_stream)
+            st.synchronize()
+            assert int(rays.sum()) == full_rays and (frame.cpu().numpy() == full).all()
+            per_rank = rays.cpu().numpy()
+            assert per_rank.max() < 1.15 * per_rank.mean()  # stripes of 4 rows balance the work
+
+
+def test_config5_sponza_1080p_64spp_rank_of_eight():
+    """The headline frame, 8-way partition: one rank's share (what each GPU of the 8xB200 run renders) is deterministic
+    and carries 1/8 of the rays within 5 %."""
+    import torch
+    from toymeshpathtracer_b200 import multigpu
+    tris, mn, mx = _sponza_tris()
+    w, h, spp, world = 1920, 1080, 64, 8
+    cam = tm.camera_for_scene("x/sponza.obj", mn, mx, w, h)
+    rows, max_rows = multigpu.stripe_plan(h, multigpu.DEFAULT_STRIPE_ROWS, world)
+    with tm.Scene(tris) as s:
+        outs = []
+        st = torch.cuda.Stream()
+        for rep in range(2):
+            packed = torch.zeros((max_rows, w, 4), dtype=torch.uint8, device="cuda")
+            rays = torch.zeros(1, dtype=torch.int64, device="cuda")
+            with torch.cuda.stream(st):
+                s.render_stripes(cam, w, h, spp, multigpu.DEFAULT_STRIPE_ROWS, 3, world, packed.data_ptr(), rays.data_ptr(), stream=st.cuda_stream)
+            st.synchronize()
+            outs.append((packed.cpu().numpy(), int(rays)))
+        assert outs[0][1] == outs[1][1] and (outs[0][0] == outs[1][0]).all()
+        assert abs(outs[0][1] / (2.3774e9 / 8) - 1) < 0.05
+        assert outs[0][0][: rows[3], :, 3].min() == 255
