@@ -406,3 +406,49 @@ def test_config5_sponza_1080p_64spp_rank_of_eight():
         assert outs[0][1] == outs[1][1] and (outs[0][0] == outs[1][0]).all()
         assert abs(outs[0][1] / (2.3774e9 / 8) - 1) < 0.05
         assert outs[0][0][: rows[3], :, 3].min() == 255
+
+
+@pytest.mark.parametrize("name", ["suzanne", "teapot", "sponza"])
+def test_grazing_rays_tree_vs_brute_force(scenes, name):
+    """Stress of box conservativeness where Moller-Trumbore is least accurate: rays that start ON a triangle's plane
+    (inside it, on its edges, at its vertices) and leave almost inside that plane, so that det is tiny and the computed
+    u, v, t carry their largest errors.  The tree must still return exactly what the all-triangle scan returns."""
+    if name == "sponza":
+        tris = _sponza_tris()[0]
+        s = tm.Scene(tris)
+    else:
+        tris = load_scene(name)["tris"]
+        s = scenes(name)
+    rng = np.random.default_rng(17)
+    n = 400_000
+    T = tris.reshape(-1, 3, 3).astype(np.float64)
+    k = rng.integers(0, T.shape[0], n)
+    v0, v1, v2 = T[k, 0], T[k, 1], T[k, 2]
+    bary = rng.dirichlet([0.6, 0.6, 0.6], n)
+    bary[: n // 8] = np.eye(3)[rng.integers(0, 3, n // 8)]                      # vertices
+    edge = rng.random(n // 8)
+    bary[n // 8: n // 4] = np.stack([edge, 1 - edge, np.zeros_like(edge)], 1)   # on an edge
+    p = bary[:, :1] * v0 + bary[:, 1:2] * v1 + bary[:, 2:] * v2
+    e1, e2 = v1 - v0, v2 - v0
+    nrm = np.cross(e1, e2)
+    nlen = np.linalg.norm(nrm, axis=1, keepdims=True)
+    ok = nlen[:, 0] > 0
+    nrm = nrm / np.maximum(nlen, 1e-300)
+    a = rng.random((n, 1)) * 2 * np.pi
+    t1 = e1 / np.maximum(np.linalg.norm(e1, axis=1, keepdims=True), 1e-300)
+    t2 = np.cross(nrm, t1)
+    tilt = (10.0 ** rng.uniform(-8, -1, (n, 1))) * rng.choice([-1.0, 1.0], (n, 1))
+    d = np.cos(a) * t1 + np.sin(a) * t2 + tilt * nrm
+    with np.errstate(invalid="ignore", divide="ignore"):  # zero-area triangles are dropped by `ok` below
+        d /= np.linalg.norm(d, axis=1, keepdims=True)
+    back = rng.uniform(0.0, 2.0, (n, 1))                                            # start up to 2 units before the point
+    rays = np.concatenate([p - back * d, d], 1)[ok].astype(np.float32)
+    a_ = s.HitScene(rays)
+    b_ = s.HitScene(rays, mode=tm.HIT_BRUTE)
+    hit = b_[0] >= 0
+    assert (a_[0] == b_[0]).all(), f"{(a_[0] != b_[0]).sum()} of {rays.shape[0]} grazing rays differ"
+    assert (bits(a_[1])[hit] == bits(b_[1])[hit]).all()
+    sa = s.HitScene(rays, mode=tm.HIT_ANY)[0]
+    assert ((sa == 1) == hit).all()
+    if name == "sponza":
+        s.close()
