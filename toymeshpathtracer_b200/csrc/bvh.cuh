@@ -158,8 +158,14 @@ TMPT_HD HitRec traverse(const SceneView& sc, ex::V3 o, ex::V3 d, float tMin, flo
     bool overflow = false;
     uint32_t cur = ray_has_nan(o, d) ? NONE : sc.rootRef;
 
-    while (cur != NONE) {
-        if (!ref_is_leaf(cur)) {
+    // A lane that reaches a leaf PARKS it (triPos..triEnd) and tests one of its triangles per
+    // iteration while it keeps walking inner nodes in the same iteration: the node step and the
+    // exact test of one ray overlap instead of alternating, and nobody loops over a whole leaf
+    // while its neighbours wait (+7 % on incoherent rays, profiles/).  The walk runs at most one
+    // leaf ahead of the tests, so almost nothing is visited that a tighter best t would have culled.
+    uint32_t triPos = 0, triEnd = 0;
+    for (;;) {
+        if (cur != NONE && !ref_is_leaf(cur)) {
             if (STATS) ++stats->nodes;
             const float4* n = sc.nodes + (size_t)cur * NODE_F4;
             const float4 nx = ld_row(n + sx), fx = ld_row(n + (sx ^ 1u));
@@ -190,32 +196,32 @@ TMPT_HD HitRec traverse(const SceneView& sc, ex::V3 o, ex::V3 d, float tMin, flo
                     }
                 }
             }
-        } else {
-            const uint32_t first = leaf_first(cur);
-            const int cnt = leaf_count(cur);
-            if (STATS) stats->tris += (unsigned)cnt;
-            for (int k = 0; k < cnt; ++k) {
-                const float4* tp = sc.tris + (size_t)(first + k) * 3;
-                const float4 a = ld_row(tp + 0), b = ld_row(tp + 1), c = ld_row(tp + 2);
-                float t, u, v;
-                if (mt_exact(o, d, ex::v3(a.x, a.y, a.z), ex::v3(b.x, b.y, b.z), ex::v3(c.x, c.y, c.z), tMin, tMax, t, u, v)) {
-                    const int id = (int)ex::f2u(a.w);
-                    if (t < best.t || (t == best.t && best.id >= 0 && id < best.id)) {
-                        best.t = t; best.id = id; best.u = u; best.v = v;
-                        if (ANY) {
-                            if (overflow && sc.status) *sc.status |= STACK_OVERFLOW;
-                            return best;
-                        }
-                    }
+        }
+        if (cur != NONE && ref_is_leaf(cur) && triPos == triEnd) {  // park the leaf, free the walker
+            triPos = leaf_first(cur);
+            triEnd = triPos + (uint32_t)leaf_count(cur);
+            cur = NONE;
+        }
+        if (triPos < triEnd) {
+            if (STATS) ++stats->tris;
+            const float4* tp = sc.tris + (size_t)triPos * 3;
+            const float4 a = ld_row(tp + 0), b = ld_row(tp + 1), c = ld_row(tp + 2);
+            ++triPos;
+            float t, u, v;
+            if (mt_exact(o, d, ex::v3(a.x, a.y, a.z), ex::v3(b.x, b.y, b.z), ex::v3(c.x, c.y, c.z), tMin, tMax, t, u, v)) {
+                const int id = (int)ex::f2u(a.w);
+                if (t < best.t || (t == best.t && best.id >= 0 && id < best.id)) {
+                    best.t = t; best.id = id; best.u = u; best.v = v;
+                    if (ANY) break;
                 }
             }
-            cur = NONE;
         }
         // pop: skip entries that the shrinking best.t has already culled
         while (cur == NONE && sp > 0) {
             const unsigned long long e = stack[--sp];
             if (ex::u2f((uint32_t)(e >> 32)) <= best.t) cur = (uint32_t)e;
         }
+        if (cur == NONE && triPos == triEnd) break;
     }
     if (overflow && sc.status) *sc.status |= STACK_OVERFLOW;
     return best;
