@@ -202,6 +202,11 @@ TMPT_HD HitRec traverse(const SceneView& sc, ex::V3 o, ex::V3 d, float tMin, flo
             triEnd = triPos + (uint32_t)leaf_count(cur);
             cur = NONE;
         }
+        // if a pop is coming, request the top entry now: its local-memory latency hides behind the triangle test
+        // (ncu: the compare after this load was the hottest stall site of the kernel)
+        const bool popping = cur == NONE && sp > 0;
+        unsigned long long top = 0;
+        if (popping) top = *(volatile unsigned long long*)&stack[sp - 1];
         if (triPos < triEnd) {
             if (STATS) ++stats->tris;
             const float4* tp = sc.tris + (size_t)triPos * 3;
@@ -217,6 +222,10 @@ TMPT_HD HitRec traverse(const SceneView& sc, ex::V3 o, ex::V3 d, float tMin, flo
             }
         }
         // pop: skip entries that the shrinking best.t has already culled
+        if (popping) {
+            --sp;
+            if (ex::u2f((uint32_t)(top >> 32)) <= best.t) cur = (uint32_t)top;
+        }
         while (cur == NONE && sp > 0) {
             const unsigned long long e = stack[--sp];
             if (ex::u2f((uint32_t)(e >> 32)) <= best.t) cur = (uint32_t)e;
