@@ -144,58 +144,82 @@ TMPT_HD bool ray_has_nan(ex::V3 o, ex::V3 d) { return o.x != o.x || o.y != o.y |
 // Culling keeps a child when tNear <= tFar with tFar clipped to the CURRENT best t -- "<=",
 // not "<", so that a triangle in another leaf with bit-equal t and a lower index is still
 // tested.  The candidate rule is the lexicographic minimum of (t, id).
-template <bool ANY, bool STATS = false>
-TMPT_HD HitRec traverse(const SceneView& sc, ex::V3 o, ex::V3 d, float tMin, float tMax, TravStats* stats = nullptr) {
-    HitRec best;
-    best.id = -1; best.t = tMax; best.u = 0.0f; best.v = 0.0f;
+// Ray constants of the slab test and the walk state of one lane.
+struct RayCtx {
+    float idx, idy, idz, ox, oy, oz;  // 1 / dir, orig / dir  (t = plane * idir - ox)
+    uint32_t sx, sy, sz;              // 1 where the direction component is negative: row offset of the near plane
+};
+TMPT_HD RayCtx make_ray_ctx(ex::V3 o, ex::V3 d) {
+    RayCtx r;
     const float sdx = safe_dir(d.x), sdy = safe_dir(d.y), sdz = safe_dir(d.z);
-    const float idx = 1.0f / sdx, idy = 1.0f / sdy, idz = 1.0f / sdz;
-    const float ox = o.x * idx, oy = o.y * idy, oz = o.z * idz;
-    const uint32_t sx = sdx < 0.0f ? 1u : 0u, sy = sdy < 0.0f ? 1u : 0u, sz = sdz < 0.0f ? 1u : 0u;
+    r.idx = 1.0f / sdx; r.idy = 1.0f / sdy; r.idz = 1.0f / sdz;
+    r.ox = o.x * r.idx; r.oy = o.y * r.idy; r.oz = o.z * r.idz;
+    r.sx = sdx < 0.0f ? 1u : 0u; r.sy = sdy < 0.0f ? 1u : 0u; r.sz = sdz < 0.0f ? 1u : 0u;
+    return r;
+}
 
-    unsigned long long stack[STACK_SIZE];  // (entry distance bits << 32) | ref
+// One 4-wide node step: enter the nearest hit child (returned; NONE if no child is hit), push the others.
+TMPT_HD uint32_t wide_node_step(const SceneView& sc, uint32_t node, const RayCtx& r, float tMin, float bestT, unsigned long long* stack, int& sp,
+                                bool& overflow) {
+    const float4* n = sc.nodes + (size_t)node * NODE_F4;
+    const float4 nx = ld_row(n + r.sx), fx = ld_row(n + (r.sx ^ 1u));
+    const float4 ny = ld_row(n + 2 + r.sy), fy = ld_row(n + 2 + (r.sy ^ 1u));
+    const float4 nz = ld_row(n + 4 + r.sz), fz = ld_row(n + 4 + (r.sz ^ 1u));
+    const float4 rf = ld_row(n + 6);
+    uint32_t key[4], ref[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const float a = fmaxf(fmaxf(fmaf_(f4c(nx, k), r.idx, -r.ox), fmaf_(f4c(ny, k), r.idy, -r.oy)), fmaxf(fmaf_(f4c(nz, k), r.idz, -r.oz), tMin));
+        const float b = fminf(fminf(fmaf_(f4c(fx, k), r.idx, -r.ox), fmaf_(f4c(fy, k), r.idy, -r.oy)), fminf(fmaf_(f4c(fz, k), r.idz, -r.oz), bestT));
+        ref[k] = ex::f2u(f4c(rf, k));
+        // clearing the two low mantissa bits only lowers the distance: still conservative for the pop-time cull
+        key[k] = (a <= b && ref[k] != NONE) ? ((ex::f2u(a) & ~3u) | (uint32_t)k) : 0xFFFFFFFFu;
+    }
+    const uint32_t k01 = key[0] < key[1] ? key[0] : key[1], k23 = key[2] < key[3] ? key[2] : key[3];
+    const uint32_t kmin = k01 < k23 ? k01 : k23;
+    if (kmin == 0xFFFFFFFFu) return NONE;
+    const uint32_t ks = kmin & 3u;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        if (key[k] != 0xFFFFFFFFu && (uint32_t)k != ks) {
+            if (sp < STACK_SIZE) stack[sp++] = ((unsigned long long)key[k] << 32) | ref[k];
+            else overflow = true;
+        }
+    }
+    return ks == 0 ? ref[0] : ks == 1 ? ref[1] : ks == 2 ? ref[2] : ref[3];
+}
+
+// One exact test of triangle slot `slot`; returns true when `best` improved.
+TMPT_HD bool tri_step(const SceneView& sc, uint32_t slot, ex::V3 o, ex::V3 d, float tMin, float tMax, HitRec& best) {
+    const float4* tp = sc.tris + (size_t)slot * 3;
+    const float4 a = ld_row(tp + 0), b = ld_row(tp + 1), c = ld_row(tp + 2);
+    float t, u, v;
+    if (mt_exact(o, d, ex::v3(a.x, a.y, a.z), ex::v3(b.x, b.y, b.z), ex::v3(c.x, c.y, c.z), tMin, tMax, t, u, v)) {
+        const int id = (int)ex::f2u(a.w);
+        if (t < best.t || (t == best.t && best.id >= 0 && id < best.id)) {
+            best.t = t; best.id = id; best.u = u; best.v = v;
+            return true;
+        }
+    }
+    return false;
+}
+
+// The walk shared by traverse and traverse_pair.  A lane that reaches a leaf PARKS it
+// (triPos..triEnd) and tests one of its triangles per iteration while it keeps walking inner
+// nodes in the same iteration: the node step and the exact test of one ray overlap instead of
+// alternating, and nobody loops over a whole leaf while its neighbours wait (+12 % on the
+// frame, profiles/).  The walk runs at most one leaf ahead of the tests, so almost nothing is
+// visited that a tighter best t would have culled.  Returns when the ray is finished.
+template <bool STATS>
+TMPT_HD void walk(const SceneView& sc, ex::V3 o, ex::V3 d, const RayCtx& r, float tMin, float tMax, bool any, unsigned long long* stack,
+                  bool& overflow, HitRec& best, TravStats* stats) {
     int sp = 0;
-    bool overflow = false;
     uint32_t cur = ray_has_nan(o, d) ? NONE : sc.rootRef;
-
-    // A lane that reaches a leaf PARKS it (triPos..triEnd) and tests one of its triangles per
-    // iteration while it keeps walking inner nodes in the same iteration: the node step and the
-    // exact test of one ray overlap instead of alternating, and nobody loops over a whole leaf
-    // while its neighbours wait (+7 % on incoherent rays, profiles/).  The walk runs at most one
-    // leaf ahead of the tests, so almost nothing is visited that a tighter best t would have culled.
     uint32_t triPos = 0, triEnd = 0;
     for (;;) {
         if (cur != NONE && !ref_is_leaf(cur)) {
             if (STATS) ++stats->nodes;
-            const float4* n = sc.nodes + (size_t)cur * NODE_F4;
-            const float4 nx = ld_row(n + sx), fx = ld_row(n + (sx ^ 1u));
-            const float4 ny = ld_row(n + 2 + sy), fy = ld_row(n + 2 + (sy ^ 1u));
-            const float4 nz = ld_row(n + 4 + sz), fz = ld_row(n + 4 + (sz ^ 1u));
-            const float4 rf = ld_row(n + 6);
-            uint32_t key[4], ref[4];
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                const float a = fmaxf(fmaxf(fmaf_(f4c(nx, k), idx, -ox), fmaf_(f4c(ny, k), idy, -oy)), fmaxf(fmaf_(f4c(nz, k), idz, -oz), tMin));
-                const float b = fminf(fminf(fmaf_(f4c(fx, k), idx, -ox), fmaf_(f4c(fy, k), idy, -oy)), fminf(fmaf_(f4c(fz, k), idz, -oz), best.t));
-                ref[k] = ex::f2u(f4c(rf, k));
-                // clearing the two low mantissa bits only lowers the distance: still conservative for the pop-time cull
-                key[k] = (a <= b && ref[k] != NONE) ? ((ex::f2u(a) & ~3u) | (uint32_t)k) : 0xFFFFFFFFu;
-            }
-            const uint32_t k01 = key[0] < key[1] ? key[0] : key[1], k23 = key[2] < key[3] ? key[2] : key[3];
-            const uint32_t kmin = k01 < k23 ? k01 : k23;
-            if (kmin == 0xFFFFFFFFu) {
-                cur = NONE;
-            } else {
-                const uint32_t ks = kmin & 3u;
-                cur = ks == 0 ? ref[0] : ks == 1 ? ref[1] : ks == 2 ? ref[2] : ref[3];
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    if (key[k] != 0xFFFFFFFFu && (uint32_t)k != ks) {
-                        if (sp < STACK_SIZE) stack[sp++] = ((unsigned long long)key[k] << 32) | ref[k];
-                        else overflow = true;
-                    }
-                }
-            }
+            cur = wide_node_step(sc, cur, r, tMin, best.t, stack, sp, overflow);
         }
         if (cur != NONE && ref_is_leaf(cur) && triPos == triEnd) {  // park the leaf, free the walker
             triPos = leaf_first(cur);
@@ -209,17 +233,7 @@ TMPT_HD HitRec traverse(const SceneView& sc, ex::V3 o, ex::V3 d, float tMin, flo
         if (popping) top = *(volatile unsigned long long*)&stack[sp - 1];
         if (triPos < triEnd) {
             if (STATS) ++stats->tris;
-            const float4* tp = sc.tris + (size_t)triPos * 3;
-            const float4 a = ld_row(tp + 0), b = ld_row(tp + 1), c = ld_row(tp + 2);
-            ++triPos;
-            float t, u, v;
-            if (mt_exact(o, d, ex::v3(a.x, a.y, a.z), ex::v3(b.x, b.y, b.z), ex::v3(c.x, c.y, c.z), tMin, tMax, t, u, v)) {
-                const int id = (int)ex::f2u(a.w);
-                if (t < best.t || (t == best.t && best.id >= 0 && id < best.id)) {
-                    best.t = t; best.id = id; best.u = u; best.v = v;
-                    if (ANY) break;
-                }
-            }
+            if (tri_step(sc, triPos++, o, d, tMin, tMax, best) && any) return;
         }
         // pop: skip entries that the shrinking best.t has already culled
         if (popping) {
@@ -230,8 +244,17 @@ TMPT_HD HitRec traverse(const SceneView& sc, ex::V3 o, ex::V3 d, float tMin, flo
             const unsigned long long e = stack[--sp];
             if (ex::u2f((uint32_t)(e >> 32)) <= best.t) cur = (uint32_t)e;
         }
-        if (cur == NONE && triPos == triEnd) break;
+        if (cur == NONE && triPos == triEnd) return;
     }
+}
+
+template <bool ANY, bool STATS = false>
+TMPT_HD HitRec traverse(const SceneView& sc, ex::V3 o, ex::V3 d, float tMin, float tMax, TravStats* stats = nullptr) {
+    HitRec best;
+    best.id = -1; best.t = tMax; best.u = 0.0f; best.v = 0.0f;
+    unsigned long long stack[STACK_SIZE];  // (entry distance bits << 32) | ref
+    bool overflow = false;
+    walk<STATS>(sc, o, d, make_ray_ctx(o, d), tMin, tMax, ANY, stack, overflow, best, stats);
     if (overflow && sc.status) *sc.status |= STACK_OVERFLOW;
     return best;
 }
