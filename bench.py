@@ -46,7 +46,8 @@ WORKLOADS = {
     "suzanne_640x360_4spp": ("suzanne", 640, 360, 4),
     "cube_640x360_4spp": ("cube", 640, 360, 4),
 }
-CPU_SAMPLE = {"sponza": (320, 180, 8), "teapot": (320, 180, 8), "suzanne": (640, 360, 4), "cube": (640, 360, 16)}
+# bounded CPU samples (about 10-30 s of CPU work on the box's host cores): same scene and camera, fewer pixels / samples
+CPU_SAMPLE = {"sponza": (640, 360, 8), "teapot": (640, 360, 8), "suzanne": (640, 360, 16), "cube": (640, 360, 64)}
 REF_BIN = os.path.join(ROOT, "oracle", "_ref", "TrimeshTracer")
 
 
