@@ -204,59 +204,72 @@ TMPT_HD bool tri_step(const SceneView& sc, uint32_t slot, ex::V3 o, ex::V3 d, fl
     return false;
 }
 
-// The walk shared by traverse and traverse_pair.  A lane that reaches a leaf PARKS it
-// (triPos..triEnd) and tests one of its triangles per iteration while it keeps walking inner
-// nodes in the same iteration: the node step and the exact test of one ray overlap instead of
-// alternating, and nobody loops over a whole leaf while its neighbours wait (+12 % on the
-// frame, profiles/).  The walk runs at most one leaf ahead of the tests, so almost nothing is
-// visited that a tighter best t would have culled.  Returns when the ray is finished.
+// Walk state of one ray in one lane.
+struct WalkState {
+    RayCtx r;
+    ex::V3 o, d;
+    HitRec best;
+    uint32_t cur, triPos, triEnd;
+    int sp;
+    bool any;
+};
+TMPT_HD void walk_start(WalkState& w, const SceneView& sc, ex::V3 o, ex::V3 d, float tMax, bool any) {
+    w.r = make_ray_ctx(o, d);
+    w.o = o; w.d = d;
+    w.best.id = -1; w.best.t = tMax; w.best.u = 0.0f; w.best.v = 0.0f;
+    w.cur = ray_has_nan(o, d) ? NONE : sc.rootRef;
+    w.triPos = 0; w.triEnd = 0;
+    w.sp = 0;
+    w.any = any;
+}
+
+// One iteration of the walk; returns true when the ray is finished.  A lane that reaches a
+// leaf PARKS it (triPos..triEnd) and tests one of its triangles per iteration while it keeps
+// walking inner nodes in the same iteration: the node step and the exact test of one ray
+// overlap instead of alternating, and nobody loops over a whole leaf while its neighbours
+// wait (+12 % on the frame, profiles/).  The walk runs at most one leaf ahead of the tests, so
+// almost nothing is visited that a tighter best t would have culled.
 template <bool STATS>
-TMPT_HD void walk(const SceneView& sc, ex::V3 o, ex::V3 d, const RayCtx& r, float tMin, float tMax, bool any, unsigned long long* stack,
-                  bool& overflow, HitRec& best, TravStats* stats) {
-    int sp = 0;
-    uint32_t cur = ray_has_nan(o, d) ? NONE : sc.rootRef;
-    uint32_t triPos = 0, triEnd = 0;
-    for (;;) {
-        if (cur != NONE && !ref_is_leaf(cur)) {
-            if (STATS) ++stats->nodes;
-            cur = wide_node_step(sc, cur, r, tMin, best.t, stack, sp, overflow);
-        }
-        if (cur != NONE && ref_is_leaf(cur) && triPos == triEnd) {  // park the leaf, free the walker
-            triPos = leaf_first(cur);
-            triEnd = triPos + (uint32_t)leaf_count(cur);
-            cur = NONE;
-        }
-        // if a pop is coming, request the top entry now: its local-memory latency hides behind the triangle test
-        // (ncu: the compare after this load was the hottest stall site of the kernel)
-        const bool popping = cur == NONE && sp > 0;
-        unsigned long long top = 0;
-        if (popping) top = *(volatile unsigned long long*)&stack[sp - 1];
-        if (triPos < triEnd) {
-            if (STATS) ++stats->tris;
-            if (tri_step(sc, triPos++, o, d, tMin, tMax, best) && any) return;
-        }
-        // pop: skip entries that the shrinking best.t has already culled
-        if (popping) {
-            --sp;
-            if (ex::u2f((uint32_t)(top >> 32)) <= best.t) cur = (uint32_t)top;
-        }
-        while (cur == NONE && sp > 0) {
-            const unsigned long long e = stack[--sp];
-            if (ex::u2f((uint32_t)(e >> 32)) <= best.t) cur = (uint32_t)e;
-        }
-        if (cur == NONE && triPos == triEnd) return;
+TMPT_HD bool walk_step(WalkState& w, const SceneView& sc, float tMin, float tMax, unsigned long long* stack, bool& overflow, TravStats* stats) {
+    if (w.cur != NONE && !ref_is_leaf(w.cur)) {
+        if (STATS) ++stats->nodes;
+        w.cur = wide_node_step(sc, w.cur, w.r, tMin, w.best.t, stack, w.sp, overflow);
     }
+    if (w.cur != NONE && ref_is_leaf(w.cur) && w.triPos == w.triEnd) {  // park the leaf, free the walker
+        w.triPos = leaf_first(w.cur);
+        w.triEnd = w.triPos + (uint32_t)leaf_count(w.cur);
+        w.cur = NONE;
+    }
+    // if a pop is coming, request the top entry now: its local-memory latency hides behind the triangle test
+    // (ncu: the compare after this load was the hottest stall site of the kernel)
+    const bool popping = w.cur == NONE && w.sp > 0;
+    unsigned long long top = 0;
+    if (popping) top = *(volatile unsigned long long*)&stack[w.sp - 1];
+    if (w.triPos < w.triEnd) {
+        if (STATS) ++stats->tris;
+        if (tri_step(sc, w.triPos++, w.o, w.d, tMin, tMax, w.best) && w.any) return true;
+    }
+    // pop: skip entries that the shrinking best.t has already culled
+    if (popping) {
+        --w.sp;
+        if (ex::u2f((uint32_t)(top >> 32)) <= w.best.t) w.cur = (uint32_t)top;
+    }
+    while (w.cur == NONE && w.sp > 0) {
+        const unsigned long long e = stack[--w.sp];
+        if (ex::u2f((uint32_t)(e >> 32)) <= w.best.t) w.cur = (uint32_t)e;
+    }
+    return w.cur == NONE && w.triPos == w.triEnd;
 }
 
 template <bool ANY, bool STATS = false>
 TMPT_HD HitRec traverse(const SceneView& sc, ex::V3 o, ex::V3 d, float tMin, float tMax, TravStats* stats = nullptr) {
-    HitRec best;
-    best.id = -1; best.t = tMax; best.u = 0.0f; best.v = 0.0f;
     unsigned long long stack[STACK_SIZE];  // (entry distance bits << 32) | ref
     bool overflow = false;
-    walk<STATS>(sc, o, d, make_ray_ctx(o, d), tMin, tMax, ANY, stack, overflow, best, stats);
+    WalkState w;
+    walk_start(w, sc, o, d, tMax, ANY);
+    while (!walk_step<STATS>(w, sc, tMin, tMax, stack, overflow, stats)) {}
     if (overflow && sc.status) *sc.status |= STACK_OVERFLOW;
-    return best;
+    return w.best;
 }
 
 // Upstream's HitScene: every triangle, no tree.  Same candidate rule, so it must agree with
