@@ -1,6 +1,7 @@
-// warpq.cuh -- "warp queue" traversal: the engine of the persistent trace kernels (device only).
+// warpq.cuh -- "warp queue" traversal (device only).  EXPERIMENT, selectable with TMPT_HIT_KERNEL=5 for A/B runs;
+// bit-exact, but slower than bvh::traverse on B200 -- kept as the measured record of the idea.
 //
-// Why it exists (ncu, profiles/r1_hit_scene_v0.txt): with one ray per lane and the leaf test
+// Why it exists (ncu, profiles/r1_hit_scene_variants_ncu.txt): with one ray per lane and the leaf test
 // inline, the wide-node step ran with ~15 of 32 lanes active but the exact Moller-Trumbore
 // code -- 46 % of all warp instructions -- ran with THREE, because only a few lanes stand at
 // a leaf in any given iteration.  Here the two kinds of work are decoupled inside the warp:

@@ -1,4 +1,6 @@
-// wtrace.cuh -- warp-synchronous traversal with DEFERRED triangle tests (device only).
+// wtrace.cuh -- warp-synchronous traversal with DEFERRED triangle tests (device only).  EXPERIMENTS, selectable
+// with TMPT_HIT_KERNEL=10/11 (deferral thresholds) and 20 (cooperative leaf phase) for A/B runs; bit-exact; the
+// per-lane "parked leaf" idea that came out of them is what bvh::traverse now does.
 //
 // Same HitScene contract as bvh::traverse.  All 32 lanes of a warp call it together, each
 // with its own ray (or active = false).  What it changes, and why (ncu, profiles/): with the
