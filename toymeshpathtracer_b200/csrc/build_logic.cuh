@@ -302,10 +302,16 @@ TMPT_HD void collapse_node(const BinTree& t, const WideOut& w, const WorkItem& i
         c[pick] = t.left[open];
         c[k++] = t.right[open];
     }
-    int nInner = 0;
-    for (int j = 0; j < k; ++j) nInner += subtree_is_leaf(t, c[j]) ? 0 : 1;
+    int nInner = 0, nLeafTris = 0;
+    for (int j = 0; j < k; ++j) {
+        if (subtree_is_leaf(t, c[j])) nLeafTris += subtree_count(t, c[j]);
+        else ++nInner;
+    }
     uint32_t wideBase = nInner ? counter_add(&w.counters[0], (uint32_t)nInner) : 0u;
     uint32_t qBase = nInner ? counter_add(outCount, (uint32_t)nInner) : 0u;
+    // the leaf children of one node get CONSECUTIVE triangle slots: a ray that visits one usually visits its
+    // siblings, and a 128-byte line holds 2.7 slots
+    uint32_t slotBase = nLeafTris ? counter_add(&w.counters[1], (uint32_t)nLeafTris) : 0u;
 
     float lox[4], loy[4], loz[4], hix[4], hiy[4], hiz[4];
     uint32_t refs[4];
@@ -318,7 +324,10 @@ TMPT_HD void collapse_node(const BinTree& t, const WideOut& w, const WorkItem& i
     int inner = 0;
     for (int j = 0; j < 4; ++j) {
         if (j >= k) {
-            lox[j] = loy[j] = loz[j] = hix[j] = hiy[j] = hiz[j] = 3.0e38f;  // far-away point box
+            // empty child: an INVERTED box (lo = +3e38, hi = -3e38) fails tNear <= tFar for every ray, so the
+            // traversal needs no "is this child there" test
+            lox[j] = loy[j] = loz[j] = 3.0e38f;
+            hix[j] = hiy[j] = hiz[j] = -3.0e38f;
             refs[j] = bvh::NONE;
             continue;
         }
@@ -326,7 +335,8 @@ TMPT_HD void collapse_node(const BinTree& t, const WideOut& w, const WorkItem& i
         lox[j] = lo.x; loy[j] = lo.y; loz[j] = lo.z; hix[j] = hi.x; hiy[j] = hi.y; hiz[j] = hi.z;
         if (subtree_is_leaf(t, c[j])) {
             const int cnt = subtree_count(t, c[j]);
-            const uint32_t first = counter_add(&w.counters[1], (uint32_t)cnt);
+            const uint32_t first = slotBase;
+            slotBase += (uint32_t)cnt;
             counter_add(&w.counters[2], 1u);
             emit_leaf_tris(t, w, c[j], first);
             refs[j] = bvh::make_leaf_ref(first, cnt);
@@ -357,11 +367,11 @@ TMPT_HD void emit_single_leaf_root(const BinTree& t, const WideOut& w, int rootN
     counter_add(&w.counters[2], 1u);
     emit_leaf_tris(t, w, rootNode, first);
     const float4 lo = t.lo[rootNode], hi = t.hi[rootNode];
-    const float F = 3.0e38f;
+    const float F = 3.0e38f;  // empty children: inverted boxes (see collapse_node)
     float4* o = w.nodes;
-    o[0] = make_float4(lo.x, F, F, F); o[1] = make_float4(hi.x, F, F, F);
-    o[2] = make_float4(lo.y, F, F, F); o[3] = make_float4(hi.y, F, F, F);
-    o[4] = make_float4(lo.z, F, F, F); o[5] = make_float4(hi.z, F, F, F);
+    o[0] = make_float4(lo.x, F, F, F); o[1] = make_float4(hi.x, -F, -F, -F);
+    o[2] = make_float4(lo.y, F, F, F); o[3] = make_float4(hi.y, -F, -F, -F);
+    o[4] = make_float4(lo.z, F, F, F); o[5] = make_float4(hi.z, -F, -F, -F);
     o[6] = make_float4(ex::u2f(bvh::make_leaf_ref(first, cnt)), ex::u2f(bvh::NONE), ex::u2f(bvh::NONE), ex::u2f(bvh::NONE));
     accum_add(&w.sahAccum[1], box_half_area(Box{lo.x, lo.y, lo.z, hi.x, hi.y, hi.z}) * (float)cnt);
 }

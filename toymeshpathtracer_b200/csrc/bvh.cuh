@@ -17,7 +17,8 @@
 //           offset rotates with the node index and the lanes spread over the banks.
 //           child ref: bit 31 clear -> index of an inner node
 //                      bit 31 set   -> leaf: bits 28..30 = triCount-1, bits 0..27 = first slot
-//           an unused child has ref 0xFFFFFFFF and a far-away point box; it is never entered.
+//           an unused child has ref 0xFFFFFFFF and an inverted box (lo = +3e38, hi = -3e38): tNear <= tFar
+//           fails for every ray, so it is never entered and the node step does not look at its ref.
 //   tris  : leaf-ordered triangle slots, 3 x float4 each, precomputed Moller-Trumbore form:
 //             [0] v0.xyz, original index (bit-cast int)   [1] e1 = v1-v0   [2] e2 = v2-v0
 //           (e1, e2 are the same correctly rounded differences maths.cpp:343-344 computes)
@@ -173,7 +174,8 @@ TMPT_HD uint32_t wide_node_step(const SceneView& sc, uint32_t node, const RayCtx
         const float b = fminf(fminf(fmaf_(f4c(fx, k), r.idx, -r.ox), fmaf_(f4c(fy, k), r.idy, -r.oy)), fminf(fmaf_(f4c(fz, k), r.idz, -r.oz), bestT));
         ref[k] = ex::f2u(f4c(rf, k));
         // clearing the two low mantissa bits only lowers the distance: still conservative for the pop-time cull
-        key[k] = (a <= b && ref[k] != NONE) ? ((ex::f2u(a) & ~3u) | (uint32_t)k) : 0xFFFFFFFFu;
+        // (an empty child has an inverted box and can never pass a <= b: no test of the ref is needed)
+        key[k] = (a <= b) ? ((ex::f2u(a) & ~3u) | (uint32_t)k) : 0xFFFFFFFFu;
     }
     const uint32_t k01 = key[0] < key[1] ? key[0] : key[1], k23 = key[2] < key[3] ? key[2] : key[3];
     const uint32_t kmin = k01 < k23 ? k01 : k23;
