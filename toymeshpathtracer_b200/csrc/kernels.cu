@@ -690,40 +690,52 @@ int build_bvh(tmpt_scene* s, unsigned flags) {
     const float cInner = getenv("TMPT_SAH_CI") ? (float)atof(getenv("TMPT_SAH_CI")) : 1.0f, cTri = 1.0f;
     const int maxLeaf = getenv("TMPT_SAH_MAXLEAF") ? std::max(1, std::min(bvh::MAX_LEAF_TRIS, atoi(getenv("TMPT_SAH_MAXLEAF")))) : bvh::MAX_LEAF_TRIS;
 
-    DevBuf<uint32_t> bounds, primA, primB, visits, counters, qCount;
-    DevBuf<uint64_t> keysA, keysB;
-    DevBuf<int> left, right, parent, first;
-    DevBuf<float4> lo, hi;
-    DevBuf<float> sah;
-    DevBuf<bld::WorkItem> qA, qB;
-    CU_TRY(bounds.alloc(6)); CU_TRY(primA.alloc(n)); CU_TRY(primB.alloc(n)); CU_TRY(keysA.alloc(n)); CU_TRY(keysB.alloc(n));
-    CU_TRY(visits.alloc(n)); CU_TRY(counters.alloc(4)); CU_TRY(qCount.alloc(2));
-    CU_TRY(left.alloc(2 * (size_t)n)); CU_TRY(right.alloc(2 * (size_t)n)); CU_TRY(parent.alloc(2 * (size_t)n)); CU_TRY(first.alloc(2 * (size_t)n));
-    CU_TRY(lo.alloc(2 * (size_t)n)); CU_TRY(hi.alloc(2 * (size_t)n)); CU_TRY(sah.alloc(2));
-    CU_TRY(qA.alloc(n)); CU_TRY(qB.alloc(n));
+    // every build scratch array comes out of ONE allocation (a dozen cudaMalloc/cudaFree pairs cost more than the kernels)
+    struct Arr { void* p = nullptr; };
+    Arr bounds, primA, primB, visits, counters, qCount, keysA, keysB, left, right, parent, first, lo, hi, sah, qA, qB, pLo, pHi, primFinal, nodeCounter, tqA, tqB;
+    DevBuf<char> arena;
+    {
+        const size_t N = (size_t)n;
+        struct Req { Arr* a; size_t bytes; };
+        const Req reqs[] = {{&bounds, 6 * 4}, {&primA, N * 4}, {&primB, N * 4}, {&visits, N * 4}, {&counters, 4 * 4}, {&qCount, 2 * 4}, {&keysA, N * 8},
+                            {&keysB, N * 8}, {&left, 2 * N * 4}, {&right, 2 * N * 4}, {&parent, 2 * N * 4}, {&first, 2 * N * 4}, {&lo, 2 * N * 16},
+                            {&hi, 2 * N * 16}, {&sah, 2 * 4}, {&qA, N * sizeof(bld::WorkItem)}, {&qB, N * sizeof(bld::WorkItem)}, {&pLo, N * 16},
+                            {&pHi, N * 16}, {&primFinal, N * 4}, {&nodeCounter, 4}, {&tqA, N * sizeof(SahTask)}, {&tqB, N * sizeof(SahTask)}};
+        size_t total = 0;
+        for (const Req& r : reqs) total += (r.bytes + 255) & ~(size_t)255;
+        CU_TRY(arena.alloc(total));
+        size_t off = 0;
+        for (const Req& r : reqs) { r.a->p = arena.p + off; off += (r.bytes + 255) & ~(size_t)255; }
+    }
     CU_TRY(cudaMalloc((void**)&s->d_nodes, (size_t)n * bvh::NODE_F4 * sizeof(float4)));
     CU_TRY(cudaMalloc((void**)&s->d_tris, (size_t)n * 3 * sizeof(float4)));
 
+    uint32_t* const d_bounds = (uint32_t*)bounds.p; uint32_t* const d_primA = (uint32_t*)primA.p; uint32_t* const d_primB = (uint32_t*)primB.p;
+    uint32_t* const d_visits = (uint32_t*)visits.p; uint32_t* const d_counters = (uint32_t*)counters.p; uint32_t* const d_qCount = (uint32_t*)qCount.p;
+    uint64_t* const d_keysA = (uint64_t*)keysA.p; uint64_t* const d_keysB = (uint64_t*)keysB.p;
+    int* const d_left = (int*)left.p; int* const d_right = (int*)right.p; int* const d_parent = (int*)parent.p; int* const d_first = (int*)first.p;
+    float4* const d_lo = (float4*)lo.p; float4* const d_hi = (float4*)hi.p; float* const d_sah = (float*)sah.p;
+    bld::WorkItem* const d_qA = (bld::WorkItem*)qA.p; bld::WorkItem* const d_qB = (bld::WorkItem*)qB.p;
     const uint32_t initBounds[6] = {0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0u, 0u, 0u};
-    CU_TRY(cudaMemcpyAsync(bounds.p, initBounds, sizeof initBounds, cudaMemcpyHostToDevice, st));
-    CU_TRY(cudaMemsetAsync(visits.p, 0, (size_t)n * sizeof(uint32_t), st));
-    CU_TRY(cudaMemsetAsync(counters.p, 0, 4 * sizeof(uint32_t), st));
-    CU_TRY(cudaMemsetAsync(sah.p, 0, 2 * sizeof(float), st));
-    CU_TRY(cudaMemsetAsync(parent.p, 0xFF, 2 * (size_t)n * sizeof(int), st));
+    CU_TRY(cudaMemcpyAsync(d_bounds, initBounds, sizeof initBounds, cudaMemcpyHostToDevice, st));
+    CU_TRY(cudaMemsetAsync(d_visits, 0, (size_t)n * sizeof(uint32_t), st));
+    CU_TRY(cudaMemsetAsync(d_counters, 0, 4 * sizeof(uint32_t), st));
+    CU_TRY(cudaMemsetAsync(d_sah, 0, 2 * sizeof(float), st));
+    CU_TRY(cudaMemsetAsync(d_parent, 0xFF, 2 * (size_t)n * sizeof(int), st));
 
     const int B = 256, G = div_up(n, B);
-    LAUNCH(k_prim_bounds, G, B, 0, st, s->d_tris9, n, bounds.p);
-    bld::BinTree t{n, keysA.p, left.p, right.p, parent.p, lo.p, hi.p, first.p, visits.p};
+    LAUNCH(k_prim_bounds, G, B, 0, st, s->d_tris9, n, d_bounds);
+    bld::BinTree t{n, d_keysA, d_left, d_right, d_parent, d_lo, d_hi, d_first, d_visits};
     bld::SahParams sp{cInner, cTri, maxLeaf};
-    const uint32_t* primOrder = primA.p;
+    const uint32_t* primOrder = d_primA;
     int rootIsLeaf = (n == 1);
     if (flags & TMPT_BUILD_LBVH) {
-        LAUNCH(k_morton, G, B, 0, st, s->d_tris9, n, bounds.p, keysA.p, primA.p);
+        LAUNCH(k_morton, G, B, 0, st, s->d_tris9, n, d_bounds, d_keysA, d_primA);
         const int passes = 16;  // 63-bit keys, 4 bits per pass; an even count leaves the result in A
         const int sortSmem = 16 * SORT_THREADS * (int)sizeof(uint32_t);
         CU_TRY(cudaFuncSetAttribute(k_radix_sort, cudaFuncAttributeMaxDynamicSharedMemorySize, sortSmem));
-        LAUNCH(k_radix_sort, 1, SORT_THREADS, sortSmem, st, keysA.p, primA.p, keysB.p, primB.p, n, passes);
-        LAUNCH(k_leaf_boxes, G, B, 0, st, s->d_tris9, primA.p, n, bounds.p, cTri, lo.p, hi.p, first.p);
+        LAUNCH(k_radix_sort, 1, SORT_THREADS, sortSmem, st, d_keysA, d_primA, d_keysB, d_primB, n, passes);
+        LAUNCH(k_leaf_boxes, G, B, 0, st, s->d_tris9, d_primA, n, d_bounds, cTri, d_lo, d_hi, d_first);
         if (n > 1) {
             LAUNCH(k_karras, div_up(n - 1, B), B, 0, st, t);
             LAUNCH(k_refit, G, B, 0, st, t, sp);
@@ -731,68 +743,66 @@ int build_bvh(tmpt_scene* s, unsigned flags) {
         s->info.builder = TMPT_BUILD_LBVH;
     } else {
         // binned SAH, level by level; tasks double-buffer in the collapse queues' memory
-        DevBuf<float4> pLo, pHi;
-        DevBuf<uint32_t> primFinal, nodeCounter;
-        DevBuf<SahTask> tqA, tqB;
-        CU_TRY(pLo.alloc(n)); CU_TRY(pHi.alloc(n)); CU_TRY(primFinal.alloc(n)); CU_TRY(nodeCounter.alloc(1));
-        CU_TRY(tqA.alloc(n)); CU_TRY(tqB.alloc(n));
-        LAUNCH(k_prim_boxes, G, B, 0, st, s->d_tris9, n, bounds.p, pLo.p, pHi.p, primA.p);
+        float4* const d_pLo = (float4*)pLo.p; float4* const d_pHi = (float4*)pHi.p;
+        uint32_t* const d_primFinal = (uint32_t*)primFinal.p; uint32_t* const d_nodeCounter = (uint32_t*)nodeCounter.p;
+        SahTask* const d_tqA = (SahTask*)tqA.p; SahTask* const d_tqB = (SahTask*)tqB.p;
+        LAUNCH(k_prim_boxes, G, B, 0, st, s->d_tris9, n, d_bounds, d_pLo, d_pHi, d_primA);
         const SahTask rootTask{0, 0, n};
         const uint32_t one = 1, zero = 0;
-        CU_TRY(cudaMemcpyAsync(tqA.p, &rootTask, sizeof rootTask, cudaMemcpyHostToDevice, st));
-        CU_TRY(cudaMemcpyAsync(nodeCounter.p, &one, 4, cudaMemcpyHostToDevice, st));
-        uint32_t* idxIn = primA.p; uint32_t* idxOut = primB.p;
-        SahTask* qin = tqA.p; SahTask* qout = tqB.p;
+        CU_TRY(cudaMemcpyAsync(d_tqA, &rootTask, sizeof rootTask, cudaMemcpyHostToDevice, st));
+        CU_TRY(cudaMemcpyAsync(d_nodeCounter, &one, 4, cudaMemcpyHostToDevice, st));
+        uint32_t* idxIn = d_primA; uint32_t* idxOut = d_primB;
+        SahTask* qin = d_tqA; SahTask* qout = d_tqB;
         uint32_t count = 1;
         int levels = 0;
         while (count > 0) {
-            CU_TRY(cudaMemcpyAsync(qCount.p, &zero, 4, cudaMemcpyHostToDevice, st));
-            LAUNCH(k_sah_level, count, SAH_THREADS, 0, st, t, pLo.p, pHi.p, idxIn, idxOut, primFinal.p, qin, qout, qCount.p, nodeCounter.p, sp);
-            CU_TRY(cudaMemcpyAsync(&count, qCount.p, 4, cudaMemcpyDeviceToHost, st));
+            CU_TRY(cudaMemcpyAsync(d_qCount, &zero, 4, cudaMemcpyHostToDevice, st));
+            LAUNCH(k_sah_level, count, SAH_THREADS, 0, st, t, d_pLo, d_pHi, idxIn, idxOut, d_primFinal, qin, qout, d_qCount, d_nodeCounter, sp);
+            CU_TRY(cudaMemcpyAsync(&count, d_qCount, 4, cudaMemcpyDeviceToHost, st));
             CU_TRY(cudaStreamSynchronize(st));
             std::swap(idxIn, idxOut);
             std::swap(qin, qout);
             if (++levels > 4096) return tmpt::fail(TMPT_ERR_CUDA, "SAH build did not terminate");
         }
         // the final order lives in primFinal; keep it in primA for the collapse (same stream, device copy)
-        CU_TRY(cudaMemcpyAsync(primA.p, primFinal.p, (size_t)n * sizeof(uint32_t), cudaMemcpyDeviceToDevice, st));
+        CU_TRY(cudaMemcpyAsync(d_primA, d_primFinal, (size_t)n * sizeof(uint32_t), cudaMemcpyDeviceToDevice, st));
         CU_TRY(cudaStreamSynchronize(st));
         s->info.builder = TMPT_BUILD_DEFAULT;
     }
-    bld::WideOut w{s->d_nodes, s->d_tris, s->d_tris9, primOrder, counters.p, sah.p};
+    bld::WideOut w{s->d_nodes, s->d_tris, s->d_tris9, primOrder, d_counters, d_sah};
     if (n > 1) {
         float4 rootHi;
-        CU_TRY(cudaMemcpyAsync(&rootHi, hi.p, sizeof rootHi, cudaMemcpyDeviceToHost, st));
+        CU_TRY(cudaMemcpyAsync(&rootHi, d_hi, sizeof rootHi, cudaMemcpyDeviceToHost, st));
         CU_TRY(cudaStreamSynchronize(st));
         int c; memcpy(&c, &rootHi.w, 4);
         rootIsLeaf = c < 0;
     }
     if (rootIsLeaf) {
         const uint32_t one = 1;
-        CU_TRY(cudaMemcpyAsync(counters.p, &one, 4, cudaMemcpyHostToDevice, st));
+        CU_TRY(cudaMemcpyAsync(d_counters, &one, 4, cudaMemcpyHostToDevice, st));
         LAUNCH(k_collapse_root_leaf, 1, 1, 0, st, t, w, 0);
     } else {
         const bld::WorkItem root{0, 0u, 0};
         const uint32_t one = 1, zero = 0;
-        CU_TRY(cudaMemcpyAsync(qA.p, &root, sizeof root, cudaMemcpyHostToDevice, st));
-        CU_TRY(cudaMemcpyAsync(counters.p, &one, 4, cudaMemcpyHostToDevice, st));   // wide node 0 is taken
-        CU_TRY(cudaMemcpyAsync(qCount.p, &one, 4, cudaMemcpyHostToDevice, st));
-        bld::WorkItem* qin = qA.p; bld::WorkItem* qout = qB.p;
+        CU_TRY(cudaMemcpyAsync(d_qA, &root, sizeof root, cudaMemcpyHostToDevice, st));
+        CU_TRY(cudaMemcpyAsync(d_counters, &one, 4, cudaMemcpyHostToDevice, st));   // wide node 0 is taken
+        CU_TRY(cudaMemcpyAsync(d_qCount, &one, 4, cudaMemcpyHostToDevice, st));
+        bld::WorkItem* qin = d_qA; bld::WorkItem* qout = d_qB;
         int cin = 0;
         uint32_t count = 1;
         while (count > 0) {
-            CU_TRY(cudaMemcpyAsync(qCount.p + (1 - cin), &zero, 4, cudaMemcpyHostToDevice, st));
-            LAUNCH(k_collapse, div_up(count, 128), 128, 0, st, t, w, qin, qCount.p + cin, qout, qCount.p + (1 - cin));
-            CU_TRY(cudaMemcpyAsync(&count, qCount.p + (1 - cin), 4, cudaMemcpyDeviceToHost, st));
+            CU_TRY(cudaMemcpyAsync(d_qCount + (1 - cin), &zero, 4, cudaMemcpyHostToDevice, st));
+            LAUNCH(k_collapse, div_up(count, 128), 128, 0, st, t, w, qin, d_qCount + cin, qout, d_qCount + (1 - cin));
+            CU_TRY(cudaMemcpyAsync(&count, d_qCount + (1 - cin), 4, cudaMemcpyDeviceToHost, st));
             CU_TRY(cudaStreamSynchronize(st));
             cin = 1 - cin;
             bld::WorkItem* tq = qin; qin = qout; qout = tq;
         }
     }
     uint32_t hc[4]; float hs[2]; uint32_t hb[6];
-    CU_TRY(cudaMemcpyAsync(hc, counters.p, sizeof hc, cudaMemcpyDeviceToHost, st));
-    CU_TRY(cudaMemcpyAsync(hs, sah.p, sizeof hs, cudaMemcpyDeviceToHost, st));
-    CU_TRY(cudaMemcpyAsync(hb, bounds.p, sizeof hb, cudaMemcpyDeviceToHost, st));
+    CU_TRY(cudaMemcpyAsync(hc, d_counters, sizeof hc, cudaMemcpyDeviceToHost, st));
+    CU_TRY(cudaMemcpyAsync(hs, d_sah, sizeof hs, cudaMemcpyDeviceToHost, st));
+    CU_TRY(cudaMemcpyAsync(hb, d_bounds, sizeof hb, cudaMemcpyDeviceToHost, st));
     CU_TRY(cudaStreamSynchronize(st));
     CU_TRY(cudaGetLastError());
     s->info.node_count = (int)hc[0];
