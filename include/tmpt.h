@@ -132,6 +132,15 @@ int tmpt_stripe_rows(int height, int stripeRows, int rank, int worldSize); /* ro
 int tmpt_unpack_stripes(const uint8_t* gathered, int width, int height, int stripeRows, int worldSize,
                         int device, uint8_t* frame, void* stream);
 
+/* One frame on several GPUs from ONE process: scenes[i] is a replica of the same triangles on its
+ * own device (tmpt_scene_create per device).  Device i renders the row stripes of rank i of
+ * nScenes (as tmpt_render_stripes) and stores its pixels straight into the frame that lives on
+ * scenes[0]'s device -- peer access over NVLink / NVSwitch -- which is then copied to `rgba`
+ * (host memory, width*height*4).  The multi-GPU form of the tbb::parallel_for of main.cpp:329-331
+ * for the command line (TMPT_GPUS=n); multi-process callers use tmpt_render_stripes + tmpt_frame_*. */
+int tmpt_render_multi(tmpt_scene* const* scenes, int nScenes, const tmpt_camera* camera, int width, int height, int spp,
+                      uint8_t* rgba, uint64_t* rayCount, double* seconds);
+
 /* Frame memory that other ranks (processes) on the same node can write: rank 0 allocates
  * the full-size frame and exports a 64-byte CUDA IPC handle; every other rank opens it and
  * passes the mapped pointer as `peerFrame` to tmpt_render_stripes, so its pixels travel over

@@ -488,3 +488,19 @@ def test_sponza_image_vs_reference_binary(tmp_path):
     assert "(66452 tris)" in r.stdout and "(66452 tris)" in g.stdout
     assert abs(kg / kr - 1) < 0.01          # same scene, same integrator: ray counts agree to a fraction of a percent
     assert mae <= 6.0 and mae_box <= 1.5 and dmean <= 0.3 and poisoned.sum() <= 16
+
+
+def test_render_multi_single_process(scenes):
+    """tmpt_render_multi: replicas on every visible device (one on the test box), pixels stored into device 0's frame."""
+    sc = load_scene("suzanne")
+    w, h, spp = 120, 66, 12
+    cam = tm.camera_for_scene("suzanne.obj", sc["bounds_min"], sc["bounds_max"], w, h)
+    want, want_rays, _ = scenes("suzanne").render(cam, w, h, spp)
+    n = min(tm.device_count(), 4)
+    reps = [tm.Scene(sc["tris"], device=d) for d in range(n)]
+    try:
+        img, rays, sec = tm.render_multi(reps, cam, w, h, spp)
+    finally:
+        for r in reps:
+            r.close()
+    assert rays == want_rays and (img == want).all() and sec > 0

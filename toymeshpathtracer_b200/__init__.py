@@ -37,7 +37,7 @@ ABI_SYMBOLS = [
     "tmpt_render_stripes", "tmpt_stripe_rows", "tmpt_unpack_stripes", "tmpt_load_obj", "tmpt_free",
     "tmpt_camera_make", "tmpt_camera_for_scene", "tmpt_write_png", "tmpt_main", "tmpt_last_error",
     "tmpt_device_count", "tmpt_launch_count", "tmpt_render_stats", "tmpt_hit_scene_stats",
-    "tmpt_frame_alloc", "tmpt_frame_open", "tmpt_frame_close", "tmpt_frame_free",
+    "tmpt_frame_alloc", "tmpt_frame_open", "tmpt_frame_close", "tmpt_frame_free", "tmpt_render_multi",
 ]
 
 
@@ -87,6 +87,7 @@ def lib() -> C.CDLL:
     L.tmpt_unpack_stripes.argtypes = [vp, i32, i32, i32, i32, i32, vp, vp]
     L.tmpt_render_stats.argtypes = [vp, vp, i32, i32, i32, vp]
     L.tmpt_hit_scene_stats.argtypes = [vp, vp, i64, f32, f32, i32, vp]
+    L.tmpt_render_multi.argtypes = [vp, i32, vp, i32, i32, i32, vp, C.POINTER(C.c_uint64), C.POINTER(C.c_double)]
     L.tmpt_frame_alloc.argtypes = [i32, C.c_size_t, C.POINTER(vp), vp]
     L.tmpt_frame_open.argtypes = [i32, vp, C.POINTER(vp)]
     L.tmpt_frame_close.argtypes = [i32, vp]
@@ -169,6 +170,16 @@ def main(argv) -> int:
     args = [b"TrimeshTracer"] + [os.fsencode(a) for a in argv]
     arr = (C.c_char_p * len(args))(*args)
     return lib().tmpt_main(len(args), arr)
+
+
+def render_multi(scenes, camera, width: int, height: int, spp: int):
+    """One frame on several GPUs from this process: scenes[i] is the replica on device i (tmpt_render_multi)."""
+    cam = _f32(camera).reshape(22)
+    rgba = np.zeros((height, width, 4), np.uint8)
+    rays, sec = C.c_uint64(0), C.c_double(0.0)
+    handles = (C.c_void_p * len(scenes))(*[s.handle for s in scenes])
+    _check(lib().tmpt_render_multi(handles, len(scenes), _ptr(cam), width, height, spp, _ptr(rgba), C.byref(rays), C.byref(sec)))
+    return rgba, rays.value, sec.value
 
 
 class Scene:

@@ -318,16 +318,24 @@ extern "C" int tmpt_main(int argc, const char** argv) {
         std::printf("ERROR: failed to load .obj file\n");
         return 1;
     }
+    // TMPT_DEVICE=<first device>, TMPT_GPUS=<n>: n replicas on devices first .. first+n-1, rows dealt out in stripes
     const char* devEnv = std::getenv("TMPT_DEVICE");
+    const char* gpusEnv = std::getenv("TMPT_GPUS");
     const int device = devEnv ? std::atoi(devEnv) : 0;
+    const int gpus = gpusEnv ? std::atoi(gpusEnv) : 1;
+    if (gpus < 1 || gpus > 64) { std::printf("ERROR: invalid TMPT_GPUS '%s'\n", gpusEnv); tmpt_free(tris); return 1; }
     const auto t0 = std::chrono::steady_clock::now();
-    tmpt_scene* scene = nullptr;
-    const int rc = tmpt_scene_create(tris, triCount, device, TMPT_BUILD_DEFAULT, &scene);
-    tmpt_free(tris);
-    if (rc != TMPT_OK) {
-        std::printf("ERROR: %s\n", tmpt_last_error());
-        return 1;
+    std::vector<tmpt_scene*> scenes((size_t)gpus, nullptr);
+    auto destroy_all = [&]() { for (tmpt_scene* sc : scenes) tmpt_scene_destroy(sc); };
+    for (int i = 0; i < gpus; ++i) {
+        if (tmpt_scene_create(tris, triCount, device + i, TMPT_BUILD_DEFAULT, &scenes[(size_t)i]) != TMPT_OK) {
+            std::printf("ERROR: %s\n", tmpt_last_error());
+            tmpt_free(tris);
+            destroy_all();
+            return 1;
+        }
     }
+    tmpt_free(tris);
     const double initSec = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
     std::printf("Initialized scene '%s' (%i tris) in %.3fs\n", argv[4], triCount, initSec);
 
@@ -336,14 +344,14 @@ extern "C" int tmpt_main(int argc, const char** argv) {
     std::vector<uint8_t> image((size_t)width * height * 4, 0);
     uint64_t rayCount = 0;
     double dt = 0.0;
-    if (tmpt_render(scene, &camera, width, height, spp, TMPT_HOST, image.data(), &rayCount, &dt, nullptr) != TMPT_OK) {
+    if (tmpt_render_multi(scenes.data(), gpus, &camera, width, height, spp, image.data(), &rayCount, &dt) != TMPT_OK) {
         std::printf("ERROR: %s\n", tmpt_last_error());
-        tmpt_scene_destroy(scene);
+        destroy_all();
         return 1;
     }
     std::printf("Rendered scene at %ix%i,%ispp in %.3f s\n", width, height, spp, dt);
     std::printf("- %.1f K Rays, %.1f K Rays/s\n", rayCount / 1000.0, rayCount / 1000.0 / dt);
-    tmpt_scene_destroy(scene);
+    destroy_all();
     if (tmpt_write_png("output.png", width, height, image.data(), 1) != TMPT_OK) {
         std::printf("ERROR: %s\n", tmpt_last_error());
         return 1;

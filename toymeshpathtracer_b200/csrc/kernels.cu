@@ -13,6 +13,7 @@
 #include <cuda_runtime.h>
 
 #include <atomic>
+#include <chrono>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -1004,6 +1005,27 @@ extern "C" int tmpt_stripe_rows(int height, int stripeRows, int rank, int worldS
 
 static ex::V3 host_light_dir() { return ex::normalize(ex::v3(-0.7f, 1.0f, 0.5f)); }  // main.cpp:36
 
+// Chunk sums go to an accumulation buffer when a pixel has more than one chunk; the frame is rendered in bands of
+// owned rows so that the buffer stays within a fixed budget (a whole 1080p x 64 spp frame is 265 MB).  Allocation
+// happens here so that callers can do it before their timed window starts.
+static int prepare_render(tmpt_scene* s, int width, int spp, int ownedRows, cudaStream_t st, int* outBandRows) {
+    const int chunks = integ::chunk_count(spp);
+    int bandRows = ownedRows;
+    if (chunks > 1 && ownedRows > 0) {
+        const size_t rowBytes = (size_t)width * chunks * sizeof(float4), budget = (size_t)1 << 30;
+        bandRows = (int)std::min<size_t>((size_t)ownedRows, std::max<size_t>(4, (budget / rowBytes) & ~(size_t)3));
+        const size_t need = (size_t)bandRows * rowBytes;
+        if (s->accumBytes < need) {
+            CU_TRY(cudaStreamSynchronize(st));
+            cudaFree(s->d_accum); s->d_accum = nullptr; s->accumBytes = 0;
+            CU_TRY(cudaMalloc((void**)&s->d_accum, need));
+            s->accumBytes = need;
+        }
+    }
+    if (outBandRows) *outBandRows = bandRows;
+    return TMPT_OK;
+}
+
 static int launch_render(const tmpt_scene* cs, const tmpt_camera* camera, int width, int height, int spp, int stripeRows, int rank, int world,
                          uint8_t* outStripes, uint8_t* frame, unsigned long long* rayCountDev, cudaStream_t st,
                          unsigned long long* statsDev = nullptr) {
@@ -1025,20 +1047,10 @@ static int launch_render(const tmpt_scene* cs, const tmpt_camera* camera, int wi
     p.stats = statsDev;
     p.accum = nullptr;
     if (p.ownedRows == 0) return TMPT_OK;
-    // bands of owned rows so that the chunk-sum buffer stays within a fixed budget (a whole 1080p x 64 spp frame is 265 MB)
-    int bandRows = p.ownedRows;
-    if (p.chunks > 1) {
-        const size_t rowBytes = (size_t)width * p.chunks * sizeof(float4), budget = (size_t)1 << 30;
-        bandRows = (int)std::min<size_t>((size_t)p.ownedRows, std::max<size_t>(4, (budget / rowBytes) & ~(size_t)3));
-        const size_t need = (size_t)bandRows * rowBytes;
-        if (s->accumBytes < need) {
-            CU_TRY(cudaStreamSynchronize(st));
-            cudaFree(s->d_accum); s->d_accum = nullptr; s->accumBytes = 0;
-            CU_TRY(cudaMalloc((void**)&s->d_accum, need));
-            s->accumBytes = need;
-        }
-        p.accum = s->d_accum;
-    }
+    int bandRows = 0;
+    const int prc = prepare_render(s, width, spp, p.ownedRows, st, &bandRows);
+    if (prc != TMPT_OK) return prc;
+    p.accum = s->d_accum;
     // 256 threads x 4 CTAs/SM = 32 warps/SM at 64 registers (sweep in profiles/r1_tuning_sweeps.txt: 24 warps at
     // 77 registers is 10 % slower, 40 warps at 48 registers spills and is 3 % slower)
     int perSM = 0;
@@ -1098,6 +1110,8 @@ extern "C" int tmpt_render(const tmpt_scene* cs, const tmpt_camera* camera, int 
         }
         dFrame = s->d_frame;
     }
+    rc = prepare_render(s, width, spp, height, st, nullptr);  // (scratch allocation stays outside the timed window)
+    if (rc != TMPT_OK) return rc;
     CU_TRY(cudaEventRecord(s->ev0, st));
     CU_TRY(cudaMemsetAsync(s->d_rayCount, 0, sizeof(unsigned long long), st));
     rc = launch_render(s, camera, width, height, spp, height, 0, 1, nullptr, dFrame, s->d_rayCount, st);
@@ -1112,6 +1126,77 @@ extern "C" int tmpt_render(const tmpt_scene* cs, const tmpt_camera* camera, int 
     if (rayCount) *rayCount = rays;
     if (seconds) *seconds = (double)ms * 1.0e-3;
     return check_status(s, st);
+}
+
+// One process, several devices: stripes of rank i on scenes[i], pixels stored into device 0's frame by peer access.
+extern "C" int tmpt_render_multi(tmpt_scene* const* scenes, int nScenes, const tmpt_camera* camera, int width, int height, int spp, uint8_t* rgba,
+                                 uint64_t* rayCount, double* seconds) {
+    if (!scenes || nScenes < 1 || nScenes > 64) return tmpt::fail(TMPT_ERR_ARG, "tmpt_render_multi: bad scene list");
+    for (int i = 0; i < nScenes; ++i) {
+        const int rc = check_render_args(scenes[i], camera, width, height, spp);
+        if (rc != TMPT_OK) return rc;
+        for (int j = 0; j < i; ++j)
+            if (scenes[j]->device == scenes[i]->device) return tmpt::fail(TMPT_ERR_ARG, "tmpt_render_multi: two scenes on device %d", scenes[i]->device);
+        if (scenes[i]->triCount != scenes[0]->triCount) return tmpt::fail(TMPT_ERR_ARG, "tmpt_render_multi: scenes are not replicas");
+    }
+    if (!rgba) return tmpt::fail(TMPT_ERR_ARG, "tmpt_render_multi: rgba is NULL");
+    if (nScenes == 1) return tmpt_render(scenes[0], camera, width, height, spp, TMPT_HOST, rgba, rayCount, seconds, nullptr);
+    tmpt_scene* s0 = scenes[0];
+    const size_t bytes = (size_t)width * height * 4;
+    int prev = 0;
+    CU_TRY(cudaGetDevice(&prev));
+    struct Restore { int d; ~Restore() { cudaSetDevice(d); } } restore{prev};
+    // the frame lives on device 0; every other device needs peer access to it
+    CU_TRY(cudaSetDevice(s0->device));
+    if (s0->frameBytes < bytes) {
+        cudaFree(s0->d_frame); s0->d_frame = nullptr; s0->frameBytes = 0;
+        CU_TRY(cudaMalloc((void**)&s0->d_frame, bytes));
+        s0->frameBytes = bytes;
+    }
+    std::vector<unsigned long long*> counters(nScenes);
+    for (int i = 0; i < nScenes; ++i) {
+        CU_TRY(cudaSetDevice(scenes[i]->device));
+        if (i > 0) {
+            int can = 0;
+            CU_TRY(cudaDeviceCanAccessPeer(&can, scenes[i]->device, s0->device));
+            if (!can) return tmpt::fail(TMPT_ERR_CUDA, "tmpt_render_multi: device %d cannot access device %d", scenes[i]->device, s0->device);
+            const cudaError_t e = cudaDeviceEnablePeerAccess(s0->device, 0);
+            if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) CU_TRY(e);
+            cudaGetLastError();
+        }
+        counters[i] = scenes[i]->d_rayCount;
+        CU_TRY(cudaMemsetAsync(counters[i], 0, sizeof(unsigned long long), scenes[i]->stream));
+        const int prc = prepare_render(scenes[i], width, spp, tmpt_stripe_rows(height, 4, i, nScenes), scenes[i]->stream, nullptr);
+        if (prc != TMPT_OK) return prc;
+        CU_TRY(cudaStreamSynchronize(scenes[i]->stream));
+    }
+    // window: from the first launch to the frame in host memory (main.cpp:319-333)
+    CU_TRY(cudaSetDevice(s0->device));
+    CU_TRY(cudaStreamSynchronize(s0->stream));
+    const auto t0 = std::chrono::steady_clock::now();
+    for (int i = 0; i < nScenes; ++i) {
+        CU_TRY(cudaSetDevice(scenes[i]->device));
+        const int rc = launch_render(scenes[i], camera, width, height, spp, 4, i, nScenes, nullptr, s0->d_frame, counters[i], scenes[i]->stream);
+        if (rc != TMPT_OK) return rc;
+    }
+    unsigned long long total = 0;
+    for (int i = nScenes - 1; i >= 0; --i) {  // device 0 last: its stream then copies the completed frame out
+        CU_TRY(cudaSetDevice(scenes[i]->device));
+        unsigned long long rays = 0;
+        CU_TRY(cudaMemcpyAsync(&rays, counters[i], sizeof rays, cudaMemcpyDeviceToHost, scenes[i]->stream));
+        CU_TRY(cudaStreamSynchronize(scenes[i]->stream));
+        total += rays;
+    }
+    CU_TRY(cudaMemcpyAsync(rgba, s0->d_frame, bytes, cudaMemcpyDeviceToHost, s0->stream));
+    CU_TRY(cudaStreamSynchronize(s0->stream));
+    const double sec = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    if (rayCount) *rayCount = total;
+    if (seconds) *seconds = sec;
+    for (int i = 0; i < nScenes; ++i) {
+        const int rc = check_status(scenes[i], scenes[i]->stream);
+        if (rc != TMPT_OK) return rc;
+    }
+    return TMPT_OK;
 }
 
 // ------------------------------------------------------------------------------------------
