@@ -297,7 +297,14 @@ def bench_b200(args, scene, w, h, spp, rank, world, local_rank):
             pass
         sm_count = torch.cuda.get_device_properties(dev).multi_processor_count
         sm_mhz = clk["sm_mhz"] or peaks.get("sm_max_mhz", 1965.0)
-        fp32_peak = sm_count * 128 * 2 * sm_mhz * 1e6 / 1e12  # TFLOP/s at the clock seen under load
+        fp32_peak = sm_count * 128 * 2 * sm_mhz * 1e6 / 1e12  # nominal TFLOP/s at the clock seen under load
+        peak_source = f"{sm_count} SM x 128 lanes x 2 x {sm_mhz:.0f} MHz (median SM clock sampled during the timed region)"
+        try:  # the FFMA rate actually measured on this pool's B200 (tools/microbench/peaks.cu), scaled to the clock seen
+            pk = json.load(open(os.path.join(ROOT, "profiles", "r1_peaks.json")))
+            fp32_peak = pk["ffma_tflops"] * sm_mhz / pk["at_sm_mhz"]
+            peak_source = f"measured FFMA rate {pk['ffma_tflops']} TFLOP/s at {pk['at_sm_mhz']} MHz (profiles/r1_microbench_peaks.txt), scaled to {sm_mhz:.0f} MHz"
+        except (OSError, KeyError, ValueError):
+            pass
         stats = sc.traversal_stats(cam, w, h, spp) if hasattr(sc, "traversal_stats") else None
         flops_per_ray = (stats["box_tests_per_ray"] * 18 + stats["tri_tests_per_ray"] * 46) if stats else None
         kernel_ms = statistics.mean(step_ms)
@@ -313,7 +320,7 @@ def bench_b200(args, scene, w, h, spp, rank, world, local_rank):
             "bound": "fp32_issue (L2-resident traversal; neither hbm nor tensor, SURVEY.md 8(d))",
             "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s", "frac": (achieved / fp32_peak) if achieved else None,
             "traffic": traffic, "per_ray": stats, "flops_per_ray": flops_per_ray,
-            "peak_source": f"{sm_count} SM x 128 lanes x 2 x {sm_mhz:.0f} MHz (median SM clock sampled during the timed region)",
+            "peak_source": peak_source,
             "hbm_context": {"algorithmic_bytes_per_frame": int(tris.size * 4 + w * h * 4), "hbm_peak_gbs_measured": peaks.get("hbm_gbs"),
                             "hbm_frac": (tris.size * 4 + w * h * 4) / (kernel_ms * 1e-3) / 1e9 / peaks["hbm_gbs"] if peaks.get("hbm_gbs") else None},
             "kernel": "k_render", "kernel_ms": kernel_ms,
