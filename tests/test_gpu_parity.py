@@ -504,3 +504,23 @@ def test_render_multi_single_process(scenes):
         for r in reps:
             r.close()
     assert rays == want_rays and (img == want).all() and sec > 0
+
+
+def test_large_random_scene(oracle):
+    """500 k small random triangles (a soup: the worst case for the builder's depth and for the traversal stack):
+    the build succeeds, the tree agrees with the all-triangle scan, nothing overflows."""
+    rng = np.random.default_rng(23)
+    n = 500_000
+    c = rng.uniform(-50, 50, (n, 1, 3))
+    tris = (c + rng.normal(scale=0.4, size=(n, 3, 3))).astype(np.float32).reshape(n, 9)
+    rays = _random_rays({"bounds_min": np.full(3, -50, np.float32), "bounds_max": np.full(3, 50, np.float32)}, 20000, 8)
+    for flags in (tm.BUILD_DEFAULT, tm.BUILD_LBVH):
+        with tm.Scene(tris, flags=flags) as s:
+            info = s.info()
+            a = s.HitScene(rays)
+            b = s.HitScene(rays, mode=tm.HIT_BRUTE)
+            print(f"builder {info['builder']}: {info['node_count']} nodes, depth {info['max_depth']}, build {info['build_ms']:.1f} ms, "
+                  f"{(a[0] >= 0).sum()} of {len(rays)} rays hit")
+            assert info["tri_count"] == n and info["max_depth"] <= 21
+            assert (a[0] == b[0]).all() and (bits(a[1]) == bits(b[1])).all()
+            assert (a[0] >= 0).sum() > 1000

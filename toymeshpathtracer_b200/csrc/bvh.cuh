@@ -41,7 +41,7 @@ constexpr uint32_t LEAF_BIT = 0x80000000u;
 constexpr int MAX_LEAF_TRIS = 8;
 constexpr int WIDTH = 4;
 constexpr int NODE_F4 = 7;              // float4 rows per node (112 bytes)
-constexpr int STACK_SIZE = 48;         // entries; the builder reports the depth it needs
+constexpr int STACK_SIZE = 64;         // entries; the builder reports the depth it needs
 constexpr uint32_t NONE = 0xFFFFFFFFu;     // empty child / empty stack; no leaf ref reaches it (slots < 2^28 - 1)
 constexpr uint32_t STACK_OVERFLOW = 1;  // bit in the scene's device status word
 
