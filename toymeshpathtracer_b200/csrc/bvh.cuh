@@ -160,13 +160,15 @@ TMPT_HD RayCtx make_ray_ctx(ex::V3 o, ex::V3 d) {
 }
 
 // One 4-wide node step: enter the nearest hit child (returned; NONE if no child is hit), push the others.
-TMPT_HD uint32_t wide_node_step(const SceneView& sc, uint32_t node, const RayCtx& r, float tMin, float bestT, unsigned long long* stack, int& sp,
-                                bool& overflow) {
-    const float4* n = sc.nodes + (size_t)node * NODE_F4;
-    const float4 nx = ld_row(n + r.sx), fx = ld_row(n + (r.sx ^ 1u));
-    const float4 ny = ld_row(n + 2 + r.sy), fy = ld_row(n + 2 + (r.sy ^ 1u));
-    const float4 nz = ld_row(n + 4 + r.sz), fz = ld_row(n + 4 + (r.sz ^ 1u));
-    const float4 rf = ld_row(n + 6);
+// The stack cannot overflow: a step pushes at most three entries and descends one level, and scene creation
+// refuses trees deeper than (STACK_SIZE - 4) / 3 levels (kernels.cu).  Rows are addressed with 32-bit row indices
+// (node * 7 + row < 2^32), which keeps the address arithmetic to one IMAD.WIDE per load.
+TMPT_HD uint32_t wide_node_step(const SceneView& sc, uint32_t node, const RayCtx& r, float tMin, float bestT, unsigned long long* stack, int& sp) {
+    const uint32_t row0 = node * (uint32_t)NODE_F4;
+    const float4 nx = ld_row(sc.nodes + (row0 + r.sx)), fx = ld_row(sc.nodes + (row0 + (r.sx ^ 1u)));
+    const float4 ny = ld_row(sc.nodes + (row0 + 2u + r.sy)), fy = ld_row(sc.nodes + (row0 + 2u + (r.sy ^ 1u)));
+    const float4 nz = ld_row(sc.nodes + (row0 + 4u + r.sz)), fz = ld_row(sc.nodes + (row0 + 4u + (r.sz ^ 1u)));
+    const float4 rf = ld_row(sc.nodes + (row0 + 6u));
     uint32_t key[4], ref[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
@@ -183,18 +185,17 @@ TMPT_HD uint32_t wide_node_step(const SceneView& sc, uint32_t node, const RayCtx
     const uint32_t ks = kmin & 3u;
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-        if (key[k] != 0xFFFFFFFFu && (uint32_t)k != ks) {
-            if (sp < STACK_SIZE) stack[sp++] = ((unsigned long long)key[k] << 32) | ref[k];
-            else overflow = true;
-        }
+        const bool push = key[k] != 0xFFFFFFFFu && (uint32_t)k != ks;
+        if (push) stack[sp] = ((unsigned long long)key[k] << 32) | ref[k];
+        sp += push ? 1 : 0;
     }
     return ks == 0 ? ref[0] : ks == 1 ? ref[1] : ks == 2 ? ref[2] : ref[3];
 }
 
 // One exact test of triangle slot `slot`; returns true when `best` improved.
 TMPT_HD bool tri_step(const SceneView& sc, uint32_t slot, ex::V3 o, ex::V3 d, float tMin, float tMax, HitRec& best) {
-    const float4* tp = sc.tris + (size_t)slot * 3;
-    const float4 a = ld_row(tp + 0), b = ld_row(tp + 1), c = ld_row(tp + 2);
+    const uint32_t row0 = slot * 3u;  // 32-bit row index: slot < 2^27
+    const float4 a = ld_row(sc.tris + row0), b = ld_row(sc.tris + (row0 + 1u)), c = ld_row(sc.tris + (row0 + 2u));
     float t, u, v;
     if (mt_exact(o, d, ex::v3(a.x, a.y, a.z), ex::v3(b.x, b.y, b.z), ex::v3(c.x, c.y, c.z), tMin, tMax, t, u, v)) {
         const int id = (int)ex::f2u(a.w);
@@ -232,10 +233,10 @@ TMPT_HD void walk_start(WalkState& w, const SceneView& sc, ex::V3 o, ex::V3 d, f
 // wait (+12 % on the frame, profiles/).  The walk runs at most one leaf ahead of the tests, so
 // almost nothing is visited that a tighter best t would have culled.
 template <bool STATS>
-TMPT_HD bool walk_step(WalkState& w, const SceneView& sc, float tMin, float tMax, unsigned long long* stack, bool& overflow, TravStats* stats) {
+TMPT_HD bool walk_step(WalkState& w, const SceneView& sc, float tMin, float tMax, unsigned long long* stack, TravStats* stats) {
     if (w.cur != NONE && !ref_is_leaf(w.cur)) {
         if (STATS) ++stats->nodes;
-        w.cur = wide_node_step(sc, w.cur, w.r, tMin, w.best.t, stack, w.sp, overflow);
+        w.cur = wide_node_step(sc, w.cur, w.r, tMin, w.best.t, stack, w.sp);
     }
     if (w.cur != NONE && ref_is_leaf(w.cur) && w.triPos == w.triEnd) {  // park the leaf, free the walker
         w.triPos = leaf_first(w.cur);
@@ -266,11 +267,9 @@ TMPT_HD bool walk_step(WalkState& w, const SceneView& sc, float tMin, float tMax
 template <bool ANY, bool STATS = false>
 TMPT_HD HitRec traverse(const SceneView& sc, ex::V3 o, ex::V3 d, float tMin, float tMax, TravStats* stats = nullptr) {
     unsigned long long stack[STACK_SIZE];  // (entry distance bits << 32) | ref
-    bool overflow = false;
     WalkState w;
     walk_start(w, sc, o, d, tMax, ANY);
-    while (!walk_step<STATS>(w, sc, tMin, tMax, stack, overflow, stats)) {}
-    if (overflow && sc.status) *sc.status |= STACK_OVERFLOW;
+    while (!walk_step<STATS>(w, sc, tMin, tMax, stack, stats)) {}
     return w.best;
 }
 

@@ -821,6 +821,10 @@ int build_bvh(tmpt_scene* s, unsigned flags) {
         s->info.sah_cost = rootArea > 0.0f ? (cInner * hs[0] + cTri * hs[1]) / rootArea : 0.0f;
     }
     if ((int)hc[1] != n) return tmpt::fail(TMPT_ERR_CUDA, "BVH build lost triangles: %u slots for %d triangles", hc[1], n);
+    // the traversal stack holds at most 3 entries per level (bvh::wide_node_step): refuse what it could not hold
+    if (3 * s->info.max_depth + 4 > bvh::STACK_SIZE)
+        return tmpt::fail(TMPT_ERR_ARG, "BVH is %d levels deep; the traversal stack (%d entries) supports %d", s->info.max_depth, bvh::STACK_SIZE,
+                          (bvh::STACK_SIZE - 4) / 3);
     s->info.device_bytes = (uint64_t)n * 9 * 4 + (uint64_t)hc[0] * bvh::NODE_F4 * 16 + (uint64_t)n * 48;
     s->view.nodes = s->d_nodes;
     s->view.tris = s->d_tris;
