@@ -72,11 +72,14 @@ TMPT_HD bool mt_exact(ex::V3 o, ex::V3 d, ex::V3 v0, ex::V3 e1, ex::V3 e2, float
     const float Epsilon = 1e-5f;
     ex::V3 pvec = ex::cross(d, e2);
     float det = ex::dot(e1, pvec);
-    if (det > -Epsilon && det < Epsilon) return false;
+    // The determinant test (maths.cpp:350-351) and the u test (:358-359) share ONE exit: the same values in the
+    // same order decide, but v0 is needed before the first branch, so the compiler cannot sink the triangle's
+    // first row below it and turn one memory round trip into two dependent ones.  (A near-zero det -- under
+    // 1 % of the tests -- makes invDet huge or infinite and u garbage; the det clause rejects those.)
     float invDet = ex::rcp(det);
     ex::V3 tvec = ex::sub(o, v0);
     u = ex::mul(ex::dot(tvec, pvec), invDet);
-    if (u < 0.0f || u > 1.0f) return false;
+    if ((det > -Epsilon && det < Epsilon) || u < 0.0f || u > 1.0f) return false;
     ex::V3 qvec = ex::cross(tvec, e1);
     v = ex::mul(ex::dot(d, qvec), invDet);
     if (v < 0.0f || ex::add(u, v) > 1.0f) return false;
@@ -105,10 +108,9 @@ struct TravStats {
     unsigned long long tris = 0;   // exact triangle tests
 };
 
-// 128-bit read-only loads.  On the device they are volatile asm so that the compiler keeps
-// them where they are written: it otherwise SINKS a triangle's v0 row below the determinant
-// test to save a load on the early exit, which turns one L2 round trip per triangle into two
-// dependent ones (ncu source view, profiles/).
+// 128-bit loads through the read-only path (ld.global.nc), spelled as asm so that every row is one
+// LDG.E.128 exactly where it is written as far as the front end is concerned.  (ptxas still schedules
+// them freely -- see mt_exact for how the triangle's three rows are kept together.)
 TMPT_HD float4 ld_row(const float4* p) {
 #ifdef __CUDA_ARCH__
     float4 v;
