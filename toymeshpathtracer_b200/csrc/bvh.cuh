@@ -183,15 +183,17 @@ TMPT_HD uint32_t wide_node_step(const SceneView& sc, uint32_t node, const RayCtx
     }
     const uint32_t k01 = key[0] < key[1] ? key[0] : key[1], k23 = key[2] < key[3] ? key[2] : key[3];
     const uint32_t kmin = k01 < k23 ? k01 : k23;
-    if (kmin == 0xFFFFFFFFu) return NONE;
+    // no early exit for "no child hit": straight-line code keeps the refs row in the same load batch as the boxes
+    // (with a branch here the compiler sinks that load below it: a second, dependent round trip per step)
     const uint32_t ks = kmin & 3u;
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-        const bool push = key[k] != 0xFFFFFFFFu && (uint32_t)k != ks;
+        const bool push = key[k] != 0xFFFFFFFFu && (uint32_t)k != ks;  // (all keys empty -> nothing is pushed)
         if (push) stack[sp] = ((unsigned long long)key[k] << 32) | ref[k];
         sp += push ? 1 : 0;
     }
-    return ks == 0 ? ref[0] : ks == 1 ? ref[1] : ks == 2 ? ref[2] : ref[3];
+    const uint32_t nearest = ks == 0 ? ref[0] : ks == 1 ? ref[1] : ks == 2 ? ref[2] : ref[3];
+    return kmin == 0xFFFFFFFFu ? NONE : nearest;
 }
 
 // One exact test of triangle slot `slot`; returns true when `best` improved.
