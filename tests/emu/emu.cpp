@@ -40,7 +40,7 @@ void* emu_scene_create2(const float* tris9, int n, int builder, float cInner, fl
     s->tris9.assign(tris9, tris9 + (size_t)n * 9);
     s->nodes.assign((size_t)std::max(n, 1) * bvh::NODE_F4, make_float4(0, 0, 0, 0));
     s->tris.assign((size_t)std::max(n, 1) * 3, make_float4(0, 0, 0, 0));
-    s->view = bvh::SceneView{s->nodes.data(), s->tris.data(), s->tris9.data(), n ? 0u : bvh::NONE, n, &s->status};
+    s->view = bvh::SceneView{s->nodes.data(), s->tris.data(), s->tris9.data(), nullptr, n ? 0u : bvh::NONE, n, &s->status};
     if (n == 0) return s;
     // k_prim_bounds
     bld::Box scene{3.0e38f, 3.0e38f, 3.0e38f, -3.0e38f, -3.0e38f, -3.0e38f};

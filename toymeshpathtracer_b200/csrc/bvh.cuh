@@ -22,8 +22,10 @@
 //   tris  : leaf-ordered triangle slots, 3 x float4 each, precomputed Moller-Trumbore form:
 //             [0] v0.xyz, original index (bit-cast int)   [1] e1 = v1-v0   [2] e2 = v2-v0
 //           (e1, e2 are the same correctly rounded differences maths.cpp:343-344 computes)
-//   tris9 : the caller's AoS array, untouched, indexed by ORIGINAL id -- read once per ray
-//           that hits, to form Hit.pos / Hit.normal with the reference's expression.
+//   tris9 : the caller's AoS array, untouched, indexed by ORIGINAL id.
+//   hitdata : per ORIGINAL id, 3 x float4: (v0, n.x) (v1, n.y) (v2, n.z) with n = normalize(e1 x e2) computed once
+//           at build time by the same operations the reference performs per hit (maths.cpp:375) -- read once per
+//           ray that hits, to form Hit.pos / Hit.normal (three aligned loads instead of nine scalar ones).
 // Child boxes are the union of PADDED triangle boxes (build_logic.cuh: pad_for) so that the
 // float slab test below can never cull a triangle the exact test would accept.
 #pragma once
@@ -54,6 +56,7 @@ struct SceneView {
     const float4* nodes;  // NODE_F4 float4 per node
     const float4* tris;   // 3 float4 per slot
     const float* tris9;   // original triangles
+    const float4* hitdata;  // 3 float4 per ORIGINAL triangle: vertices + precomputed normal (may be null: host emulation)
     uint32_t rootRef;     // may itself be a leaf ref for tiny scenes
     int triCount;
     uint32_t* status;     // device status word (STACK_OVERFLOW)
@@ -88,12 +91,21 @@ TMPT_HD bool mt_exact(ex::V3 o, ex::V3 d, ex::V3 v0, ex::V3 e1, ex::V3 e2, float
 }
 
 // Hit.pos / Hit.normal exactly as maths.cpp:374-375 forms them, from the ORIGINAL vertices.
+TMPT_HD ex::V3 tri_normal(ex::V3 v0, ex::V3 v1, ex::V3 v2) { return ex::normalize(ex::cross(ex::sub(v1, v0), ex::sub(v2, v0))); }
 TMPT_HD void hit_payload(const SceneView& sc, int id, float u, float v, ex::V3& pos, ex::V3& normal) {
-    const float* p = sc.tris9 + (size_t)id * 9;
-    ex::V3 v0 = ex::v3(p[0], p[1], p[2]), v1 = ex::v3(p[3], p[4], p[5]), v2 = ex::v3(p[6], p[7], p[8]);
+    ex::V3 v0, v1, v2;
+    if (sc.hitdata) {
+        const float4* h = sc.hitdata + (size_t)id * 3;
+        const float4 a = h[0], b = h[1], c = h[2];
+        v0 = ex::v3(a.x, a.y, a.z); v1 = ex::v3(b.x, b.y, b.z); v2 = ex::v3(c.x, c.y, c.z);
+        normal = ex::v3(a.w, b.w, c.w);
+    } else {
+        const float* p = sc.tris9 + (size_t)id * 9;
+        v0 = ex::v3(p[0], p[1], p[2]); v1 = ex::v3(p[3], p[4], p[5]); v2 = ex::v3(p[6], p[7], p[8]);
+        normal = tri_normal(v0, v1, v2);
+    }
     float w = ex::sub(ex::sub(1.0f, u), v);
     pos = ex::add(ex::add(ex::muls(v0, w), ex::muls(v1, u)), ex::muls(v2, v));
-    normal = ex::normalize(ex::cross(ex::sub(v1, v0), ex::sub(v2, v0)));
 }
 
 // A zero (or denormal) direction component would make idir infinite and b*inf - o*inf a NaN

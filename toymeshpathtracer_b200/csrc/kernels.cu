@@ -79,6 +79,7 @@ struct tmpt_scene {
     float* d_tris9 = nullptr;      // caller's triangles, original order
     float4* d_nodes = nullptr;     // wide nodes
     float4* d_tris = nullptr;      // leaf-ordered MT slots
+    float4* d_hitdata = nullptr;   // per original triangle: vertices + precomputed normal
     uint32_t* d_status = nullptr;  // [0] status bits
     // render scratch
     uint32_t* d_tileCounter = nullptr;
@@ -243,6 +244,18 @@ __global__ void k_refit(bld::BinTree t, bld::SahParams sp) {
         bld::refit_node(t, node, sp);
         node = t.parent[node];
     }
+}
+
+// per original triangle: (v0, n.x) (v1, n.y) (v2, n.z), n = normalize(e1 x e2) exactly as maths.cpp:375 computes it per hit
+__global__ void k_hitdata(const float* __restrict__ tris9, int n, float4* __restrict__ hitdata) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float* p = tris9 + (size_t)i * 9;
+    const ex::V3 v0 = ex::v3(p[0], p[1], p[2]), v1 = ex::v3(p[3], p[4], p[5]), v2 = ex::v3(p[6], p[7], p[8]);
+    const ex::V3 nrm = bvh::tri_normal(v0, v1, v2);
+    hitdata[(size_t)i * 3 + 0] = make_float4(v0.x, v0.y, v0.z, nrm.x);
+    hitdata[(size_t)i * 3 + 1] = make_float4(v1.x, v1.y, v1.z, nrm.y);
+    hitdata[(size_t)i * 3 + 2] = make_float4(v2.x, v2.y, v2.z, nrm.z);
 }
 
 // ---- binned-SAH top-down builder (the default): one CTA per (node, range) task per level ----
@@ -710,6 +723,7 @@ int build_bvh(tmpt_scene* s, unsigned flags) {
     }
     CU_TRY(cudaMalloc((void**)&s->d_nodes, (size_t)n * bvh::NODE_F4 * sizeof(float4)));
     CU_TRY(cudaMalloc((void**)&s->d_tris, (size_t)n * 3 * sizeof(float4)));
+    CU_TRY(cudaMalloc((void**)&s->d_hitdata, (size_t)n * 3 * sizeof(float4)));
 
     uint32_t* const d_bounds = (uint32_t*)bounds.p; uint32_t* const d_primA = (uint32_t*)primA.p; uint32_t* const d_primB = (uint32_t*)primB.p;
     uint32_t* const d_visits = (uint32_t*)visits.p; uint32_t* const d_counters = (uint32_t*)counters.p; uint32_t* const d_qCount = (uint32_t*)qCount.p;
@@ -726,6 +740,7 @@ int build_bvh(tmpt_scene* s, unsigned flags) {
 
     const int B = 256, G = div_up(n, B);
     LAUNCH(k_prim_bounds, G, B, 0, st, s->d_tris9, n, d_bounds);
+    LAUNCH(k_hitdata, G, B, 0, st, s->d_tris9, n, s->d_hitdata);
     bld::BinTree t{n, d_keysA, d_left, d_right, d_parent, d_lo, d_hi, d_first, d_visits};
     bld::SahParams sp{cInner, cTri, maxLeaf};
     const uint32_t* primOrder = d_primA;
@@ -825,10 +840,11 @@ int build_bvh(tmpt_scene* s, unsigned flags) {
     if (3 * s->info.max_depth + 4 > bvh::STACK_SIZE)
         return tmpt::fail(TMPT_ERR_ARG, "BVH is %d levels deep; the traversal stack (%d entries) supports %d", s->info.max_depth, bvh::STACK_SIZE,
                           (bvh::STACK_SIZE - 4) / 3);
-    s->info.device_bytes = (uint64_t)n * 9 * 4 + (uint64_t)hc[0] * bvh::NODE_F4 * 16 + (uint64_t)n * 48;
+    s->info.device_bytes = (uint64_t)n * 9 * 4 + (uint64_t)hc[0] * bvh::NODE_F4 * 16 + (uint64_t)n * 48 + (uint64_t)n * 48;
     s->view.nodes = s->d_nodes;
     s->view.tris = s->d_tris;
     s->view.tris9 = s->d_tris9;
+    s->view.hitdata = s->d_hitdata;
     s->view.rootRef = 0u;
     s->view.triCount = n;
     s->view.status = s->d_status;
@@ -887,7 +903,7 @@ extern "C" int tmpt_scene_create(const float* tris9, int triCount, int device, u
             const int brc = build_bvh(s, flags);
             if (brc != TMPT_OK) return brc;
         } else {
-            s->view = bvh::SceneView{nullptr, nullptr, nullptr, bvh::NONE, 0, s->d_status};
+            s->view = bvh::SceneView{nullptr, nullptr, nullptr, nullptr, bvh::NONE, 0, s->d_status};
         }
         CU_TRY(cudaEventRecord(s->ev1, s->stream));
         CU_TRY(cudaStreamSynchronize(s->stream));
@@ -906,7 +922,7 @@ extern "C" void tmpt_scene_destroy(tmpt_scene* s) {
     if (!s) return;
     DeviceGuard guard(s->device);
     if (s->stream) cudaStreamSynchronize(s->stream);
-    cudaFree(s->d_tris9); cudaFree(s->d_nodes); cudaFree(s->d_tris); cudaFree(s->d_status);
+    cudaFree(s->d_tris9); cudaFree(s->d_nodes); cudaFree(s->d_tris); cudaFree(s->d_hitdata); cudaFree(s->d_status);
     cudaFree(s->d_tileCounter); cudaFree(s->d_rayCount); cudaFree(s->d_fetchCounter); cudaFree(s->d_frame); cudaFree(s->d_accum);
     if (s->ev0) cudaEventDestroy(s->ev0);
     if (s->ev1) cudaEventDestroy(s->ev1);
