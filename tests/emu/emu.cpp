@@ -23,6 +23,7 @@ namespace {
 struct EmuScene {
     std::vector<float> tris9;
     std::vector<float4> nodes, tris;
+    std::vector<uint4> qnodes;
     uint32_t status = 0;
     uint32_t counters[4] = {0, 0, 0, 0};
     float sah[2] = {0, 0};
@@ -166,6 +167,10 @@ void* emu_scene_create2(const float* tris9, int n, int builder, float cInner, fl
             count = next;
         }
     }
+    // k_quantize_nodes
+    s->qnodes.assign((size_t)s->counters[0] * bvh::QNODE_STRIDE, make_uint4(0, 0, 0, 0));
+    for (uint32_t i = 0; i < s->counters[0]; ++i) bld::quantize_node(s->nodes.data(), s->qnodes.data(), i);
+    s->view.qnodes = s->qnodes.data();
     return s;
 }
 void* emu_scene_create(const float* tris9, int n) { return emu_scene_create2(tris9, n, 1, 1.0f, 1.0f, bvh::MAX_LEAF_TRIS); }
@@ -180,6 +185,12 @@ int emu_nodes(void* h, float* out) {
     EmuScene* s = (EmuScene*)h;
     if (out) memcpy(out, s->nodes.data(), (size_t)s->counters[0] * bvh::NODE_F4 * 16);
     return (int)s->counters[0];
+}
+// the quantised nodes, in LOGICAL row order (the bank skew undone): 16 uint32 per node
+void emu_qnodes(void* h, uint32_t* out) {
+    EmuScene* s = (EmuScene*)h;
+    for (uint32_t i = 0; i < s->counters[0]; ++i)
+        for (uint32_t r = 0; r < (uint32_t)bvh::QNODE_ROWS; ++r) memcpy(out + ((size_t)i * bvh::QNODE_ROWS + r) * 4, &s->qnodes[bvh::qnode_row(i, r)], 16);
 }
 void emu_slots(void* h, float* out) {
     EmuScene* s = (EmuScene*)h;

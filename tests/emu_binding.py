@@ -15,19 +15,21 @@ CSRC = os.path.join(os.path.dirname(HERE), "toymeshpathtracer_b200", "csrc")
 CUDA_INC = os.environ.get("CUDA_INC", "/usr/local/cuda/include")
 
 
-def _stale():
-    if not os.path.exists(SO):
+def _stale(so=SO):
+    if not os.path.exists(so):
         return True
-    t = os.path.getmtime(SO)
+    t = os.path.getmtime(so)
     deps = [SRC] + [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".cuh")]
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build():
-    if _stale():
-        subprocess.run(["g++", "-std=c++17", "-O2", "-ffp-contract=off", "-fno-fast-math", "-fopenmp", "-fPIC", "-shared",
-                        "-I" + CUDA_INC, "-o", SO, SRC], check=True)
-    return SO
+def build(defines=(), tag=""):
+    """`defines` / `tag`: a second build of the same logic with compile-time switches (e.g. -DTMPT_QNODES=1 -> libemu_q.so)."""
+    so = SO if not tag else SO.replace("libemu.so", f"libemu_{tag}.so")
+    if _stale(so):
+        subprocess.run(["g++", "-std=c++17", "-O2", "-ffp-contract=off", "-fno-fast-math", "-fopenmp", "-fPIC", "-shared", *defines,
+                        "-I" + CUDA_INC, "-o", so, SRC], check=True)
+    return so
 
 
 def _p(a):
@@ -35,8 +37,8 @@ def _p(a):
 
 
 class Emu:
-    def __init__(self):
-        self.L = C.CDLL(build())
+    def __init__(self, defines=(), tag=""):
+        self.L = C.CDLL(build(defines, tag))
         self.L.emu_scene_create.restype = C.c_void_p
         self.L.emu_scene_create2.restype = C.c_void_p
         self.L.emu_pixel_seed.restype = C.c_uint32
@@ -68,6 +70,13 @@ class EmuScene:
         n = self.L.emu_nodes(self.h, None)
         out = np.zeros((n, 7, 4), np.float32)
         self.L.emu_nodes(self.h, _p(out))
+        return out
+
+    def qnodes(self):
+        """Quantised nodes in logical row order: uint32 [n, 4 rows, 4 words]."""
+        n = self.L.emu_nodes(self.h, None)
+        out = np.zeros((n, 4, 4), np.uint32)
+        self.L.emu_qnodes(self.h, _p(out))
         return out
 
     def slots(self):

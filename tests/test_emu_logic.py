@@ -91,6 +91,72 @@ def test_tree_equals_brute_force_on_random_rays(emu):
     assert (c[0] == d2[0]).all() and (c[1][c[0] >= 0] < tcut).all()
 
 
+# ---- quantised nodes (bvh.cuh: qnode_step, build_logic.cuh: quantize_node; compile-time option TMPT_QNODES) ----
+@pytest.fixture(scope="module")
+def emu_q():
+    return Emu(defines=("-DTMPT_QNODES=1",), tag="q")
+
+
+def _decode_qnodes(q):
+    """-> lo[n,3,4], hi[n,3,4] (float64, exact), refs[n,4] of the 64-byte nodes"""
+    origin = q[:, 0, :3].copy().view(np.float32).astype(np.float64)
+    e = np.stack([(q[:, 0, 3] >> (8 * a)) & 0xFF for a in range(3)], 1).astype(np.int64) - 127 - 15
+    step = np.ldexp(1.0, e)
+    words_lo = np.stack([q[:, 2, 0], q[:, 2, 2], q[:, 3, 0]], 1)
+    words_hi = np.stack([q[:, 2, 1], q[:, 2, 3], q[:, 3, 1]], 1)
+    by = lambda w: np.stack([(w >> (8 * k)) & 0xFF for k in range(4)], 2).astype(np.float64)
+    lo = origin[:, :, None] + by(words_lo) * step[:, :, None]
+    hi = origin[:, :, None] + by(words_hi) * step[:, :, None]
+    return lo, hi, q[:, 1, :], by(words_lo), by(words_hi)
+
+
+@pytest.mark.parametrize("builder", [0, 1], ids=["sah", "lbvh"])
+@pytest.mark.parametrize("name", SCENES)
+def test_quantised_nodes_contain_the_float_boxes(emu_q, name, builder):
+    sc = load_scene(name)
+    s = emu_q.scene(sc["tris"], builder=builder)
+    nodes, q = s.nodes(), s.qnodes()
+    lo, hi, refs, qlo, qhi = _decode_qnodes(q)
+    frefs = nodes[:, 6, :].copy().view(np.uint32)
+    assert (q[:, 3, 2] == 0x3F800000).all()
+    for a in range(3):
+        flo, fhi = nodes[:, 2 * a, :].astype(np.float64), nodes[:, 2 * a + 1, :].astype(np.float64)
+        real = frefs != 0xFFFFFFFF
+        step = (hi[:, a, :] - lo[:, a, :])[real] / np.maximum((qhi - qlo)[:, a, :][real], 1)
+        # contained, with the 1/64-step margin, and tight: within two grid steps of the float box
+        assert (lo[:, a, :][real] <= flo[real] - step / 64 * 0.999).all() and (hi[:, a, :][real] >= fhi[real] + step / 64 * 0.999).all()
+        assert (flo[real] - lo[:, a, :][real] <= 2 * step).all() and (hi[:, a, :][real] - fhi[real] <= 2 * step).all()
+        # empty children: inverted box, harmless reference
+        assert (qlo[:, a, :][~real] == 255).all() and (qhi[:, a, :][~real] == 0).all()
+    assert (refs[frefs != 0xFFFFFFFF] == frefs[frefs != 0xFFFFFFFF]).all() and (refs[frefs == 0xFFFFFFFF] == 0x80000000).all()
+
+
+@pytest.mark.parametrize("name", SCENES)
+def test_quantised_traversal_equals_reference_hits(emu_q, name):
+    sc, g = load_scene(name), load_rays(name)
+    s = emu_q.scene(sc["tris"])
+    ids, t, pos, nrm = s.hit(g["rays"])
+    hit = g["id"] >= 0
+    assert (ids == g["id"]).all() and (bits(t)[hit] == bits(g["t"])[hit]).all()
+    anyid, *_ = s.hit(g["rays"], mode=1)
+    assert ((anyid >= 0) == hit).all()
+
+
+def test_quantised_tree_equals_brute_force(emu_q):
+    sc = load_scene("teapot")
+    s = emu_q.scene(sc["tris"])
+    rng = np.random.default_rng(12)
+    n = 4000
+    o = rng.uniform(sc["bounds_min"] - 1.0, sc["bounds_max"] + 1.0, (n, 3)).astype(np.float32)
+    d = rng.normal(size=(n, 3)); d = (d / np.linalg.norm(d, axis=1, keepdims=True)).astype(np.float32)
+    d[: n // 8, rng.integers(0, 3)] = 0.0
+    d /= np.maximum(np.linalg.norm(d, axis=1, keepdims=True), 1e-20).astype(np.float32)
+    o[n // 2:] *= 50.0  # far origins: large |C| in t = v * A + C
+    rays = np.concatenate([o, d], 1).astype(np.float32)
+    a, b = s.hit(rays, mode=0), s.hit(rays, mode=2)
+    assert (a[0] == b[0]).all() and (bits(a[1]) == bits(b[1])).all()
+
+
 @pytest.mark.parametrize("name,w,h,spp", [("cube", 96, 54, 3), ("suzanne", 64, 36, 2), ("teapot", 32, 18, 1), ("cube", 40, 24, 20)])
 def test_integrator_equals_oracle_pixel_mode(emu, oracle, name, w, h, spp):
     sc = load_scene(name)

@@ -376,4 +376,79 @@ TMPT_HD void emit_single_leaf_root(const BinTree& t, const WideOut& w, int rootN
     accum_add(&w.sahAccum[1], box_half_area(Box{lo.x, lo.y, lo.z, hi.x, hi.y, hi.z}) * (float)cnt);
 }
 
+
+// ---- quantise: float wide node -> 64-byte node (bvh.cuh: qnode_step) ----
+// Per axis: grid step 2^e, the smallest power of two that fits the children's span into the 8-bit range with the margins
+// below; origin = a float at least 1/64 step under the lowest child plane; lo bytes floor(x - 1/64), hi bytes ceil(x + 1/64)
+// in grid units.  The differences are formed in binary64, where they are exact (or wrong by far less than the margin).
+// An empty child keeps its inverted box (lo byte 255, hi byte 0) and refers to triangle slot 0: should rounding in the slab
+// test ever let a ray into it, it tests a real triangle it is allowed to test anyway.
+TMPT_HD float float_below(float x) {  // the next float towards -infinity (finite, non-NaN input)
+    uint32_t u = ex::f2u(x);
+    if ((u & 0x7FFFFFFFu) == 0u) return ex::u2f(0x80000001u);
+    return ex::u2f((u & 0x80000000u) ? u + 1u : u - 1u);
+}
+TMPT_HD double pow2_d(int e) {  // 2^e as a double, |e| < 1000
+    unsigned long long b = (unsigned long long)(e + 1023) << 52;
+    double d;
+#ifdef __CUDA_ARCH__
+    d = __longlong_as_double((long long)b);
+#else
+    memcpy(&d, &b, 8);
+#endif
+    return d;
+}
+TMPT_HD void quantize_node(const float4* nodesF, uint4* qnodes, uint32_t i) {
+    const float4* n = nodesF + (size_t)i * bvh::NODE_F4;
+    uint32_t refs[4];
+    {
+        const float4 rf = n[6];
+        refs[0] = ex::f2u(rf.x); refs[1] = ex::f2u(rf.y); refs[2] = ex::f2u(rf.z); refs[3] = ex::f2u(rf.w);
+    }
+    uint32_t originBits[3], expo[3], loW[3], hiW[3];
+    for (int a = 0; a < 3; ++a) {
+        const float4 lo4 = n[2 * a], hi4 = n[2 * a + 1];
+        const float lo[4] = {lo4.x, lo4.y, lo4.z, lo4.w}, hi[4] = {hi4.x, hi4.y, hi4.z, hi4.w};
+        float mn = 3.0e38f, mx = -3.0e38f;
+        for (int k = 0; k < 4; ++k)
+            if (refs[k] != bvh::NONE) { mn = fminf(mn, lo[k]); mx = fmaxf(mx, hi[k]); }
+        const double ext = (double)mx - (double)mn;
+        // first guess for e: 2^e * 240 >= ext, and not below a quarter ulp of the larger coordinate (the origin is a float)
+        int e = -100;
+        {
+            const float m = fmaxf(fabsf(mn), fabsf(mx));
+            const int ulpExp = (int)((ex::f2u(m) >> 23) & 0xFFu) - 127 - 23 - 2;
+            if (m > 0.0f && ulpExp > e) e = ulpExp;
+            while (e < 100 && pow2_d(e) * 240.0 < ext) ++e;
+        }
+        for (;; ++e) {
+            const double step = pow2_d(e);
+            float origin = (float)((double)mn - 0.5 * step);
+            while ((double)origin > (double)mn - step * (1.0 / 64.0)) origin = float_below(origin);
+            bool fits = true;
+            uint32_t lw = 0, hw = 0;
+            for (int k = 0; k < 4; ++k) {
+                uint32_t ql = 255u, qh = 0u;
+                if (refs[k] != bvh::NONE) {
+                    const double fl = floor(((double)lo[k] - (double)origin) / step - 1.0 / 64.0);
+                    const double ch = ceil(((double)hi[k] - (double)origin) / step + 1.0 / 64.0);
+                    if (fl < 0.0 || ch > 255.0) { fits = false; break; }
+                    ql = (uint32_t)fl; qh = (uint32_t)ch;
+                }
+                lw |= ql << (8 * k); hw |= qh << (8 * k);
+            }
+            if (!fits && e < 120) continue;
+            originBits[a] = ex::f2u(origin); expo[a] = (uint32_t)(e + 15 + 127); loW[a] = lw; hiW[a] = hw;
+            break;
+        }
+    }
+    for (int k = 0; k < 4; ++k)
+        if (refs[k] == bvh::NONE) refs[k] = bvh::make_leaf_ref(0u, 1);
+    uint4* o = qnodes;
+    o[bvh::qnode_row(i, 0)] = make_uint4(originBits[0], originBits[1], originBits[2], expo[0] | (expo[1] << 8) | (expo[2] << 16));
+    o[bvh::qnode_row(i, 1)] = make_uint4(refs[0], refs[1], refs[2], refs[3]);
+    o[bvh::qnode_row(i, 2)] = make_uint4(loW[0], hiW[0], loW[1], hiW[1]);
+    o[bvh::qnode_row(i, 3)] = make_uint4(loW[2], hiW[2], 0x3F800000u, 0u);
+}
+
 }  // namespace bld

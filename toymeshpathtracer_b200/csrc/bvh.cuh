@@ -42,7 +42,8 @@ namespace bvh {
 constexpr uint32_t LEAF_BIT = 0x80000000u;
 constexpr int MAX_LEAF_TRIS = 8;
 constexpr int WIDTH = 4;
-constexpr int NODE_F4 = 7;              // float4 rows per node (112 bytes)
+constexpr int NODE_F4 = 7;              // float4 rows per float node (112 bytes)
+constexpr int QNODE_ROWS = 4;           // 16-byte rows per quantised node (64 bytes)
 constexpr int STACK_SIZE = 64;         // entries; the builder reports the depth it needs
 constexpr uint32_t NONE = 0xFFFFFFFFu;     // empty child / empty stack; no leaf ref reaches it (slots < 2^28 - 1)
 constexpr uint32_t STACK_OVERFLOW = 1;  // bit in the scene's device status word
@@ -60,6 +61,7 @@ struct SceneView {
     uint32_t rootRef;     // may itself be a leaf ref for tiny scenes
     int triCount;
     uint32_t* status;     // device status word (STACK_OVERFLOW)
+    const uint4* qnodes;  // QNODE_ROWS rows per node: the quantised form of `nodes` the walk reads (TMPT_QNODES)
 };
 
 struct HitRec {
@@ -183,24 +185,17 @@ TMPT_HD RayCtx make_ray_ctx(ex::V3 o, ex::V3 d) {
 // i.e. the far and the big boxes, where an occluder is most likely: on the four test scenes this never costs more and
 // saves 12 % of all node + triangle rows on the Sponza stand-in (24 % of the shadow rays' own work); the answer (a
 // boolean) cannot depend on the order.
-TMPT_HD uint32_t wide_node_step(const SceneView& sc, uint32_t node, const RayCtx& r, float tMin, float bestT, unsigned long long* stack, int& sp,
-                                bool anyRay) {
-    const uint32_t row0 = node * (uint32_t)NODE_F4;
-    const float4 nx = ld_row(sc.nodes + (row0 + r.sx)), fx = ld_row(sc.nodes + (row0 + (r.sx ^ 1u)));
-    const float4 ny = ld_row(sc.nodes + (row0 + 2u + r.sy)), fy = ld_row(sc.nodes + (row0 + 2u + (r.sy ^ 1u)));
-    const float4 nz = ld_row(sc.nodes + (row0 + 4u + r.sz)), fz = ld_row(sc.nodes + (row0 + 4u + (r.sz ^ 1u)));
-    const float4 rf = ld_row(sc.nodes + (row0 + 6u));
-    uint32_t key[4], okey[4], ref[4];
+// The part of a node step that follows the four slab tests: a[k] / b[k] = entry / exit distance of child k (already
+// clipped to [tMin, bestT]), ref[k] its reference.
+TMPT_HD uint32_t enter_and_push(const float (&a)[4], const float (&b)[4], const uint32_t (&ref)[4], unsigned long long* stack, int& sp, bool anyRay) {
+    uint32_t key[4], okey[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-        const float a = fmaxf(fmaxf(fmaf_(f4c(nx, k), r.idx, -r.ox), fmaf_(f4c(ny, k), r.idy, -r.oy)), fmaxf(fmaf_(f4c(nz, k), r.idz, -r.oz), tMin));
-        const float b = fminf(fminf(fmaf_(f4c(fx, k), r.idx, -r.ox), fmaf_(f4c(fy, k), r.idy, -r.oy)), fminf(fmaf_(f4c(fz, k), r.idz, -r.oz), bestT));
-        ref[k] = ex::f2u(f4c(rf, k));
         // stack key = entry distance (for the pop-time cull) with the child slot in its two low mantissa bits; clearing those
         // bits only lowers the distance: still conservative.  (An empty child has an inverted box and can never pass a <= b.)
-        key[k] = (a <= b) ? ((ex::f2u(a) & ~3u) | (uint32_t)k) : 0xFFFFFFFFu;
+        key[k] = (a[k] <= b[k]) ? ((ex::f2u(a[k]) & ~3u) | (uint32_t)k) : 0xFFFFFFFFu;
         // order key: smallest wins.  b >= tMin >= 0 for a hit child, so its bit pattern orders like its value.
-        okey[k] = !anyRay ? key[k] : (a <= b) ? (((0x7F800000u - ex::f2u(b)) & ~3u) | (uint32_t)k) : 0xFFFFFFFFu;
+        okey[k] = !anyRay ? key[k] : (a[k] <= b[k]) ? (((0x7F800000u - ex::f2u(b[k])) & ~3u) | (uint32_t)k) : 0xFFFFFFFFu;
     }
     const uint32_t k01 = okey[0] < okey[1] ? okey[0] : okey[1], k23 = okey[2] < okey[3] ? okey[2] : okey[3];
     const uint32_t kmin = k01 < k23 ? k01 : k23;
@@ -215,6 +210,114 @@ TMPT_HD uint32_t wide_node_step(const SceneView& sc, uint32_t node, const RayCtx
     }
     const uint32_t nearest = ks == 0 ? ref[0] : ks == 1 ? ref[1] : ks == 2 ? ref[2] : ref[3];
     return kmin == 0xFFFFFFFFu ? NONE : nearest;
+}
+
+TMPT_HD uint32_t wide_node_step(const SceneView& sc, uint32_t node, const RayCtx& r, float tMin, float bestT, unsigned long long* stack, int& sp,
+                                bool anyRay) {
+    const uint32_t row0 = node * (uint32_t)NODE_F4;
+    const float4 nx = ld_row(sc.nodes + (row0 + r.sx)), fx = ld_row(sc.nodes + (row0 + (r.sx ^ 1u)));
+    const float4 ny = ld_row(sc.nodes + (row0 + 2u + r.sy)), fy = ld_row(sc.nodes + (row0 + 2u + (r.sy ^ 1u)));
+    const float4 nz = ld_row(sc.nodes + (row0 + 4u + r.sz)), fz = ld_row(sc.nodes + (row0 + 4u + (r.sz ^ 1u)));
+    const float4 rf = ld_row(sc.nodes + (row0 + 6u));
+    float a[4], b[4];
+    uint32_t ref[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        a[k] = fmaxf(fmaxf(fmaf_(f4c(nx, k), r.idx, -r.ox), fmaf_(f4c(ny, k), r.idy, -r.oy)), fmaxf(fmaf_(f4c(nz, k), r.idz, -r.oz), tMin));
+        b[k] = fminf(fminf(fmaf_(f4c(fx, k), r.idx, -r.ox), fmaf_(f4c(fy, k), r.idy, -r.oy)), fminf(fmaf_(f4c(fz, k), r.idz, -r.oz), bestT));
+        ref[k] = ex::f2u(f4c(rf, k));
+    }
+    return enter_and_push(a, b, ref, stack, sp, anyRay);
+}
+
+// ---- quantised nodes (TMPT_QNODES, the default): 64 bytes = 4 rows instead of 7 -------------------------------------------
+// The walk is bound by the L1 data stage -- 16-byte rows gathered per ray -- so a node is stored the way
+// Ylitie, Karras & Laine 2017 ("Efficient incoherent ray traversal on GPUs through compressed wide BVHs") store theirs:
+// child planes as 8-bit offsets on a per-node grid, plane = origin + q * 2^e per axis.
+//   row 0: origin.x origin.y origin.z | E.x E.y E.z 0   (E = biased float exponent of 2^(e+15), one byte per axis)
+//   row 1: child refs[4]              (as in the float node; an empty child refers to triangle slot 0 and has an inverted box)
+//   row 2: lo.x[4] hi.x[4] lo.y[4] hi.y[4]   (one byte per child)
+//   row 3: lo.z[4] hi.z[4] 0x3F800000 0
+// lo bytes are rounded down, hi bytes up, each by an extra 1/64 step (build_logic.cuh: quantize_node), so the decoded box
+// contains the float box; the children only grow by up to a 255th of the node's extent per side.
+// Decode: one PRMT drops the byte into the mantissa of 1.0f, v = 1 + q / 32768 (exact), and the plane's ray distance is one
+// FFMA, t = v * A + C, with per-node  A = 2^(e+15) / d  and  C = (origin - o) / d - A.  Forming C cancels at most 128 node
+// extents against each other: an error of 2^-17 of the extent = 0.002 grid steps, inside the 1/64 step margin.
+// The rows of node n sit at n*4 + (r ^ (n>>1 & 3)): with a plain 64-byte stride every lane of a warp would read the same
+// two 16-byte columns of its L1 line (the bank conflict that made 128-byte float nodes slow, see above).
+#ifndef TMPT_QSTRIDE
+#define TMPT_QSTRIDE 4
+#endif
+constexpr int QNODE_STRIDE = TMPT_QSTRIDE;  // rows from one node to the next: 4 (skewed as described) or 5 (80 bytes, one row unused, no skew needed)
+TMPT_HD uint32_t qnode_row(uint32_t node, uint32_t r) {
+    return QNODE_STRIDE == 4 ? ((node << 2) ^ ((node >> 1) & 3u) ^ r) : node * (uint32_t)QNODE_STRIDE + r;
+}
+TMPT_HD uint4 ld_rowu(const uint4* p) {
+#ifdef __CUDA_ARCH__
+    uint4 v;
+    asm volatile("ld.global.nc.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+    return v;
+#else
+    return *p;
+#endif
+}
+// `one` = 0x3F800000 held in a REGISTER: PRMT has a single immediate slot, and with the constant in it the selector
+// would need a register (and a MOV) per use.
+template <int K>
+TMPT_HD float qbyte_f(uint32_t w, uint32_t one) {  // 1 + (byte K of w) / 32768
+#ifdef __CUDA_ARCH__
+    uint32_t d;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(w), "r"(one), "n"(0x7604 | (K << 4)));
+    return __uint_as_float(d);
+#else
+    return ex::u2f(one | (((w >> (8 * K)) & 0xFFu) << 8));
+#endif
+}
+template <int K>
+TMPT_HD void qchild(uint32_t one, uint32_t nxw, uint32_t nyw, uint32_t nzw, uint32_t fxw, uint32_t fyw, uint32_t fzw, float ax, float ay, float az,
+                    float cx, float cy, float cz, float tMin, float bestT, float& a, float& b) {
+    a = fmaxf(fmaxf(fmaf_(qbyte_f<K>(nxw, one), ax, cx), fmaf_(qbyte_f<K>(nyw, one), ay, cy)), fmaxf(fmaf_(qbyte_f<K>(nzw, one), az, cz), tMin));
+    b = fminf(fminf(fmaf_(qbyte_f<K>(fxw, one), ax, cx), fmaf_(qbyte_f<K>(fyw, one), ay, cy)), fminf(fmaf_(qbyte_f<K>(fzw, one), az, cz), bestT));
+}
+TMPT_HD uint32_t qnode_step(const SceneView& sc, uint32_t node, const RayCtx& r, float tMin, float bestT, unsigned long long* stack, int& sp,
+                            bool anyRay) {
+    uint4 h, rf, qa, qb;
+    if (QNODE_STRIDE == 4) {
+        const uint32_t base = (node << 2) ^ ((node >> 1) & 3u);
+        h = ld_rowu(sc.qnodes + base); rf = ld_rowu(sc.qnodes + (base ^ 1u));
+        qa = ld_rowu(sc.qnodes + (base ^ 2u)); qb = ld_rowu(sc.qnodes + (base ^ 3u));
+    } else {
+        const uint4* p = sc.qnodes + node * (uint32_t)QNODE_STRIDE;
+        h = ld_rowu(p); rf = ld_rowu(p + 1); qa = ld_rowu(p + 2); qb = ld_rowu(p + 3);
+    }
+    const float ax = ex::u2f((h.w << 23) & 0x7F800000u) * r.idx, ay = ex::u2f((h.w << 15) & 0x7F800000u) * r.idy,
+                az = ex::u2f((h.w << 7) & 0x7F800000u) * r.idz;
+    const float cx = fmaf_(ex::u2f(h.x), r.idx, -r.ox) - ax, cy = fmaf_(ex::u2f(h.y), r.idy, -r.oy) - ay, cz = fmaf_(ex::u2f(h.z), r.idz, -r.oz) - az;
+    const uint32_t nxw = r.sx ? qa.y : qa.x, fxw = r.sx ? qa.x : qa.y;
+    const uint32_t nyw = r.sy ? qa.w : qa.z, fyw = r.sy ? qa.z : qa.w;
+    const uint32_t nzw = r.sz ? qb.y : qb.x, fzw = r.sz ? qb.x : qb.y;
+    const uint32_t one = qb.z;  // 0x3F800000, stored in the node so that it arrives in a register (see qbyte_f)
+    float a[4], b[4];
+    qchild<0>(one, nxw, nyw, nzw, fxw, fyw, fzw, ax, ay, az, cx, cy, cz, tMin, bestT, a[0], b[0]);
+    qchild<1>(one, nxw, nyw, nzw, fxw, fyw, fzw, ax, ay, az, cx, cy, cz, tMin, bestT, a[1], b[1]);
+    qchild<2>(one, nxw, nyw, nzw, fxw, fyw, fzw, ax, ay, az, cx, cy, cz, tMin, bestT, a[2], b[2]);
+    qchild<3>(one, nxw, nyw, nzw, fxw, fyw, fzw, ax, ay, az, cx, cy, cz, tMin, bestT, a[3], b[3]);
+    const uint32_t ref[4] = {rf.x, rf.y, rf.z, rf.w};
+    return enter_and_push(a, b, ref, stack, sp, anyRay);
+}
+
+#ifndef TMPT_QNODES
+#define TMPT_QNODES 0
+#endif
+#ifndef TMPT_NODE_UNROLL
+#define TMPT_NODE_UNROLL 1
+#endif
+TMPT_HD uint32_t node_step(const SceneView& sc, uint32_t node, const RayCtx& r, float tMin, float bestT, unsigned long long* stack, int& sp, bool anyRay) {
+#if TMPT_QNODES
+    return qnode_step(sc, node, r, tMin, bestT, stack, sp, anyRay);
+#else
+    return wide_node_step(sc, node, r, tMin, bestT, stack, sp, anyRay);
+#endif
 }
 
 // One exact test of triangle slot `slot`; returns true when `best` improved.
@@ -261,8 +364,29 @@ template <bool STATS>
 TMPT_HD bool walk_step(WalkState& w, const SceneView& sc, float tMin, float tMax, unsigned long long* stack, TravStats* stats) {
     if (w.cur != NONE && !ref_is_leaf(w.cur)) {
         if (STATS) ++stats->nodes;
-        w.cur = wide_node_step(sc, w.cur, w.r, tMin, w.best.t, stack, w.sp, w.any);
+        w.cur = node_step(sc, w.cur, w.r, tMin, w.best.t, stack, w.sp, w.any);
     }
+#if TMPT_NODE_UNROLL == 3
+    // (variant: park / pop between the two steps so that more lanes have an inner node for the second one)
+    if (w.cur != NONE && ref_is_leaf(w.cur) && w.triPos == w.triEnd) {
+        w.triPos = leaf_first(w.cur);
+        w.triEnd = w.triPos + (uint32_t)leaf_count(w.cur);
+        w.cur = NONE;
+    }
+    if (w.cur == NONE && w.sp > 0) {
+        const unsigned long long e = stack[--w.sp];
+        if (ex::u2f((uint32_t)(e >> 32)) <= w.best.t) w.cur = (uint32_t)e;
+    }
+#endif
+#if TMPT_NODE_UNROLL >= 2
+    // a ray makes ~2.5 node steps per triangle test: a second node step per iteration (for lanes whose first one entered
+    // another inner node) halves the number of iterations, so the triangle code and the loop control run half as often
+    // and with twice the lanes
+    if (w.cur != NONE && !ref_is_leaf(w.cur)) {
+        if (STATS) ++stats->nodes;
+        w.cur = node_step(sc, w.cur, w.r, tMin, w.best.t, stack, w.sp, w.any);
+    }
+#endif
     if (w.cur != NONE && ref_is_leaf(w.cur) && w.triPos == w.triEnd) {  // park the leaf, free the walker
         w.triPos = leaf_first(w.cur);
         w.triEnd = w.triPos + (uint32_t)leaf_count(w.cur);

@@ -77,7 +77,8 @@ struct tmpt_scene {
     int smCount = 148;
     cudaStream_t stream = nullptr;
     float* d_tris9 = nullptr;      // caller's triangles, original order
-    float4* d_nodes = nullptr;     // wide nodes
+    float4* d_nodes = nullptr;     // wide nodes (float form: builder output, experimental kernels)
+    uint4* d_qnodes = nullptr;     // wide nodes, quantised (what the walk reads)
     float4* d_tris = nullptr;      // leaf-ordered MT slots
     float4* d_hitdata = nullptr;   // per original triangle: vertices + precomputed normal
     uint32_t* d_status = nullptr;  // [0] status bits
@@ -403,6 +404,10 @@ __global__ void k_collapse(bld::BinTree t, bld::WideOut w, const bld::WorkItem* 
     if (i >= *inCount) return;
     bld::collapse_node(t, w, inQueue[i], outQueue, outCount);
 }
+__global__ void k_quantize_nodes(const float4* __restrict__ nodesF, uint4* __restrict__ qnodes, uint32_t count) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < count) bld::quantize_node(nodesF, qnodes, i);
+}
 __global__ void k_collapse_root_leaf(bld::BinTree t, bld::WideOut w, int rootNode) { bld::emit_single_leaf_root(t, w, rootNode); }
 
 // ------------------------------------------------------------------------------------------
@@ -623,6 +628,7 @@ struct RenderParams {
     uchar4* frame;       // full frame (possibly peer memory)
     unsigned long long* rayCount;
     uint32_t* tileCounter;
+    unsigned long long* laneCounter;  // k_render_regen: next lane item
     unsigned long long* stats;  // instrumented pass only
 };
 
@@ -659,6 +665,131 @@ __global__ void __launch_bounds__(THREADS, MINB) k_render(const RenderParams p) 
     }
     if (STATS) flush_stats(p.stats, rays, ts, 0);
     for (int o = 16; o > 0; o >>= 1) rays += __shfl_xor_sync(0xffffffffu, rays, o);
+    if (lane == 0 && rays) atomicAdd(p.rayCount, rays);
+}
+
+// K4': the same frame with per-lane RAY REGENERATION.  In k_render a warp's lanes trace their rays in lockstep: a lane whose
+// ray ends early idles until the warp's longest ray is done (about half of all lane slots of the walk).  Here every lane
+// is a small state machine over its own path -- closest-hit walk -> shade -> shadow walk -> next bounce ... -> next sample
+// -> next work item -- and the warp's loop body is ONE walk step for whichever ray each lane currently has.  The
+// transitions between rays (payload + scatter, unwind + next camera ray, work fetch) are divergent by nature, so they are
+// GATED: lanes that finished a ray wait until TA of them (TB for the rarer end-of-path work) can make the transition
+// together, or until nobody in the warp is walking.  The per-lane arithmetic and its order are those of
+// integ::render_chunk, so the frame is byte-identical to k_render's (tests/test_gpu_parity.py).
+// Work item = one (pixel, chunk) per LANE from a global counter; consecutive items are the pixels of one 8x4 tile.
+enum : int { ST_WALK = 0, ST_HIT = 1, ST_SHADOW_DONE = 2, ST_PATH_END = 3, ST_NEED_ITEM = 4, ST_IDLE = 5 };
+
+template <bool STATS, int THREADS, int MINB, int TA, int TB>
+__global__ void __launch_bounds__(THREADS, MINB) k_render_regen(const RenderParams p) {
+    constexpr unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    unsigned long long stack[bvh::STACK_SIZE];
+    float kk[integ::kMaxDepth];
+    bvh::WalkState w;
+    bvh::TravStats ts;
+    w.any = false; w.best.id = -1;
+    unsigned long long rays = 0;
+    int state = ST_NEED_ITEM;
+    bool exhausted = false;
+    uint32_t rng = 0;
+    int depth = 0, s = 0, sEnd = 0, x = 0, y = 0, rb = 0, chunk = 0;
+    ex::V3 sum = ex::v3(0.0f, 0.0f, 0.0f), nd = ex::v3(0.0f, 0.0f, 0.0f);
+    float sunk = 0.0f;
+    const float invW = ex::divf(1.0f, (float)p.width), invH = ex::divf(1.0f, (float)p.height);
+    const unsigned long long totalItems = (unsigned long long)p.numTiles * (unsigned long long)p.chunks * 32ull;
+    for (;;) {
+        const unsigned notWalking = __ballot_sync(FULL, state != ST_WALK);
+        if (notWalking) {
+            bool newRay = false, newAny = false;
+            ex::V3 no = ex::v3(0.0f, 0.0f, 0.0f), ndir = no;
+            // ---- A: a closest-hit walk found a hit (payload, sun term, scatter, shadow ray) or a shadow walk ended (next bounce)
+            const unsigned adv = __ballot_sync(FULL, state == ST_HIT || state == ST_SHADOW_DONE);
+            if (adv && (__popc(adv) >= TA || notWalking == FULL)) {
+                if (state == ST_HIT) {
+                    ex::V3 pos, normal;
+                    bvh::hit_payload(p.sc, w.best.id, w.best.u, w.best.v, pos, normal);
+                    sunk = integ::sun_term(normal, w.d, p.lightDir);
+                    nd = integ::scatter_dir(pos, normal, rng);  // drawn before the shadow walk: that walk draws nothing
+                    no = pos; ndir = p.lightDir; newRay = true; newAny = true;
+                } else if (state == ST_SHADOW_DONE) {
+                    kk[depth] = w.best.id < 0 ? sunk : 0.0f;
+                    ++depth;
+                    if (depth < integ::kMaxDepth) { no = w.o; ndir = nd; newRay = true; newAny = false; }
+                    else state = ST_PATH_END;  // w.any stays true: "ended by depth", colour starts at 0
+                }
+            }
+            // ---- B: end of a path (unwind, add the sample), next camera ray or next work item
+            const unsigned endp = __ballot_sync(FULL, state == ST_PATH_END || state == ST_NEED_ITEM);
+            const unsigned busy = __ballot_sync(FULL, state == ST_WALK || newRay);
+            if (endp && (__popc(endp) >= TB || busy == 0)) {
+                if (state == ST_PATH_END) {
+                    ex::V3 color = w.any ? ex::v3(0.0f, 0.0f, 0.0f) : integ::sky(w.d);
+                    for (int i = depth - 1; i >= 0; --i) color = integ::unwind_step(kk[i], color);
+                    sum = ex::add(sum, color);
+                    if (++s == sEnd) {
+                        if (p.chunks > 1) {
+                            p.accum[((size_t)rb * p.width + x) * p.chunks + chunk] = make_float4(sum.x, sum.y, sum.z, 0.0f);
+                        } else {
+                            const uchar4 px = integ::resolve_pixel(sum, ex::divf(1.0f, (float)p.spp));
+                            if (p.frame) p.frame[(size_t)y * p.width + x] = px;
+                            else p.outStripes[(size_t)(p.bandRow0 + rb) * p.width + x] = px;
+                        }
+                        state = ST_NEED_ITEM;
+                    }
+                }
+                const unsigned want = __ballot_sync(FULL, state == ST_NEED_ITEM);
+                if (want) {
+                    if (exhausted) {
+                        if (state == ST_NEED_ITEM) state = ST_IDLE;
+                    } else {
+                        const int cnt = __popc(want);
+                        unsigned long long base = 0;
+                        if (lane == 0) base = atomicAdd(p.laneCounter, (unsigned long long)cnt);
+                        base = __shfl_sync(FULL, base, 0);
+                        exhausted = base + (unsigned long long)cnt >= totalItems;
+                        if (state == ST_NEED_ITEM) {
+                            const unsigned long long item = base + (unsigned long long)__popc(want & ((1u << lane) - 1u));
+                            if (item >= totalItems) {
+                                state = ST_IDLE;
+                            } else {
+                                const uint32_t wi = (uint32_t)(item >> 5), li = (uint32_t)item & 31u;
+                                chunk = (int)(wi / (uint32_t)p.numTiles);
+                                const uint32_t tile = wi - (uint32_t)chunk * (uint32_t)p.numTiles;
+                                const int tx = (int)(tile % (uint32_t)p.tilesX), ty = (int)(tile / (uint32_t)p.tilesX);
+                                x = tx * 8 + (int)(li & 7u); rb = ty * 4 + (int)(li >> 3);
+                                const int r = p.bandRow0 + rb;
+                                if (x < p.width && r < p.ownedRows) {  // (an item outside the frame is simply dropped: the lane asks again)
+                                    y = owned_row_to_global(r, p.stripeRows, p.rank, p.world);
+                                    rng = ex::pixel_seed((uint32_t)chunk * ((uint32_t)p.width * (uint32_t)p.height) + (uint32_t)y * (uint32_t)p.width + (uint32_t)x);
+                                    s = chunk * integ::kChunkSamples;
+                                    sEnd = s + integ::kChunkSamples < p.spp ? s + integ::kChunkSamples : p.spp;
+                                    sum = ex::v3(0.0f, 0.0f, 0.0f);
+                                    state = ST_PATH_END;  // marks "has an item, needs a camera ray" for the block below
+                                    depth = -1;
+                                }
+                            }
+                        }
+                    }
+                }
+                if (state == ST_PATH_END) {  // next sample of the item
+                    integ::primary_ray(p.cam, x, y, invW, invH, rng, no, ndir);
+                    depth = 0; newRay = true; newAny = false;
+                }
+            }
+            if (newRay) {
+                ++rays;
+                bvh::walk_start(w, p.sc, no, ndir, integ::kMaxT, newAny);
+                state = ST_WALK;
+            }
+            if (__all_sync(FULL, state == ST_IDLE)) break;
+        }
+        if (state == ST_WALK) {
+            if (bvh::walk_step<STATS>(w, p.sc, integ::kMinT, integ::kMaxT, stack, &ts))
+                state = w.any ? ST_SHADOW_DONE : w.best.id < 0 ? ST_PATH_END : ST_HIT;
+        }
+    }
+    if (STATS) flush_stats(p.stats, rays, ts, 0);
+    for (int o = 16; o > 0; o >>= 1) rays += __shfl_xor_sync(FULL, rays, o);
     if (lane == 0 && rays) atomicAdd(p.rayCount, rays);
 }
 
@@ -836,12 +967,15 @@ int build_bvh(tmpt_scene* s, unsigned flags) {
         s->info.sah_cost = rootArea > 0.0f ? (cInner * hs[0] + cTri * hs[1]) / rootArea : 0.0f;
     }
     if ((int)hc[1] != n) return tmpt::fail(TMPT_ERR_CUDA, "BVH build lost triangles: %u slots for %d triangles", hc[1], n);
+    CU_TRY(cudaMalloc((void**)&s->d_qnodes, ((size_t)hc[0] * bvh::QNODE_STRIDE) * sizeof(uint4)));
+    LAUNCH(k_quantize_nodes, div_up((int)hc[0], 128), 128, 0, st, s->d_nodes, s->d_qnodes, hc[0]);
     // the traversal stack holds at most 3 entries per level (bvh::wide_node_step): refuse what it could not hold
     if (3 * s->info.max_depth + 4 > bvh::STACK_SIZE)
         return tmpt::fail(TMPT_ERR_ARG, "BVH is %d levels deep; the traversal stack (%d entries) supports %d", s->info.max_depth, bvh::STACK_SIZE,
                           (bvh::STACK_SIZE - 4) / 3);
-    s->info.device_bytes = (uint64_t)n * 9 * 4 + (uint64_t)hc[0] * bvh::NODE_F4 * 16 + (uint64_t)n * 48 + (uint64_t)n * 48;
+    s->info.device_bytes = (uint64_t)n * 9 * 4 + (uint64_t)hc[0] * (bvh::NODE_F4 + bvh::QNODE_ROWS) * 16 + (uint64_t)n * 48 + (uint64_t)n * 48;
     s->view.nodes = s->d_nodes;
+    s->view.qnodes = s->d_qnodes;
     s->view.tris = s->d_tris;
     s->view.tris9 = s->d_tris9;
     s->view.hitdata = s->d_hitdata;
@@ -922,7 +1056,7 @@ extern "C" void tmpt_scene_destroy(tmpt_scene* s) {
     if (!s) return;
     DeviceGuard guard(s->device);
     if (s->stream) cudaStreamSynchronize(s->stream);
-    cudaFree(s->d_tris9); cudaFree(s->d_nodes); cudaFree(s->d_tris); cudaFree(s->d_hitdata); cudaFree(s->d_status);
+    cudaFree(s->d_tris9); cudaFree(s->d_nodes); cudaFree(s->d_qnodes); cudaFree(s->d_tris); cudaFree(s->d_hitdata); cudaFree(s->d_status);
     cudaFree(s->d_tileCounter); cudaFree(s->d_rayCount); cudaFree(s->d_fetchCounter); cudaFree(s->d_frame); cudaFree(s->d_accum);
     if (s->ev0) cudaEventDestroy(s->ev0);
     if (s->ev1) cudaEventDestroy(s->ev1);
@@ -1064,6 +1198,7 @@ static int launch_render(const tmpt_scene* cs, const tmpt_camera* camera, int wi
     p.frame = (uchar4*)frame;
     p.rayCount = rayCountDev;
     p.tileCounter = s->d_tileCounter;
+    p.laneCounter = s->d_fetchCounter;
     p.stats = statsDev;
     p.accum = nullptr;
     if (p.ownedRows == 0) return TMPT_OK;
@@ -1082,7 +1217,21 @@ static int launch_render(const tmpt_scene* cs, const tmpt_camera* camera, int wi
         if (items >= 0xFFFFFFFFll) return tmpt::fail(TMPT_ERR_ARG, "render: too many work items in one band");
         CU_TRY(cudaMemsetAsync(s->d_tileCounter, 0, sizeof(uint32_t), st));
         const int grid = (int)std::min<long long>((long long)s->smCount * std::max(perSM, 1), (items + 7) / 8);
-        if (statsDev) LAUNCH((k_render<true, 256, 4>), grid, 256, 0, st, p);
+        // TMPT_RENDER_KERNEL: 0 = lockstep lanes (k_render), 1.. = per-lane ray regeneration with gate sizes (TA, TB)
+        static const int rk = getenv("TMPT_RENDER_KERNEL") ? atoi(getenv("TMPT_RENDER_KERNEL")) : 0;
+        if (rk > 0 && !statsDev) {
+            CU_TRY(cudaMemsetAsync(s->d_fetchCounter, 0, sizeof(unsigned long long), st));
+            int perSMr = 0;
+#define REGEN_CASE(V, TA, TB)                                                                                        \
+            if (rk == V) {                                                                                           \
+                CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSMr, k_render_regen<false, 256, 4, TA, TB>, 256, 0)); \
+                const int gridR = (int)std::min<long long>((long long)s->smCount * std::max(perSMr, 1), (items * 32 + 255) / 256); \
+                LAUNCH((k_render_regen<false, 256, 4, TA, TB>), gridR, 256, 0, st, p);                                 \
+            } else
+            REGEN_CASE(1, 8, 4) REGEN_CASE(2, 4, 2) REGEN_CASE(3, 12, 6) REGEN_CASE(4, 16, 4)
+#undef REGEN_CASE
+            return tmpt::fail(TMPT_ERR_ARG, "TMPT_RENDER_KERNEL=%d: no such render kernel", rk);
+        } else if (statsDev) LAUNCH((k_render<true, 256, 4>), grid, 256, 0, st, p);
         else LAUNCH((k_render<false, 256, 4>), grid, 256, 0, st, p);
         if (p.chunks > 1) LAUNCH(k_resolve, div_up((long long)rowsHere * width, 256), 256, 0, st, p, rowsHere);
     }
