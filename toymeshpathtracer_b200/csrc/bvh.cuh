@@ -309,9 +309,7 @@ TMPT_HD uint32_t qnode_step(const SceneView& sc, uint32_t node, const RayCtx& r,
 #ifndef TMPT_QNODES
 #define TMPT_QNODES 0
 #endif
-#ifndef TMPT_NODE_UNROLL
-#define TMPT_NODE_UNROLL 1
-#endif
+
 TMPT_HD uint32_t node_step(const SceneView& sc, uint32_t node, const RayCtx& r, float tMin, float bestT, unsigned long long* stack, int& sp, bool anyRay) {
 #if TMPT_QNODES
     return qnode_step(sc, node, r, tMin, bestT, stack, sp, anyRay);
@@ -366,27 +364,6 @@ TMPT_HD bool walk_step(WalkState& w, const SceneView& sc, float tMin, float tMax
         if (STATS) ++stats->nodes;
         w.cur = node_step(sc, w.cur, w.r, tMin, w.best.t, stack, w.sp, w.any);
     }
-#if TMPT_NODE_UNROLL == 3
-    // (variant: park / pop between the two steps so that more lanes have an inner node for the second one)
-    if (w.cur != NONE && ref_is_leaf(w.cur) && w.triPos == w.triEnd) {
-        w.triPos = leaf_first(w.cur);
-        w.triEnd = w.triPos + (uint32_t)leaf_count(w.cur);
-        w.cur = NONE;
-    }
-    if (w.cur == NONE && w.sp > 0) {
-        const unsigned long long e = stack[--w.sp];
-        if (ex::u2f((uint32_t)(e >> 32)) <= w.best.t) w.cur = (uint32_t)e;
-    }
-#endif
-#if TMPT_NODE_UNROLL >= 2
-    // a ray makes ~2.5 node steps per triangle test: a second node step per iteration (for lanes whose first one entered
-    // another inner node) halves the number of iterations, so the triangle code and the loop control run half as often
-    // and with twice the lanes
-    if (w.cur != NONE && !ref_is_leaf(w.cur)) {
-        if (STATS) ++stats->nodes;
-        w.cur = node_step(sc, w.cur, w.r, tMin, w.best.t, stack, w.sp, w.any);
-    }
-#endif
     if (w.cur != NONE && ref_is_leaf(w.cur) && w.triPos == w.triEnd) {  // park the leaf, free the walker
         w.triPos = leaf_first(w.cur);
         w.triEnd = w.triPos + (uint32_t)leaf_count(w.cur);
