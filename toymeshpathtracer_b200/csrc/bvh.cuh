@@ -31,6 +31,7 @@
 #pragma once
 #include "exact.cuh"
 
+
 #ifdef __CUDA_ARCH__
 #define TMPT_LDG4(p) __ldg(p)
 #else
@@ -208,7 +209,9 @@ TMPT_HD uint32_t enter_and_push(const float (&a)[4], const float (&b)[4], const 
         if (push) stack[sp] = ((unsigned long long)key[k] << 32) | ref[k];
         sp += push ? 1 : 0;
     }
-    const uint32_t nearest = ks == 0 ? ref[0] : ks == 1 ? ref[1] : ks == 2 ? ref[2] : ref[3];
+    // a two-level select: the chain "ks == 0 ? .. : ks == 1 ? .." compiled to branches and a reconvergence point (+2.2 %)
+    const uint32_t r01 = (ks & 1u) ? ref[1] : ref[0], r23 = (ks & 1u) ? ref[3] : ref[2];
+    const uint32_t nearest = (ks & 2u) ? r23 : r01;
     return kmin == 0xFFFFFFFFu ? NONE : nearest;
 }
 
@@ -378,16 +381,14 @@ TMPT_HD bool walk_step(WalkState& w, const SceneView& sc, float tMin, float tMax
         if (STATS) ++stats->tris;
         if (tri_step(sc, w.triPos++, w.o, w.d, tMin, tMax, w.best) && w.any) return true;
     }
-    // pop: skip entries that the shrinking best.t has already culled
+    // pop ONE entry per iteration.  If the shrinking best.t has culled it the lane sits out the next node step and pops again
+    // behind the next prefetch.  (A loop here that pops until something survives ran in 75 % of the iterations for a single
+    // lane, with its local-memory latency exposed to the whole warp: +3.3 % without it.)
     if (popping) {
         --w.sp;
         if (ex::u2f((uint32_t)(top >> 32)) <= w.best.t) w.cur = (uint32_t)top;
     }
-    while (w.cur == NONE && w.sp > 0) {
-        const unsigned long long e = stack[--w.sp];
-        if (ex::u2f((uint32_t)(e >> 32)) <= w.best.t) w.cur = (uint32_t)e;
-    }
-    return w.cur == NONE && w.triPos == w.triEnd;
+    return w.cur == NONE && w.triPos == w.triEnd && w.sp == 0;
 }
 
 template <bool ANY, bool STATS = false>
