@@ -374,9 +374,9 @@ static void render_row(render_job* j, int y, int64_t* rayCount) { /* main.cpp:20
     for (int x = 0; x < j->w; ++x) {
         v3 col = V(0.0f, 0.0f, 0.0f);
         /* ORC_RNG_ROW: one chunk holding every sample, the row's stream flowing on (the reference).
-         * ORC_RNG_PIXEL: chunks of ORC_CHUNK_SAMPLES samples, each with its own stream seeded from
+         * ORC_RNG_PIXEL: chunks of ORC_CHUNK_SAMPLES(spp) samples, each with its own stream seeded from
          * (chunk, pixel); chunk sums are added in chunk order (DESIGN.md "RNG"). */
-        const int chunkLen = j->rngMode == ORC_RNG_PIXEL ? ORC_CHUNK_SAMPLES : j->spp;
+        const int chunkLen = j->rngMode == ORC_RNG_PIXEL ? ORC_CHUNK_SAMPLES(j->spp) : j->spp;
         for (int s0 = 0, c = 0; s0 < j->spp; s0 += chunkLen, ++c) {
             if (j->rngMode == ORC_RNG_PIXEL)
                 rng = orc_pixel_seed((uint32_t)c * ((uint32_t)j->w * (uint32_t)j->h) + (uint32_t)y * (uint32_t)j->w + (uint32_t)x);

@@ -106,10 +106,16 @@ TMPT_HD ex::V3 trace_path(const Scene& sc, const Camera& cam, ex::V3 o, ex::V3 d
 
 // The unit of parallel work: one CHUNK of a pixel's samples.  A chunk owns an XorShift32 stream
 // seeded from (chunk, pixel) and adds its samples in order; a pixel is the in-order sum of its
-// chunk sums (DESIGN.md "RNG").  With spp <= kChunkSamples there is one chunk per pixel and the
-// result equals a single per-pixel stream.
-constexpr int kChunkSamples = 8;
-TMPT_HD int chunk_count(int spp) { return (spp + kChunkSamples - 1) / kChunkSamples; }
+// chunk sums (DESIGN.md "RNG").  The chunk length depends on spp only -- spp/8 clamped to
+// [1, 8] -- so a frame does not depend on how it is split over lanes or GPUs: 8 samples at the
+// headline 64 spp and above, ONE sample at 4 spp, where a 640x360 frame would otherwise have
+// 1.5 work items per resident warp (and 0.2 per warp on each of 8 GPUs).
+constexpr int kMaxChunkSamples = 8;
+TMPT_HD int chunk_len(int spp) {
+    const int c = spp / 8;
+    return c < 1 ? 1 : c > kMaxChunkSamples ? kMaxChunkSamples : c;
+}
+TMPT_HD int chunk_count(int spp) { const int c = chunk_len(spp); return (spp + c - 1) / c; }
 
 template <bool STATS = false, class Scene>
 TMPT_HD ex::V3 render_chunk(const Scene& sc, const Camera& cam, int x, int y, int chunk, int width, int height, int spp, ex::V3 lightDir,
@@ -117,7 +123,7 @@ TMPT_HD ex::V3 render_chunk(const Scene& sc, const Camera& cam, int x, int y, in
     const float invW = ex::divf(1.0f, (float)width), invH = ex::divf(1.0f, (float)height);
     uint32_t rng = ex::pixel_seed((uint32_t)chunk * ((uint32_t)width * (uint32_t)height) + (uint32_t)y * (uint32_t)width + (uint32_t)x);
     ex::V3 sum = ex::v3(0.0f, 0.0f, 0.0f);
-    const int s0 = chunk * kChunkSamples, s1 = s0 + kChunkSamples < spp ? s0 + kChunkSamples : spp;
+    const int len = chunk_len(spp), s0 = chunk * len, s1 = s0 + len < spp ? s0 + len : spp;
     for (int s = s0; s < s1; ++s) {
         ex::V3 o, d;
         primary_ray(cam, x, y, invW, invH, rng, o, d);

@@ -761,8 +761,9 @@ __global__ void __launch_bounds__(THREADS, MINB) k_render_regen(const RenderPara
                                 if (x < p.width && r < p.ownedRows) {  // (an item outside the frame is simply dropped: the lane asks again)
                                     y = owned_row_to_global(r, p.stripeRows, p.rank, p.world);
                                     rng = ex::pixel_seed((uint32_t)chunk * ((uint32_t)p.width * (uint32_t)p.height) + (uint32_t)y * (uint32_t)p.width + (uint32_t)x);
-                                    s = chunk * integ::kChunkSamples;
-                                    sEnd = s + integ::kChunkSamples < p.spp ? s + integ::kChunkSamples : p.spp;
+                                    const int len = integ::chunk_len(p.spp);
+                                    s = chunk * len;
+                                    sEnd = s + len < p.spp ? s + len : p.spp;
                                     sum = ex::v3(0.0f, 0.0f, 0.0f);
                                     state = ST_PATH_END;  // marks "has an item, needs a camera ray" for the block below
                                     depth = -1;
