@@ -310,7 +310,7 @@ def bench_b200(args, scene, w, h, spp, rank, world, local_rank):
         kernel_ms = statistics.mean(step_ms)
         traffic = None
         try:  # dram__bytes_read + dram__bytes_write of this kernel on this workload, from the committed ncu capture
-            tj = json.load(open(os.path.join(ROOT, "profiles", "r1b_traffic.json")))["k_render"]
+            tj = json.load(open(os.path.join(ROOT, "profiles", "r1f_traffic.json")))["k_render"]
             if args.workload == "sponza_1080p_64spp" and world == 1:
                 traffic = tj["dram_bytes_read"] + tj["dram_bytes_write"]
         except (OSError, KeyError, ValueError):
@@ -339,7 +339,7 @@ def bench_b200(args, scene, w, h, spp, rank, world, local_rank):
             "config": {"workload": f"{scene_label(scene)} {w}x{h} {spp}spp", "rays_per_frame": step_rays[-1] if world == 1 else tot_rays // args.steps,
                        "parallelism": "single GPU" if world == 1 else f"row stripes of {multigpu.DEFAULT_STRIPE_ROWS} over {world} GPUs, BVH replica per GPU, " + (
                            "pixels stored straight into rank 0's frame over NVLink (CUDA IPC peer memory)" if peer else "frame gathered to rank 0 (NCCL)"),
-                       "work_unit": "8x4 pixel tile x chunk of 8 samples per warp, dynamic fetch",
+                       "work_unit": "8x4 pixel tile x chunk of spp/8 (1..8) samples per warp, dynamic fetch",
                        "l2": "flushed between timed iterations (256 MB write)", "bvh": {k: info[k] for k in ("node_count", "leaf_count", "max_depth", "sah_cost", "build_ms", "device_bytes")},
                        "scene_build_wall_ms": build_wall_ms},
             "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": 88, "d2h_bytes_per_step": w * h * 4 + 8,
