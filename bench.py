@@ -114,13 +114,50 @@ def run_reference_cpu(scene: str, w: int, h: int, spp: int):
 # clocks sampling during the timed region
 # ------------------------------------------------------------------------------------------
 class ClockSampler:
+    """SM clock, throttle reasons and power of one GPU, sampled while the timed region runs: NVML from a thread every
+    5 ms (an 8-GPU frame takes 60 ms: an nvidia-smi child process does not deliver a sample that fast), nvidia-smi -lms
+    as the fallback when NVML is unavailable."""
     Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap,power.draw"
 
     def __init__(self, gpu_index: int):
         self.samples, self.proc, self.thread, self.idx = [], None, None, gpu_index
+        self.stop = threading.Event()
+        self.nvml = None
+
+    def _nvml_loop(self):
+        nv, h = self.nvml
+        bits = []
+        for name, label in (("nvmlClocksEventReasonHwSlowdown", "hw_slowdown"), ("nvmlClocksEventReasonHwThermalSlowdown", "hw_thermal_slowdown"),
+                            ("nvmlClocksEventReasonSwThermalSlowdown", "sw_thermal_slowdown"), ("nvmlClocksEventReasonSwPowerCap", "sw_power_cap")):
+            bit = getattr(nv, name, None) or getattr(nv, name.replace("ClocksEventReason", "ClocksThrottleReason"), None)
+            bits.append((bit, label))
+        reasons_fn = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or getattr(nv, "nvmlDeviceGetCurrentClocksThrottleReasons")
+        try:
+            mx = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+        except Exception:
+            mx = None
+        while not self.stop.is_set():
+            try:
+                sm = nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
+                r = reasons_fn(h)
+                pw = nv.nvmlDeviceGetPowerUsage(h) / 1000.0
+                flags = ["Active" if (bit and (r & bit)) else "Not Active" for bit, _ in bits]
+                self.samples.append([str(sm), str(mx) if mx else "", *flags, "%.2f" % pw])
+            except Exception:
+                pass
+            self.stop.wait(0.005)
 
     def __enter__(self):
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            self.nvml = (nv, nv.nvmlDeviceGetHandleByIndex(self.idx))
+            self.thread = threading.Thread(target=self._nvml_loop, daemon=True)
+            self.thread.start()
+            return self
+        except Exception:
+            self.nvml = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
@@ -135,6 +172,9 @@ class ClockSampler:
             self.samples.append([x.strip() for x in line.split(",")])
 
     def __exit__(self, *exc):
+        self.stop.set()
+        if self.nvml and self.thread:
+            self.thread.join(1.0)
         if self.proc:
             self.proc.terminate()
             try:
@@ -149,7 +189,7 @@ class ClockSampler:
         reasons = sorted({names[k] for s in self.samples if len(s) >= 6 for k in range(4) if s[2 + k].lower().startswith("active")})
         pw = [float(s[6]) for s in self.samples if len(s) > 6 and re.match(r"^[0-9.]+$", s[6])]
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
-                "power_w_max": max(pw) if pw else None, "samples": len(sm)}
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "source": "nvml" if self.nvml else "nvidia-smi"}
 
 
 # ------------------------------------------------------------------------------------------

@@ -110,8 +110,8 @@ int tmpt_hit_scene(const tmpt_scene* scene, const float* rays6, int64_t nRays, f
  *   rayCount   one count per HitScene-equivalent query (main.cpp:57, 91), 64-bit
  *   seconds    device time of the render window (main.cpp:319-333): kernel(s) plus, for
  *              TMPT_HOST, the device-to-host copy of the frame
- * RNG: one XorShift32 stream (maths.cpp:5-13) per PIXEL and per chunk of 8 samples, seeded
- * from (chunk, pixel index) (DESIGN.md "RNG"); the reference seeds one per row (main.cpp:204).
+ * RNG: one XorShift32 stream (maths.cpp:5-13) per PIXEL and per chunk of spp/8 (clamped to 1..8)
+ * samples, seeded from (chunk, pixel index) (DESIGN.md "RNG"); the reference seeds one per row (main.cpp:204).
  * A scene renders one frame at a time (its scratch buffers are per scene). */
 int tmpt_render(const tmpt_scene* scene, const tmpt_camera* camera, int width, int height, int spp,
                 int mem, uint8_t* rgba, uint64_t* rayCount, double* seconds, void* stream);

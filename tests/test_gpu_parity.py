@@ -162,7 +162,7 @@ def test_edge_cases():
 
 
 @pytest.mark.parametrize("name,w,h,spp", [("cube", 160, 90, 4), ("suzanne", 128, 72, 3), ("teapot", 64, 36, 2), ("triangle", 33, 17, 5),
-                                          ("cube", 70, 41, 20), ("suzanne", 48, 28, 9)])  # the last two: several 8-sample chunks per pixel
+                                          ("cube", 70, 41, 20), ("suzanne", 48, 28, 9)])  # the last two: several chunks per pixel (chunk length = spp/8 clamped to 1..8)
 def test_frame_bit_exact_vs_oracle_pixel_mode(scenes, oracle, name, w, h, spp):
     sc = load_scene(name)
     cam = tm.camera_for_scene(f"{name}.obj", sc["bounds_min"], sc["bounds_max"], w, h)
@@ -308,7 +308,7 @@ def _sponza_tris():
 
 def test_config3_teapot_720p_16spp_properties(scenes):
     """teapot.obj 1280x720 16 spp, 1 GPU: deterministic, and the 8-way stripe partition composes to the same frame
-    (two 8-sample chunks per pixel, so the accumulate + resolve path is exercised at full size)."""
+    (several chunks per pixel, so the accumulate + resolve path is exercised at full size)."""
     import torch
     from toymeshpathtracer_b200 import multigpu
     sc = load_scene("teapot")
@@ -524,3 +524,19 @@ def test_large_random_scene(oracle):
             assert info["tri_count"] == n and info["max_depth"] <= 21
             assert (a[0] == b[0]).all() and (bits(a[1]) == bits(b[1])).all()
             assert (a[0] >= 0).sum() > 1000
+
+
+def test_regeneration_render_kernel_gives_the_same_bytes():
+    """k_render_regen (per-lane ray regeneration, TMPT_RENDER_KERNEL=1; measured, not the default) schedules the same per-lane
+    arithmetic differently: frame and ray count equal the lockstep kernel's.  The variant is read once per process."""
+    import sys
+    outs = []
+    for k in ("0", "1"):
+        env = dict(os.environ, TMPT_RENDER_KERNEL=k)
+        r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "exp_regen.py"), "--scene", "suzanne", "--width", "101", "--height", "57",
+                            "--spp", "20", "--reps", "0"], env=env, capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0, r.stderr[-2000:]
+        m = re.search(r"sha (\w+) rays (\d+)", r.stdout)
+        assert m, r.stdout
+        outs.append(m.groups())
+    assert outs[0] == outs[1]

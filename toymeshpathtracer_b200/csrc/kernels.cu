@@ -607,7 +607,7 @@ __global__ void __launch_bounds__(128) k_hit_scene_wq(bvh::SceneView sc, const f
 }
 
 // ------------------------------------------------------------------------------------------
-// K4: path tracing.  Work unit = (8x4 pixel tile, chunk of 8 samples) per warp, fetched from a
+// K4: path tracing.  Work unit = (8x4 pixel tile, one chunk of chunk_len(spp) samples) per warp, fetched from a
 // global counter (persistent CTAs); a lane runs the samples of its pixel's chunk serially
 // because the chunk's XorShift32 stream flows through them (DESIGN.md "RNG").  With more than
 // one chunk per pixel the chunk sums go to an accumulation buffer and k_resolve adds them in
