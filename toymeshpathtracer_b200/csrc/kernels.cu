@@ -10,6 +10,7 @@
 //   K5  stripe gather  k_unpack_stripes       (rank 0 after the multi-GPU gather)
 //
 // There is no CPU fallback in this file: every entry point needs a CUDA device.
+#include <cooperative_groups.h>
 #include <cuda_runtime.h>
 
 #include <atomic>
@@ -289,11 +290,11 @@ __device__ __forceinline__ bld::Box smem_box_load(const uint32_t* b6) {
                     bld::ordered_to_float(b6[3]), bld::ordered_to_float(b6[4]), bld::ordered_to_float(b6[5])};
 }
 
-__global__ void __launch_bounds__(SAH_THREADS) k_sah_level(bld::BinTree t, const float4* __restrict__ pLo, const float4* __restrict__ pHi,
-                                                           const uint32_t* __restrict__ idxIn, uint32_t* __restrict__ idxOut,
-                                                           uint32_t* __restrict__ primFinal, const SahTask* __restrict__ inQ,
-                                                           SahTask* __restrict__ outQ, uint32_t* __restrict__ outCount,
-                                                           uint32_t* __restrict__ nodeCounter, bld::SahParams sp) {
+// One (node, range) task, by one CTA: node box, binning, plane choice, partition into the other index buffer.
+__device__ __forceinline__ void sah_task(const SahTask tk, const bld::BinTree& t, const float4* __restrict__ pLo, const float4* __restrict__ pHi,
+                                         const uint32_t* __restrict__ idxIn, uint32_t* __restrict__ idxOut, uint32_t* __restrict__ primFinal,
+                                         SahTask* __restrict__ outQ, uint32_t* __restrict__ outCount, uint32_t* __restrict__ nodeCounter,
+                                         const bld::SahParams& sp) {
     __shared__ uint32_t sNode[6], sCen[6];
     __shared__ uint32_t sBinBox[3][bld::SAH_BINS][6];
     __shared__ int sBinCnt[3][bld::SAH_BINS];
@@ -301,7 +302,6 @@ __global__ void __launch_bounds__(SAH_THREADS) k_sah_level(bld::BinTree t, const
     __shared__ int sLeft[3 * (bld::SAH_BINS - 1)];
     __shared__ bld::SahDecision sDec;
     __shared__ int sNl, sNr;
-    const SahTask tk = inQ[blockIdx.x];
     const int tid = threadIdx.x;
     if (tid < 6) { sNode[tid] = tid < 3 ? 0xFFFFFFFFu : 0u; sCen[tid] = tid < 3 ? 0xFFFFFFFFu : 0u; }
     for (int k = tid; k < 3 * bld::SAH_BINS; k += SAH_THREADS) {
@@ -315,7 +315,7 @@ __global__ void __launch_bounds__(SAH_THREADS) k_sah_level(bld::BinTree t, const
     {
         bld::Box nb = bld::empty_box(), cb = bld::empty_box();
         for (int i = tid; i < tk.count; i += SAH_THREADS) {
-            const uint32_t id = idxIn[tk.first + i];
+            const uint32_t id = __ldcg(&idxIn[tk.first + i]);
             const float4 lo = pLo[id], hi = pHi[id];
             nb = bld::box_union(nb, bld::Box{lo.x, lo.y, lo.z, hi.x, hi.y, hi.z});
             const float cx = 0.5f * (lo.x + hi.x), cy = 0.5f * (lo.y + hi.y), cz = 0.5f * (lo.z + hi.z);
@@ -341,7 +341,7 @@ __global__ void __launch_bounds__(SAH_THREADS) k_sah_level(bld::BinTree t, const
     // 2. bin the primitives on all three axes
     if (tk.count > 1) {
         for (int i = tid; i < tk.count; i += SAH_THREADS) {
-            const uint32_t id = idxIn[tk.first + i];
+            const uint32_t id = __ldcg(&idxIn[tk.first + i]);
             const float4 lo = pLo[id], hi = pHi[id];
             const float c[3] = {0.5f * (lo.x + hi.x), 0.5f * (lo.y + hi.y), 0.5f * (lo.z + hi.z)};
 #pragma unroll
@@ -384,7 +384,7 @@ __global__ void __launch_bounds__(SAH_THREADS) k_sah_level(bld::BinTree t, const
     // 4. leaf: the range is final.  split: partition into the other index buffer.
     const bld::SahDecision d = sDec;
     for (int i = tid; i < tk.count; i += SAH_THREADS) {
-        const uint32_t id = idxIn[tk.first + i];
+        const uint32_t id = __ldcg(&idxIn[tk.first + i]);
         if (d.axis < 0) { primFinal[tk.first + i] = id; continue; }
         bool goLeft;
         if (d.axis == 3) goLeft = i < d.leftCount;
@@ -398,11 +398,68 @@ __global__ void __launch_bounds__(SAH_THREADS) k_sah_level(bld::BinTree t, const
     }
 }
 
+// one level per launch (the host reads the task count back between levels): the fallback form
+__global__ void __launch_bounds__(SAH_THREADS) k_sah_level(bld::BinTree t, const float4* __restrict__ pLo, const float4* __restrict__ pHi,
+                                                           const uint32_t* __restrict__ idxIn, uint32_t* __restrict__ idxOut,
+                                                           uint32_t* __restrict__ primFinal, const SahTask* __restrict__ inQ,
+                                                           SahTask* __restrict__ outQ, uint32_t* __restrict__ outCount,
+                                                           uint32_t* __restrict__ nodeCounter, bld::SahParams sp) {
+    sah_task(inQ[blockIdx.x], t, pLo, pHi, idxIn, idxOut, primFinal, outQ, outCount, nodeCounter, sp);
+}
+
+// The whole top-down build in ONE cooperative launch: resident CTAs loop over the tasks of a level, a grid-wide barrier
+// separates the levels.  (With one launch per level the build of a 66 k-triangle scene spent 3.4 ms in kernels and
+// 3-10 ms in ~30 host round trips.)  Three task counters rotate: level L reads counts[L % 3], appends to
+// counts[(L+1) % 3] and clears counts[(L+2) % 3], so one barrier per level is enough.  The index and task buffers
+// alternate with the level's parity exactly as in the host loop.
+__global__ void __launch_bounds__(SAH_THREADS) k_sah_build(bld::BinTree t, const float4* __restrict__ pLo, const float4* __restrict__ pHi,
+                                                           uint32_t* idxA, uint32_t* idxB, uint32_t* __restrict__ primFinal, SahTask* qA, SahTask* qB,
+                                                           uint32_t* counts, uint32_t* __restrict__ nodeCounter, bld::SahParams sp, int maxLevels,
+                                                           uint32_t* status) {
+    cooperative_groups::grid_group grid = cooperative_groups::this_grid();
+    for (int level = 0;; ++level) {
+        const uint32_t cnt = *(volatile uint32_t*)&counts[level % 3];
+        if (cnt == 0) break;
+        if (level >= maxLevels) {
+            if (blockIdx.x == 0 && threadIdx.x == 0) atomicOr(status, 2u);  // did not terminate
+            break;
+        }
+        if (blockIdx.x == 0 && threadIdx.x == 0) counts[(level + 2) % 3] = 0u;
+        const uint32_t* idxIn = (level & 1) ? idxB : idxA;
+        uint32_t* idxOut = (level & 1) ? idxA : idxB;
+        const SahTask* inQ = (level & 1) ? qB : qA;
+        SahTask* outQ = (level & 1) ? qA : qB;
+        for (uint32_t k = blockIdx.x; k < cnt; k += gridDim.x) {
+            const SahTask tk{__ldcg(&inQ[k].node), __ldcg(&inQ[k].first), __ldcg(&inQ[k].count)};
+            sah_task(tk, t, pLo, pHi, idxIn, idxOut, primFinal, outQ, &counts[(level + 1) % 3], nodeCounter, sp);
+            __syncthreads();  // the task's shared arrays are reused by the next one
+        }
+        grid.sync();
+    }
+}
+
 __global__ void k_collapse(bld::BinTree t, bld::WideOut w, const bld::WorkItem* __restrict__ inQueue, const uint32_t* __restrict__ inCount,
                            bld::WorkItem* __restrict__ outQueue, uint32_t* __restrict__ outCount) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= *inCount) return;
     bld::collapse_node(t, w, inQueue[i], outQueue, outCount);
+}
+// the collapse, level by level, in one cooperative launch (same counter rotation as k_sah_build)
+__global__ void __launch_bounds__(128) k_collapse_all(bld::BinTree t, bld::WideOut w, bld::WorkItem* qA, bld::WorkItem* qB, uint32_t* counts) {
+    cooperative_groups::grid_group grid = cooperative_groups::this_grid();
+    const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x, nthreads = gridDim.x * blockDim.x;
+    for (int level = 0;; ++level) {
+        const uint32_t cnt = *(volatile uint32_t*)&counts[level % 3];
+        if (cnt == 0) break;
+        if (tid == 0) counts[(level + 2) % 3] = 0u;
+        const bld::WorkItem* inQ = (level & 1) ? qB : qA;
+        bld::WorkItem* outQ = (level & 1) ? qA : qB;
+        for (uint32_t i = tid; i < cnt; i += nthreads) {
+            const bld::WorkItem it{__ldcg(&inQ[i].bnode), __ldcg(&inQ[i].wide), __ldcg(&inQ[i].depth)};  // written by other SMs a level ago
+            bld::collapse_node(t, w, it, outQ, &counts[(level + 1) % 3]);
+        }
+        grid.sync();
+    }
 }
 __global__ void k_quantize_nodes(const float4* __restrict__ nodesF, uint4* __restrict__ qnodes, uint32_t count) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -834,6 +891,11 @@ int build_bvh(tmpt_scene* s, unsigned flags) {
     cudaStream_t st = s->stream;
     // SAH constants: one binary inner node vs one exact triangle test (TMPT_SAH_CI / TMPT_SAH_MAXLEAF: tuning overrides)
     const float cInner = getenv("TMPT_SAH_CI") ? (float)atof(getenv("TMPT_SAH_CI")) : 1.0f, cTri = 1.0f;
+    // the level loops of the SAH build and of the collapse run inside one cooperative launch each; TMPT_BUILD_HOSTLOOP=1 (or a
+    // device without cooperative launch) keeps them on the host, one launch and one read-back per level
+    int coopAttr = 0;
+    CU_TRY(cudaDeviceGetAttribute(&coopAttr, cudaDevAttrCooperativeLaunch, s->device));
+    const bool coop = coopAttr != 0 && !(getenv("TMPT_BUILD_HOSTLOOP") && atoi(getenv("TMPT_BUILD_HOSTLOOP")) != 0);
     const int maxLeaf = getenv("TMPT_SAH_MAXLEAF") ? std::max(1, std::min(bvh::MAX_LEAF_TRIS, atoi(getenv("TMPT_SAH_MAXLEAF")))) : bvh::MAX_LEAF_TRIS;
 
     // every build scratch array comes out of ONE allocation (a dozen cudaMalloc/cudaFree pairs cost more than the kernels)
@@ -843,7 +905,7 @@ int build_bvh(tmpt_scene* s, unsigned flags) {
     {
         const size_t N = (size_t)n;
         struct Req { Arr* a; size_t bytes; };
-        const Req reqs[] = {{&bounds, 6 * 4}, {&primA, N * 4}, {&primB, N * 4}, {&visits, N * 4}, {&counters, 4 * 4}, {&qCount, 2 * 4}, {&keysA, N * 8},
+        const Req reqs[] = {{&bounds, 6 * 4}, {&primA, N * 4}, {&primB, N * 4}, {&visits, N * 4}, {&counters, 4 * 4}, {&qCount, 4 * 4}, {&keysA, N * 8},
                             {&keysB, N * 8}, {&left, 2 * N * 4}, {&right, 2 * N * 4}, {&parent, 2 * N * 4}, {&first, 2 * N * 4}, {&lo, 2 * N * 16},
                             {&hi, 2 * N * 16}, {&sah, 2 * 4}, {&qA, N * sizeof(bld::WorkItem)}, {&qB, N * sizeof(bld::WorkItem)}, {&pLo, N * 16},
                             {&pHi, N * 16}, {&primFinal, N * 4}, {&nodeCounter, 4}, {&tqA, N * sizeof(SahTask)}, {&tqB, N * sizeof(SahTask)}};
@@ -899,29 +961,49 @@ int build_bvh(tmpt_scene* s, unsigned flags) {
         const uint32_t one = 1, zero = 0;
         CU_TRY(cudaMemcpyAsync(d_tqA, &rootTask, sizeof rootTask, cudaMemcpyHostToDevice, st));
         CU_TRY(cudaMemcpyAsync(d_nodeCounter, &one, 4, cudaMemcpyHostToDevice, st));
-        uint32_t* idxIn = d_primA; uint32_t* idxOut = d_primB;
-        SahTask* qin = d_tqA; SahTask* qout = d_tqB;
-        uint32_t count = 1;
-        int levels = 0;
-        while (count > 0) {
-            CU_TRY(cudaMemcpyAsync(d_qCount, &zero, 4, cudaMemcpyHostToDevice, st));
-            LAUNCH(k_sah_level, count, SAH_THREADS, 0, st, t, d_pLo, d_pHi, idxIn, idxOut, d_primFinal, qin, qout, d_qCount, d_nodeCounter, sp);
-            CU_TRY(cudaMemcpyAsync(&count, d_qCount, 4, cudaMemcpyDeviceToHost, st));
-            CU_TRY(cudaStreamSynchronize(st));
-            std::swap(idxIn, idxOut);
-            std::swap(qin, qout);
-            if (++levels > 4096) return tmpt::fail(TMPT_ERR_CUDA, "SAH build did not terminate");
+        if (coop) {
+            // one cooperative launch for all levels (k_sah_build); d_qCount = three rotating task counters
+            const uint32_t counts0[3] = {1u, 0u, 0u};
+            CU_TRY(cudaMemcpyAsync(d_qCount, counts0, sizeof counts0, cudaMemcpyHostToDevice, st));
+            int perSM = 0;
+            CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, k_sah_build, SAH_THREADS, 0));
+            const int grid = std::max(1, std::min(s->smCount * std::max(perSM, 1), n));
+            uint32_t* idxA = d_primA; uint32_t* idxB = d_primB;
+            SahTask* qA = d_tqA; SahTask* qB = d_tqB;
+            uint32_t* countsP = d_qCount; uint32_t* nodeCounterP = d_nodeCounter; uint32_t* primFinalP = d_primFinal;
+            const float4* pLoP = d_pLo; const float4* pHiP = d_pHi;
+            int maxLevels = 4096;
+            uint32_t* statusP = s->d_status + 1;
+            void* args[] = {&t, &pLoP, &pHiP, &idxA, &idxB, &primFinalP, &qA, &qB, &countsP, &nodeCounterP, &sp, &maxLevels, &statusP};
+            CU_TRY(cudaLaunchCooperativeKernel((void*)k_sah_build, dim3(grid), dim3(SAH_THREADS), args, 0, st));
+            tmpt::count_launch();
+        } else {
+            uint32_t* idxIn = d_primA; uint32_t* idxOut = d_primB;
+            SahTask* qin = d_tqA; SahTask* qout = d_tqB;
+            uint32_t count = 1;
+            int levels = 0;
+            while (count > 0) {
+                CU_TRY(cudaMemcpyAsync(d_qCount, &zero, 4, cudaMemcpyHostToDevice, st));
+                LAUNCH(k_sah_level, count, SAH_THREADS, 0, st, t, d_pLo, d_pHi, idxIn, idxOut, d_primFinal, qin, qout, d_qCount, d_nodeCounter, sp);
+                CU_TRY(cudaMemcpyAsync(&count, d_qCount, 4, cudaMemcpyDeviceToHost, st));
+                CU_TRY(cudaStreamSynchronize(st));
+                std::swap(idxIn, idxOut);
+                std::swap(qin, qout);
+                if (++levels > 4096) return tmpt::fail(TMPT_ERR_CUDA, "SAH build did not terminate");
+            }
         }
         // the final order lives in primFinal; keep it in primA for the collapse (same stream, device copy)
         CU_TRY(cudaMemcpyAsync(d_primA, d_primFinal, (size_t)n * sizeof(uint32_t), cudaMemcpyDeviceToDevice, st));
-        CU_TRY(cudaStreamSynchronize(st));
         s->info.builder = TMPT_BUILD_DEFAULT;
     }
     bld::WideOut w{s->d_nodes, s->d_tris, s->d_tris9, primOrder, d_counters, d_sah};
     if (n > 1) {
         float4 rootHi;
+        uint32_t bst = 0;
         CU_TRY(cudaMemcpyAsync(&rootHi, d_hi, sizeof rootHi, cudaMemcpyDeviceToHost, st));
+        CU_TRY(cudaMemcpyAsync(&bst, s->d_status + 1, 4, cudaMemcpyDeviceToHost, st));
         CU_TRY(cudaStreamSynchronize(st));
+        if (bst & 2u) return tmpt::fail(TMPT_ERR_CUDA, "SAH build did not terminate");
         int c; memcpy(&c, &rootHi.w, 4);
         rootIsLeaf = c < 0;
     }
@@ -935,16 +1017,29 @@ int build_bvh(tmpt_scene* s, unsigned flags) {
         CU_TRY(cudaMemcpyAsync(d_qA, &root, sizeof root, cudaMemcpyHostToDevice, st));
         CU_TRY(cudaMemcpyAsync(d_counters, &one, 4, cudaMemcpyHostToDevice, st));   // wide node 0 is taken
         CU_TRY(cudaMemcpyAsync(d_qCount, &one, 4, cudaMemcpyHostToDevice, st));
-        bld::WorkItem* qin = d_qA; bld::WorkItem* qout = d_qB;
-        int cin = 0;
-        uint32_t count = 1;
-        while (count > 0) {
-            CU_TRY(cudaMemcpyAsync(d_qCount + (1 - cin), &zero, 4, cudaMemcpyHostToDevice, st));
-            LAUNCH(k_collapse, div_up(count, 128), 128, 0, st, t, w, qin, d_qCount + cin, qout, d_qCount + (1 - cin));
-            CU_TRY(cudaMemcpyAsync(&count, d_qCount + (1 - cin), 4, cudaMemcpyDeviceToHost, st));
-            CU_TRY(cudaStreamSynchronize(st));
-            cin = 1 - cin;
-            bld::WorkItem* tq = qin; qin = qout; qout = tq;
+        if (coop) {
+            const uint32_t counts0[3] = {1u, 0u, 0u};
+            CU_TRY(cudaMemcpyAsync(d_qCount, counts0, sizeof counts0, cudaMemcpyHostToDevice, st));
+            int perSM = 0;
+            CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, k_collapse_all, 128, 0));
+            const int grid = std::max(1, std::min(s->smCount * std::max(perSM, 1), div_up(n, 128)));
+            bld::WorkItem* qA = d_qA; bld::WorkItem* qB = d_qB;
+            uint32_t* countsP = d_qCount;
+            void* args[] = {&t, &w, &qA, &qB, &countsP};
+            CU_TRY(cudaLaunchCooperativeKernel((void*)k_collapse_all, dim3(grid), dim3(128), args, 0, st));
+            tmpt::count_launch();
+        } else {
+            bld::WorkItem* qin = d_qA; bld::WorkItem* qout = d_qB;
+            int cin = 0;
+            uint32_t count = 1;
+            while (count > 0) {
+                CU_TRY(cudaMemcpyAsync(d_qCount + (1 - cin), &zero, 4, cudaMemcpyHostToDevice, st));
+                LAUNCH(k_collapse, div_up(count, 128), 128, 0, st, t, w, qin, d_qCount + cin, qout, d_qCount + (1 - cin));
+                CU_TRY(cudaMemcpyAsync(&count, d_qCount + (1 - cin), 4, cudaMemcpyDeviceToHost, st));
+                CU_TRY(cudaStreamSynchronize(st));
+                cin = 1 - cin;
+                bld::WorkItem* tq = qin; qin = qout; qout = tq;
+            }
         }
     }
     uint32_t hc[4]; float hs[2]; uint32_t hb[6];
