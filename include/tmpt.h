@@ -84,6 +84,12 @@ typedef struct tmpt_scene_info {
 int tmpt_scene_create(const float* tris9, int triCount, int device, unsigned flags, tmpt_scene** outScene);
 void tmpt_scene_destroy(tmpt_scene* scene); /* Scene::~Scene (scene.cpp:59) */
 int tmpt_scene_get_info(const tmpt_scene* scene, tmpt_scene_info* outInfo);
+/* Beyond the reference: the same triangles, moved.  `tris9` has the layout and the count the
+ * scene was created with; the BVH keeps its topology and is refitted on the device (boxes, Moller-Trumbore slots, hit
+ * payload).  Every query after the call answers for the NEW positions, exactly as a freshly created scene would (the
+ * tree only culls); traversal gets slower the further the vertices move from where the tree was built.
+ * `seconds` (may be NULL): upload + device time.  Not to be called while a query or a render of the scene is in flight. */
+int tmpt_scene_refit(tmpt_scene* scene, const float* tris9, int triCount, double* seconds);
 
 /* ---- query: int Scene::HitScene(const Ray&, float tMin, float tMax, Hit&) const
  * (scene.h:36-37, scene.cpp:86-97), batched over nRays.
@@ -115,6 +121,17 @@ int tmpt_hit_scene(const tmpt_scene* scene, const float* rays6, int64_t nRays, f
  * A scene renders one frame at a time (its scratch buffers are per scene). */
 int tmpt_render(const tmpt_scene* scene, const tmpt_camera* camera, int width, int height, int spp,
                 int mem, uint8_t* rgba, uint64_t* rayCount, double* seconds, void* stream);
+
+/* Progressive rendering (beyond the reference): the frame converges over calls.
+ * tmpt_progressive_begin fixes the frame size and clears the running per-pixel sums kept with the scene; every
+ * tmpt_progressive_pass traces `nChunks` (1..128) more chunks of 8 samples per pixel with the SAME camera, adds them to
+ * the sums in chunk order and writes the mean over all samples so far (quantised like tmpt_render's frame).  Chunk c of
+ * a pixel is the same XorShift32 stream whether it is traced by a one-shot frame or by a pass, so after P chunks in total
+ * the frame equals tmpt_render(spp = 8 * P) byte for byte whenever P >= 8 (a one-shot frame uses 8-sample chunks from
+ * 64 spp on).  rayCount / seconds: this pass only.  samplesSoFar (may be NULL): 8 * chunks so far.  Single GPU. */
+int tmpt_progressive_begin(tmpt_scene* scene, int width, int height);
+int tmpt_progressive_pass(tmpt_scene* scene, const tmpt_camera* camera, int nChunks, int mem, uint8_t* rgba,
+                          uint64_t* rayCount, double* seconds, int* samplesSoFar, void* stream);
 
 /* Multi-GPU form: this rank renders only the row stripes it owns -- stripe k (rows
  * [k*stripeRows, (k+1)*stripeRows)) belongs to rank k % worldSize -- and writes them

@@ -186,6 +186,23 @@ int emu_nodes(void* h, float* out) {
     if (out) memcpy(out, s->nodes.data(), (size_t)s->counters[0] * bvh::NODE_F4 * 16);
     return (int)s->counters[0];
 }
+// tmpt_scene_refit, serially: children have larger indices than their parents (the collapse allocates level by level), so a
+// sweep from the last node to the root is bottom-up
+void emu_scene_refit(void* h, const float* tris9) {
+    EmuScene* s = (EmuScene*)h;
+    if (s->n == 0) return;
+    s->tris9.assign(tris9, tris9 + (size_t)s->n * 9);
+    s->view.tris9 = s->tris9.data();
+    bld::Box scene{3.0e38f, 3.0e38f, 3.0e38f, -3.0e38f, -3.0e38f, -3.0e38f};
+    for (int i = 0; i < s->n; ++i) scene = bld::box_union(scene, bld::tri_box(tris9 + (size_t)i * 9));
+    const float maxAbs = std::max(std::max(std::max(std::fabs(scene.lox), std::fabs(scene.hix)), std::max(std::fabs(scene.loy), std::fabs(scene.hiy))),
+                                  std::max(std::fabs(scene.loz), std::fabs(scene.hiz)));
+    const float4* nodes = s->nodes.data();
+    for (uint32_t i = s->counters[0]; i-- > 0;)
+        bld::refit_wide_node(s->nodes.data(), s->tris.data(), s->tris9.data(), i, maxAbs,
+                             [nodes](uint32_t n, int row) { return nodes[(size_t)n * bvh::NODE_F4 + row]; });
+    for (uint32_t i = 0; i < s->counters[0]; ++i) bld::quantize_node(s->nodes.data(), s->qnodes.data(), i);
+}
 // the quantised nodes, in LOGICAL row order (the bank skew undone): 16 uint32 per node
 void emu_qnodes(void* h, uint32_t* out) {
     EmuScene* s = (EmuScene*)h;

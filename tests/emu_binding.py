@@ -61,6 +61,10 @@ class EmuScene:
 
     __del__ = close
 
+    def refit(self, tris):
+        self.tris = np.ascontiguousarray(tris, np.float32).reshape(-1, 9)
+        self.L.emu_scene_refit(self.h, _p(self.tris))
+
     def info(self):
         out = np.zeros(5, np.uint32)
         self.L.emu_scene_info(self.h, _p(out))

@@ -197,3 +197,39 @@ def test_sah_tree_is_cheaper_than_lbvh(emu, oracle):
     lbvh = emu.scene(sc["tris"], builder=1).render_stats(cam, 64, 36, 1)
     assert sah["rays"] == lbvh["rays"]
     assert sah["nodes_per_ray"] < 0.9 * lbvh["nodes_per_ray"]
+
+
+# ---- refit (tmpt_scene_refit): same topology, moved vertices ----
+def _wobble(tris, rng, amp):
+    """Move every VERTEX (shared positions stay shared) by a smooth displacement field + a little noise."""
+    v = tris.reshape(-1, 3).astype(np.float64)
+    d = amp * np.stack([np.sin(1.7 * v[:, 1] + 0.3), np.cos(2.1 * v[:, 2]), np.sin(1.3 * v[:, 0] + 1.0)], 1)
+    return (v + d).astype(np.float32).reshape(-1, 9)
+
+
+@pytest.mark.parametrize("builder", [0, 1], ids=["sah", "lbvh"])
+@pytest.mark.parametrize("name", ["cube", "suzanne", "teapot"])
+def test_refit_answers_for_the_new_positions(emu, name, builder):
+    sc = load_scene(name)
+    rng = np.random.default_rng(5)
+    size = float(np.max(sc["bounds_max"] - sc["bounds_min"]))
+    moved = _wobble(sc["tris"], rng, 0.15 * size)
+    s = emu.scene(sc["tris"], builder=builder)
+    s.refit(moved)
+    n = 3000
+    o = rng.uniform(sc["bounds_min"] - 0.5 * size, sc["bounds_max"] + 0.5 * size, (n, 3)).astype(np.float32)
+    d = rng.normal(size=(n, 3)); d = (d / np.linalg.norm(d, axis=1, keepdims=True)).astype(np.float32)
+    rays = np.concatenate([o, d], 1).astype(np.float32)
+    a, b = s.hit(rays, mode=0), s.hit(rays, mode=2)           # refitted tree vs all-triangle scan of the new positions
+    fresh = emu.scene(moved, builder=builder).hit(rays, mode=0)  # vs a tree built for the new positions
+    assert (a[0] >= 0).sum() > 100
+    for other in (b, fresh):
+        hit = a[0] >= 0
+        assert (a[0] == other[0]).all() and (bits(a[1])[hit] == bits(other[1])[hit]).all()
+        assert (bits(a[2])[hit] == bits(other[2])[hit]).all() and (bits(a[3])[hit] == bits(other[3])[hit]).all()
+    # the slots hold the new vertices; refitting back restores the original answers
+    ids = s.slots()[:, 0, 3].copy().view(np.uint32)
+    assert (bits(s.slots()[:, 0, :3]) == bits(moved.reshape(-1, 3, 3)[ids][:, 0])).all()
+    s.refit(sc["tris"])
+    back, orig = s.hit(rays, mode=0), emu.scene(sc["tris"], builder=builder).hit(rays, mode=0)
+    assert (back[0] == orig[0]).all() and (bits(back[1])[back[0] >= 0] == bits(orig[1])[back[0] >= 0]).all()

@@ -540,3 +540,67 @@ def test_regeneration_render_kernel_gives_the_same_bytes():
         assert m, r.stdout
         outs.append(m.groups())
     assert outs[0] == outs[1]
+
+
+def test_refit_moved_vertices(scenes):
+    """tmpt_scene_refit: same topology, moved vertices.  Hits equal the all-triangle scan of the NEW positions and a scene
+    created from them, a frame rendered after the refit equals the fresh scene's frame byte for byte (the tree only culls)."""
+    sc = load_scene("teapot")
+    size = float(np.max(sc["bounds_max"] - sc["bounds_min"]))
+    v = sc["tris"].reshape(-1, 3).astype(np.float64)
+    moved = (v + 0.12 * size * np.stack([np.sin(1.7 * v[:, 1] + 0.3), np.cos(2.1 * v[:, 2]), np.sin(1.3 * v[:, 0] + 1.0)], 1)).astype(np.float32).reshape(-1, 9)
+    rays = _random_rays(sc, 60000, 31)
+    w, h, spp = 96, 54, 8
+    with tm.Scene(sc["tris"]) as s, tm.Scene(moved) as fresh:
+        before = s.HitScene(rays)
+        sec = s.refit(moved)
+        assert 0 < sec < 1.0
+        a, b, c = s.HitScene(rays), s.HitScene(rays, mode=tm.HIT_BRUTE), fresh.HitScene(rays)
+        hit = a[0] >= 0
+        assert hit.sum() > 1000 and (a[0] != before[0]).any()
+        for other in (b, c):
+            assert (a[0] == other[0]).all() and (bits(a[1])[hit] == bits(other[1])[hit]).all()
+            assert (bits(a[2])[hit] == bits(other[2])[hit]).all() and (bits(a[3])[hit] == bits(other[3])[hit]).all()
+        anyhit = s.HitScene(rays, mode=tm.HIT_ANY)
+        assert ((anyhit[0] >= 0) == hit).all()
+        mn, mx = moved.reshape(-1, 3).min(0), moved.reshape(-1, 3).max(0)
+        cam = tm.camera_for_scene("teapot.obj", mn, mx, w, h)
+        f1, r1, _ = s.render(cam, w, h, spp)
+        f2, r2, _ = fresh.render(cam, w, h, spp)
+        assert r1 == r2 and (f1 == f2).all()
+        info = s.info()
+        assert np.allclose(info["bounds_min"], mn) and np.allclose(info["bounds_max"], mx)
+        with pytest.raises(tm.TmptError):
+            s.refit(moved[:-1])
+        s.refit(sc["tris"])  # and back
+        again = s.HitScene(rays)
+        assert (again[0] == before[0]).all() and (bits(again[1])[before[0] >= 0] == bits(before[1])[before[0] >= 0]).all()
+
+
+def test_progressive_passes_converge_to_the_one_shot_frame(scenes):
+    """tmpt_progressive_*: P chunks of 8 samples traced over several passes give, byte for byte, the frame tmpt_render
+    produces at spp = 8 P (P >= 8), and the same number of rays; the frame is rendered in one-chunk and multi-chunk passes."""
+    sc = load_scene("suzanne")
+    w, h = 85, 47
+    cam = tm.camera_for_scene("suzanne.obj", sc["bounds_min"], sc["bounds_max"], w, h)
+    s = scenes("suzanne")
+    want, want_rays, _ = s.render(cam, w, h, 80)
+    s.progressive_begin(w, h)
+    total, frames = 0, []
+    for n in (1, 3, 2, 1, 3):  # 10 chunks = 80 samples
+        img, rays, sec, spp = s.progressive_pass(cam, n)
+        total += rays
+        frames.append(img)
+        assert sec > 0 and img[..., 3].min() == 255
+    assert spp == 80 and total == want_rays and (frames[-1] == want).all()
+    # the first 8 chunks are the 64 spp frame; earlier passes are noisier estimates of the same image
+    want64, rays64, _ = s.render(cam, w, h, 64)
+    s.progressive_begin(w, h)
+    img, rays, _, spp = s.progressive_pass(cam, 8)
+    assert spp == 64 and rays == rays64 and (img == want64).all()
+    err = [np.abs(f.astype(np.float64) - want).mean() for f in frames]
+    assert err[0] > err[2] > err[-1] == 0.0
+    with tm.Scene(sc["tris"]) as fresh:  # a pass without tmpt_progressive_begin is an argument error
+        fresh._prog = (w, h)
+        with pytest.raises(tm.TmptError):
+            fresh.progressive_pass(cam, 1)

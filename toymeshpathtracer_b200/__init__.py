@@ -38,6 +38,7 @@ ABI_SYMBOLS = [
     "tmpt_camera_make", "tmpt_camera_for_scene", "tmpt_write_png", "tmpt_main", "tmpt_last_error",
     "tmpt_device_count", "tmpt_launch_count", "tmpt_render_stats", "tmpt_hit_scene_stats",
     "tmpt_frame_alloc", "tmpt_frame_open", "tmpt_frame_close", "tmpt_frame_free", "tmpt_render_multi",
+    "tmpt_scene_refit", "tmpt_progressive_begin", "tmpt_progressive_pass",
 ]
 
 
@@ -80,8 +81,11 @@ def lib() -> C.CDLL:
     L.tmpt_scene_destroy.argtypes = [vp]
     L.tmpt_scene_destroy.restype = None
     L.tmpt_scene_get_info.argtypes = [vp, C.POINTER(SceneInfo)]
+    L.tmpt_scene_refit.argtypes = [vp, vp, i32, C.POINTER(C.c_double)]
     L.tmpt_hit_scene.argtypes = [vp, vp, i64, f32, f32, i32, i32, vp, vp, vp, vp, vp]
     L.tmpt_render.argtypes = [vp, vp, i32, i32, i32, i32, vp, C.POINTER(C.c_uint64), C.POINTER(C.c_double), vp]
+    L.tmpt_progressive_begin.argtypes = [vp, i32, i32]
+    L.tmpt_progressive_pass.argtypes = [vp, vp, i32, i32, vp, C.POINTER(C.c_uint64), C.POINTER(C.c_double), C.POINTER(i32), vp]
     L.tmpt_render_stripes.argtypes = [vp, vp, i32, i32, i32, i32, i32, i32, vp, vp, vp, vp]
     L.tmpt_stripe_rows.argtypes = [i32, i32, i32, i32]
     L.tmpt_unpack_stripes.argtypes = [vp, i32, i32, i32, i32, i32, vp, vp]
@@ -191,6 +195,13 @@ class Scene:
         self.device = device
         _check(lib().tmpt_scene_create(_ptr(tris), tris.shape[0], device, flags, C.byref(self._h)))
 
+    def refit(self, tris) -> float:
+        """Same triangles, moved (tmpt_scene_refit): the BVH keeps its topology, boxes / slots / payload follow -> seconds."""
+        tris = _f32(tris).reshape(-1, 9)
+        sec = C.c_double(0.0)
+        _check(lib().tmpt_scene_refit(self._h, _ptr(tris), tris.shape[0], C.byref(sec)))
+        return sec.value
+
     def close(self):
         if getattr(self, "_h", None) and _lib is not None:  # (module globals may be gone at interpreter exit)
             _lib.tmpt_scene_destroy(self._h)
@@ -238,6 +249,20 @@ class Scene:
         rays, sec = C.c_uint64(0), C.c_double(0.0)
         _check(lib().tmpt_render(self._h, _ptr(cam), width, height, spp, HOST, _ptr(rgba), C.byref(rays), C.byref(sec), None))
         return rgba, rays.value, sec.value
+
+    def progressive_begin(self, width: int, height: int):
+        """Start (or restart) a progressive render of a width x height frame (tmpt_progressive_begin)."""
+        _check(lib().tmpt_progressive_begin(self._h, width, height))
+        self._prog = (width, height)
+
+    def progressive_pass(self, camera, n_chunks: int = 1):
+        """n_chunks more 8-sample chunks per pixel -> (rgba mean so far, rays of this pass, seconds, samples so far)."""
+        width, height = self._prog
+        cam = _f32(camera).reshape(22)
+        rgba = np.zeros((height, width, 4), np.uint8)
+        rays, sec, spp = C.c_uint64(0), C.c_double(0.0), C.c_int32(0)
+        _check(lib().tmpt_progressive_pass(self._h, _ptr(cam), n_chunks, HOST, _ptr(rgba), C.byref(rays), C.byref(sec), C.byref(spp), None))
+        return rgba, rays.value, sec.value, spp.value
 
     def traversal_stats(self, camera, width: int, height: int, spp: int) -> dict:
         """Instrumented render pass -> mean box / triangle tests per ray (bench.py's roofline figures)."""

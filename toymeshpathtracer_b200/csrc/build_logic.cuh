@@ -229,6 +229,7 @@ struct WideOut {
     const uint32_t* prim;  // sorted position -> original index
     uint32_t* counters;    // [0] wide nodes allocated, [1] triangle slots allocated, [2] leaves, [3] max depth
     float* sahAccum;       // [0] sum over inner nodes of half-area, [1] sum over leaves of half-area * count
+    uint32_t* parent;      // [wide node] its parent's index (root: itself); may be null.  Kept for tmpt_scene_refit.
 };
 struct WorkItem {
     int bnode;     // binary inner node to expand
@@ -344,6 +345,7 @@ TMPT_HD void collapse_node(const BinTree& t, const WideOut& w, const WorkItem& i
         } else {
             const uint32_t wi = wideBase + (uint32_t)inner;
             refs[j] = wi;
+            if (w.parent) w.parent[wi] = it.wide;
             outQueue[qBase + inner] = WorkItem{c[j], wi, it.depth + 1};
             ++inner;
         }
@@ -376,6 +378,59 @@ TMPT_HD void emit_single_leaf_root(const BinTree& t, const WideOut& w, int rootN
     accum_add(&w.sahAccum[1], box_half_area(Box{lo.x, lo.y, lo.z, hi.x, hi.y, hi.z}) * (float)cnt);
 }
 
+
+// ---- refit: same topology, moved vertices (tmpt_scene_refit) ----
+// Recompute every child box of wide node `node` from the CURRENT triangle array: a leaf child's box is the union of
+// its triangles' padded boxes (and its slots are rewritten with the new v0 / e1 / e2), an inner child's box is the
+// union of that child's own four child boxes, which must already be up to date (the kernel walks bottom-up).
+// `ldnode` reads a row of another node (on the device: a load that bypasses the non-coherent L1).
+template <class LoadRow>
+TMPT_HD void refit_wide_node(float4* nodes, float4* tris, const float* tris9, uint32_t node, float sceneMaxAbs, LoadRow ldnode) {
+    float4* o = nodes + (size_t)node * bvh::NODE_F4;
+    const float4 rf = o[6];
+    const uint32_t refs[4] = {ex::f2u(rf.x), ex::f2u(rf.y), ex::f2u(rf.z), ex::f2u(rf.w)};
+    float lo[3][4], hi[3][4];
+    for (int k = 0; k < 4; ++k) {
+        Box b{3.0e38f, 3.0e38f, 3.0e38f, -3.0e38f, -3.0e38f, -3.0e38f};  // empty child: stays inverted
+        if (refs[k] != bvh::NONE && bvh::ref_is_leaf(refs[k])) {
+            const uint32_t first = bvh::leaf_first(refs[k]);
+            for (int j = 0; j < bvh::leaf_count(refs[k]); ++j) {
+                float4* slot = tris + (size_t)(first + j) * 3;
+                const uint32_t id = ex::f2u(slot[0].w);
+                const float* p = tris9 + (size_t)id * 9;
+                const ex::V3 v0 = ex::v3(p[0], p[1], p[2]), v1 = ex::v3(p[3], p[4], p[5]), v2 = ex::v3(p[6], p[7], p[8]);
+                const ex::V3 e1 = ex::sub(v1, v0), e2 = ex::sub(v2, v0);  // maths.cpp:343-344
+                slot[0] = make_float4(v0.x, v0.y, v0.z, ex::u2f(id));
+                slot[1] = make_float4(e1.x, e1.y, e1.z, 0.0f);
+                slot[2] = make_float4(e2.x, e2.y, e2.z, 0.0f);
+                Box tb = tri_box(p);
+                const float dx = tb.hix - tb.lox, dy = tb.hiy - tb.loy, dz = tb.hiz - tb.loz;
+                const float pad = pad_for(sqrtf(dx * dx + dy * dy + dz * dz), sceneMaxAbs);
+                tb.lox -= pad; tb.loy -= pad; tb.loz -= pad; tb.hix += pad; tb.hiy += pad; tb.hiz += pad;
+                b = box_union(b, tb);
+            }
+        } else if (refs[k] != bvh::NONE) {
+            const float4 r0 = ldnode(refs[k], 0), r1 = ldnode(refs[k], 1), r2 = ldnode(refs[k], 2), r3 = ldnode(refs[k], 3), r4 = ldnode(refs[k], 4),
+                         r5 = ldnode(refs[k], 5);
+            // (a child's empty slots are inverted boxes: min / max ignore them)
+            b.lox = fminf(fminf(r0.x, r0.y), fminf(r0.z, r0.w)); b.hix = fmaxf(fmaxf(r1.x, r1.y), fmaxf(r1.z, r1.w));
+            b.loy = fminf(fminf(r2.x, r2.y), fminf(r2.z, r2.w)); b.hiy = fmaxf(fmaxf(r3.x, r3.y), fmaxf(r3.z, r3.w));
+            b.loz = fminf(fminf(r4.x, r4.y), fminf(r4.z, r4.w)); b.hiz = fmaxf(fmaxf(r5.x, r5.y), fmaxf(r5.z, r5.w));
+        }
+        lo[0][k] = b.lox; lo[1][k] = b.loy; lo[2][k] = b.loz; hi[0][k] = b.hix; hi[1][k] = b.hiy; hi[2][k] = b.hiz;
+    }
+    for (int a = 0; a < 3; ++a) {
+        o[2 * a] = make_float4(lo[a][0], lo[a][1], lo[a][2], lo[a][3]);
+        o[2 * a + 1] = make_float4(hi[a][0], hi[a][1], hi[a][2], hi[a][3]);
+    }
+}
+TMPT_HD int wide_inner_children(const float4* nodes, uint32_t node) {
+    const float4 rf = nodes[(size_t)node * bvh::NODE_F4 + 6];
+    const uint32_t refs[4] = {ex::f2u(rf.x), ex::f2u(rf.y), ex::f2u(rf.z), ex::f2u(rf.w)};
+    int c = 0;
+    for (int k = 0; k < 4; ++k) c += (refs[k] != bvh::NONE && !bvh::ref_is_leaf(refs[k])) ? 1 : 0;
+    return c;
+}
 
 // ---- quantise: float wide node -> 64-byte node (bvh.cuh: qnode_step) ----
 // Per axis: grid step 2^e, the smallest power of two that fits the children's span into the 8-bit range with the margins

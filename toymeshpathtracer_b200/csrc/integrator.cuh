@@ -117,13 +117,14 @@ TMPT_HD int chunk_len(int spp) {
 }
 TMPT_HD int chunk_count(int spp) { const int c = chunk_len(spp); return (spp + c - 1) / c; }
 
+// `len` = samples per chunk: chunk_len(spp) for a one-shot frame, kMaxChunkSamples for a progressive pass
 template <bool STATS = false, class Scene>
-TMPT_HD ex::V3 render_chunk(const Scene& sc, const Camera& cam, int x, int y, int chunk, int width, int height, int spp, ex::V3 lightDir,
+TMPT_HD ex::V3 render_chunk(const Scene& sc, const Camera& cam, int x, int y, int chunk, int width, int height, int spp, int len, ex::V3 lightDir,
                             unsigned long long& rays, bvh::TravStats* stats = nullptr) {
     const float invW = ex::divf(1.0f, (float)width), invH = ex::divf(1.0f, (float)height);
     uint32_t rng = ex::pixel_seed((uint32_t)chunk * ((uint32_t)width * (uint32_t)height) + (uint32_t)y * (uint32_t)width + (uint32_t)x);
     ex::V3 sum = ex::v3(0.0f, 0.0f, 0.0f);
-    const int len = chunk_len(spp), s0 = chunk * len, s1 = s0 + len < spp ? s0 + len : spp;
+    const int s0 = chunk * len, s1 = s0 + len < spp ? s0 + len : spp;
     for (int s = s0; s < s1; ++s) {
         ex::V3 o, d;
         primary_ray(cam, x, y, invW, invH, rng, o, d);
@@ -138,7 +139,7 @@ TMPT_HD uchar4 render_pixel(const Scene& sc, const Camera& cam, int x, int y, in
                             unsigned long long& rays, ex::V3* outLinear = nullptr, bvh::TravStats* stats = nullptr) {
     const float sppRecip = ex::divf(1.0f, (float)spp);
     ex::V3 sum = ex::v3(0.0f, 0.0f, 0.0f);
-    for (int c = 0; c < chunk_count(spp); ++c) sum = ex::add(sum, render_chunk<STATS>(sc, cam, x, y, c, width, height, spp, lightDir, rays, stats));
+    for (int c = 0; c < chunk_count(spp); ++c) sum = ex::add(sum, render_chunk<STATS>(sc, cam, x, y, c, width, height, spp, chunk_len(spp), lightDir, rays, stats));
     if (outLinear) *outLinear = ex::muls(sum, sppRecip);
     return resolve_pixel(sum, sppRecip);
 }

@@ -82,6 +82,9 @@ struct tmpt_scene {
     uint4* d_qnodes = nullptr;     // wide nodes, quantised (what the walk reads)
     float4* d_tris = nullptr;      // leaf-ordered MT slots
     float4* d_hitdata = nullptr;   // per original triangle: vertices + precomputed normal
+    uint32_t* d_parent = nullptr;  // per wide node: parent index (refit)
+    uint32_t* d_pending = nullptr; // per wide node: inner children not yet refitted (refit scratch)
+    uint32_t* d_bounds = nullptr;  // scene bounds as ordered uints (refit scratch)
     uint32_t* d_status = nullptr;  // [0] status bits
     // render scratch
     uint32_t* d_tileCounter = nullptr;
@@ -91,6 +94,9 @@ struct tmpt_scene {
     size_t frameBytes = 0;
     float4* d_accum = nullptr;     // chunk sums of the band being rendered
     size_t accumBytes = 0;
+    float4* d_sum = nullptr;       // progressive render: running per-pixel sums
+    size_t sumBytes = 0;
+    int progW = 0, progH = 0, progChunks = -1;  // -1: no progressive render begun
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     bvh::SceneView view{};
     tmpt_scene_info info{};
@@ -461,6 +467,33 @@ __global__ void __launch_bounds__(128) k_collapse_all(bld::BinTree t, bld::WideO
         grid.sync();
     }
 }
+// ---- refit (tmpt_scene_refit): bottom-up over the wide tree, one thread per node that has only leaf children; the last
+// thread to arrive at a parent (atomic countdown of its inner children) carries on upwards ----
+struct LoadNodeRowCg {  // a row of ANOTHER node, written by another thread of the refit: bypass the non-coherent L1
+    const float4* nodes;
+    __device__ float4 operator()(uint32_t n, int row) const { return __ldcg(nodes + (size_t)n * bvh::NODE_F4 + row); }
+};
+__global__ void k_refit_pending(const float4* __restrict__ nodes, uint32_t count, uint32_t* __restrict__ pending) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < count) pending[i] = (uint32_t)bld::wide_inner_children(nodes, i);
+}
+__global__ void k_refit_wide(float4* nodes, float4* tris, const float* __restrict__ tris9, const uint32_t* __restrict__ parent, uint32_t* pending,
+                             uint32_t count, const uint32_t* __restrict__ bounds) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count || bld::wide_inner_children(nodes, i) != 0) return;
+    const bld::Box scene = load_scene_box(bounds);
+    const float maxAbs = fmaxf(fmaxf(fmaxf(fabsf(scene.lox), fabsf(scene.hix)), fmaxf(fabsf(scene.loy), fabsf(scene.hiy))),
+                               fmaxf(fabsf(scene.loz), fabsf(scene.hiz)));
+    uint32_t node = i;
+    for (;;) {
+        bld::refit_wide_node(nodes, tris, tris9, node, maxAbs, LoadNodeRowCg{nodes});
+        if (node == 0) break;
+        __threadfence();
+        const uint32_t p = parent[node];
+        if (atomicSub(&pending[p], 1u) != 1u) break;  // a sibling subtree is still on its way
+        node = p;
+    }
+}
 __global__ void k_quantize_nodes(const float4* __restrict__ nodesF, uint4* __restrict__ qnodes, uint32_t count) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < count) bld::quantize_node(nodesF, qnodes, i);
@@ -678,7 +711,10 @@ struct RenderParams {
     int width, height, spp;
     int stripeRows, rank, world, ownedRows;
     int tilesX, numTiles;
-    int chunks;          // sample chunks per pixel
+    int chunks;          // sample chunks per pixel rendered by this launch
+    int chunk0, chunkLen; // first chunk index (progressive passes continue where the last one stopped), samples per chunk
+    int useAccum;        // chunk sums go through `accum` + k_resolve (more than one chunk, or a progressive pass)
+    float4* sumBuf;      // progressive: running per-pixel sums of the whole frame (null for a one-shot frame)
     int bandRow0;        // first owned row of the band being rendered (the accumulation buffer covers one band)
     float4* accum;       // [bandRows][width][chunks] chunk sums, when chunks > 1
     uchar4* outStripes;  // packed owned rows, or
@@ -710,8 +746,8 @@ __global__ void __launch_bounds__(THREADS, MINB) k_render(const RenderParams p) 
         const int x = tx * 8 + (lane & 7), rb = ty * 4 + (lane >> 3), r = p.bandRow0 + rb;
         if (x < p.width && r < p.ownedRows) {
             const int y = owned_row_to_global(r, p.stripeRows, p.rank, p.world);
-            const ex::V3 sum = integ::render_chunk<STATS>(p.sc, p.cam, x, y, chunk, p.width, p.height, p.spp, p.lightDir, rays, &ts);
-            if (p.chunks > 1) {
+            const ex::V3 sum = integ::render_chunk<STATS>(p.sc, p.cam, x, y, p.chunk0 + chunk, p.width, p.height, p.spp, p.chunkLen, p.lightDir, rays, &ts);
+            if (p.useAccum) {
                 p.accum[((size_t)rb * p.width + x) * p.chunks + chunk] = make_float4(sum.x, sum.y, sum.z, 0.0f);
             } else {
                 const uchar4 px = integ::resolve_pixel(sum, ex::divf(1.0f, (float)p.spp));
@@ -784,7 +820,7 @@ __global__ void __launch_bounds__(THREADS, MINB) k_render_regen(const RenderPara
                     for (int i = depth - 1; i >= 0; --i) color = integ::unwind_step(kk[i], color);
                     sum = ex::add(sum, color);
                     if (++s == sEnd) {
-                        if (p.chunks > 1) {
+                        if (p.useAccum) {
                             p.accum[((size_t)rb * p.width + x) * p.chunks + chunk] = make_float4(sum.x, sum.y, sum.z, 0.0f);
                         } else {
                             const uchar4 px = integ::resolve_pixel(sum, ex::divf(1.0f, (float)p.spp));
@@ -818,7 +854,7 @@ __global__ void __launch_bounds__(THREADS, MINB) k_render_regen(const RenderPara
                                 if (x < p.width && r < p.ownedRows) {  // (an item outside the frame is simply dropped: the lane asks again)
                                     y = owned_row_to_global(r, p.stripeRows, p.rank, p.world);
                                     rng = ex::pixel_seed((uint32_t)chunk * ((uint32_t)p.width * (uint32_t)p.height) + (uint32_t)y * (uint32_t)p.width + (uint32_t)x);
-                                    const int len = integ::chunk_len(p.spp);
+                                    const int len = p.chunkLen;
                                     s = chunk * len;
                                     sEnd = s + len < p.spp ? s + len : p.spp;
                                     sum = ex::v3(0.0f, 0.0f, 0.0f);
@@ -856,11 +892,14 @@ __global__ void k_resolve(const RenderParams p, int bandRows) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= (long long)bandRows * p.width) return;
     const int rb = (int)(i / p.width), x = (int)(i - (long long)rb * p.width), r = p.bandRow0 + rb;
+    const size_t pix = (size_t)owned_row_to_global(r, p.stripeRows, p.rank, p.world) * p.width + x;
     const float4* a = p.accum + (size_t)i * p.chunks;
     ex::V3 sum = ex::v3(0.0f, 0.0f, 0.0f);
+    if (p.sumBuf) { const float4 v = p.sumBuf[pix]; sum = ex::v3(v.x, v.y, v.z); }  // progressive: the chunks before this pass
     for (int c = 0; c < p.chunks; ++c) { const float4 v = a[c]; sum = ex::add(sum, ex::v3(v.x, v.y, v.z)); }
+    if (p.sumBuf) p.sumBuf[pix] = make_float4(sum.x, sum.y, sum.z, 0.0f);
     const uchar4 px = integ::resolve_pixel(sum, ex::divf(1.0f, (float)p.spp));
-    if (p.frame) p.frame[(size_t)owned_row_to_global(r, p.stripeRows, p.rank, p.world) * p.width + x] = px;
+    if (p.frame) p.frame[pix] = px;
     else p.outStripes[(size_t)r * p.width + x] = px;
 }
 
@@ -915,9 +954,14 @@ int build_bvh(tmpt_scene* s, unsigned flags) {
         size_t off = 0;
         for (const Req& r : reqs) { r.a->p = arena.p + off; off += (r.bytes + 255) & ~(size_t)255; }
     }
-    CU_TRY(cudaMalloc((void**)&s->d_nodes, (size_t)n * bvh::NODE_F4 * sizeof(float4)));
-    CU_TRY(cudaMalloc((void**)&s->d_tris, (size_t)n * 3 * sizeof(float4)));
-    CU_TRY(cudaMalloc((void**)&s->d_hitdata, (size_t)n * 3 * sizeof(float4)));
+    // nodes, slots and hit payload share one allocation (each cudaMalloc costs as much as a build kernel)
+    CU_TRY(cudaMalloc((void**)&s->d_nodes, (size_t)n * (bvh::NODE_F4 + 3 + 3) * sizeof(float4) + ((size_t)n * 2 + 8) * sizeof(uint32_t)));
+    s->d_tris = s->d_nodes + (size_t)n * bvh::NODE_F4;
+    s->d_hitdata = s->d_tris + (size_t)n * 3;
+    s->d_parent = (uint32_t*)(s->d_hitdata + (size_t)n * 3);
+    s->d_pending = s->d_parent + n;
+    s->d_bounds = s->d_pending + n;
+    CU_TRY(cudaMemsetAsync(s->d_parent, 0, sizeof(uint32_t), st));  // the root is its own parent
 
     uint32_t* const d_bounds = (uint32_t*)bounds.p; uint32_t* const d_primA = (uint32_t*)primA.p; uint32_t* const d_primB = (uint32_t*)primB.p;
     uint32_t* const d_visits = (uint32_t*)visits.p; uint32_t* const d_counters = (uint32_t*)counters.p; uint32_t* const d_qCount = (uint32_t*)qCount.p;
@@ -996,7 +1040,7 @@ int build_bvh(tmpt_scene* s, unsigned flags) {
         CU_TRY(cudaMemcpyAsync(d_primA, d_primFinal, (size_t)n * sizeof(uint32_t), cudaMemcpyDeviceToDevice, st));
         s->info.builder = TMPT_BUILD_DEFAULT;
     }
-    bld::WideOut w{s->d_nodes, s->d_tris, s->d_tris9, primOrder, d_counters, d_sah};
+    bld::WideOut w{s->d_nodes, s->d_tris, s->d_tris9, primOrder, d_counters, d_sah, s->d_parent};
     if (n > 1) {
         float4 rootHi;
         uint32_t bst = 0;
@@ -1063,13 +1107,15 @@ int build_bvh(tmpt_scene* s, unsigned flags) {
         s->info.sah_cost = rootArea > 0.0f ? (cInner * hs[0] + cTri * hs[1]) / rootArea : 0.0f;
     }
     if ((int)hc[1] != n) return tmpt::fail(TMPT_ERR_CUDA, "BVH build lost triangles: %u slots for %d triangles", hc[1], n);
+#if TMPT_QNODES
     CU_TRY(cudaMalloc((void**)&s->d_qnodes, ((size_t)hc[0] * bvh::QNODE_STRIDE) * sizeof(uint4)));
     LAUNCH(k_quantize_nodes, div_up((int)hc[0], 128), 128, 0, st, s->d_nodes, s->d_qnodes, hc[0]);
+#endif
     // the traversal stack holds at most 3 entries per level (bvh::wide_node_step): refuse what it could not hold
     if (3 * s->info.max_depth + 4 > bvh::STACK_SIZE)
         return tmpt::fail(TMPT_ERR_ARG, "BVH is %d levels deep; the traversal stack (%d entries) supports %d", s->info.max_depth, bvh::STACK_SIZE,
                           (bvh::STACK_SIZE - 4) / 3);
-    s->info.device_bytes = (uint64_t)n * 9 * 4 + (uint64_t)hc[0] * (bvh::NODE_F4 + bvh::QNODE_ROWS) * 16 + (uint64_t)n * 48 + (uint64_t)n * 48;
+    s->info.device_bytes = (uint64_t)n * 9 * 4 + (uint64_t)hc[0] * (bvh::NODE_F4 + (TMPT_QNODES ? bvh::QNODE_STRIDE : 0)) * 16 + (uint64_t)n * 48 + (uint64_t)n * 48;
     s->view.nodes = s->d_nodes;
     s->view.qnodes = s->d_qnodes;
     s->view.tris = s->d_tris;
@@ -1148,12 +1194,50 @@ extern "C" int tmpt_scene_create(const float* tris9, int triCount, int device, u
     return TMPT_OK;
 }
 
+// Animated vertices: same triangle count and order, new positions.  The tree keeps its topology; boxes, slots and hit
+// payload are recomputed on the device (k_refit_wide).  Results stay exact for any motion -- the tree only culls --
+// but a tree built for the old positions gets slower the further the vertices move.
+extern "C" int tmpt_scene_refit(tmpt_scene* s, const float* tris9, int triCount, double* seconds) {
+    if (!s || (triCount > 0 && !tris9)) return tmpt::fail(TMPT_ERR_ARG, "tmpt_scene_refit: NULL scene / triangles");
+    if (triCount != s->triCount) return tmpt::fail(TMPT_ERR_ARG, "tmpt_scene_refit: %d triangles, the scene was built with %d", triCount, s->triCount);
+    if (seconds) *seconds = 0.0;
+    if (triCount == 0) return TMPT_OK;
+    DeviceGuard guard(s->device);
+    if (!guard.ok) return tmpt::fail(TMPT_ERR_CUDA, "tmpt_scene_refit: cudaSetDevice(%d) failed", s->device);
+    cudaStream_t st = s->stream;
+    const int n = triCount, B = 256, G = div_up(n, B), nodes = s->info.node_count;
+    CU_TRY(cudaEventRecord(s->ev0, st));
+    CU_TRY(cudaMemcpyAsync(s->d_tris9, tris9, (size_t)n * 9 * sizeof(float), cudaMemcpyHostToDevice, st));
+    const uint32_t initBounds[6] = {0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0u, 0u, 0u};
+    CU_TRY(cudaMemcpyAsync(s->d_bounds, initBounds, sizeof initBounds, cudaMemcpyHostToDevice, st));
+    LAUNCH(k_prim_bounds, G, B, 0, st, s->d_tris9, n, s->d_bounds);
+    LAUNCH(k_hitdata, G, B, 0, st, s->d_tris9, n, s->d_hitdata);
+    LAUNCH(k_refit_pending, div_up(nodes, 128), 128, 0, st, s->d_nodes, (uint32_t)nodes, s->d_pending);
+    LAUNCH(k_refit_wide, div_up(nodes, 128), 128, 0, st, s->d_nodes, s->d_tris, s->d_tris9, s->d_parent, s->d_pending, (uint32_t)nodes, s->d_bounds);
+#if TMPT_QNODES
+    LAUNCH(k_quantize_nodes, div_up(nodes, 128), 128, 0, st, s->d_nodes, s->d_qnodes, (uint32_t)nodes);
+#endif
+    uint32_t hb[6];
+    CU_TRY(cudaMemcpyAsync(hb, s->d_bounds, sizeof hb, cudaMemcpyDeviceToHost, st));
+    CU_TRY(cudaEventRecord(s->ev1, st));
+    CU_TRY(cudaStreamSynchronize(st));
+    CU_TRY(cudaGetLastError());
+    for (int k = 0; k < 3; ++k) {
+        s->info.bounds_min[k] = bld::ordered_to_float(hb[k]);
+        s->info.bounds_max[k] = bld::ordered_to_float(hb[3 + k]);
+    }
+    float ms = 0.0f;
+    CU_TRY(cudaEventElapsedTime(&ms, s->ev0, s->ev1));
+    if (seconds) *seconds = ms * 1e-3;
+    return TMPT_OK;
+}
+
 extern "C" void tmpt_scene_destroy(tmpt_scene* s) {
     if (!s) return;
     DeviceGuard guard(s->device);
     if (s->stream) cudaStreamSynchronize(s->stream);
-    cudaFree(s->d_tris9); cudaFree(s->d_nodes); cudaFree(s->d_qnodes); cudaFree(s->d_tris); cudaFree(s->d_hitdata); cudaFree(s->d_status);
-    cudaFree(s->d_tileCounter); cudaFree(s->d_rayCount); cudaFree(s->d_fetchCounter); cudaFree(s->d_frame); cudaFree(s->d_accum);
+    cudaFree(s->d_tris9); cudaFree(s->d_nodes); cudaFree(s->d_qnodes); cudaFree(s->d_status);  // (d_tris, d_hitdata live inside d_nodes)
+    cudaFree(s->d_tileCounter); cudaFree(s->d_rayCount); cudaFree(s->d_fetchCounter); cudaFree(s->d_frame); cudaFree(s->d_accum); cudaFree(s->d_sum);
     if (s->ev0) cudaEventDestroy(s->ev0);
     if (s->ev1) cudaEventDestroy(s->ev1);
     if (s->stream) cudaStreamDestroy(s->stream);
@@ -1258,10 +1342,9 @@ static ex::V3 host_light_dir() { return ex::normalize(ex::v3(-0.7f, 1.0f, 0.5f))
 // Chunk sums go to an accumulation buffer when a pixel has more than one chunk; the frame is rendered in bands of
 // owned rows so that the buffer stays within a fixed budget (a whole 1080p x 64 spp frame is 265 MB).  Allocation
 // happens here so that callers can do it before their timed window starts.
-static int prepare_render(tmpt_scene* s, int width, int spp, int ownedRows, cudaStream_t st, int* outBandRows) {
-    const int chunks = integ::chunk_count(spp);
+static int prepare_render_chunks(tmpt_scene* s, int width, int chunks, bool forceAccum, int ownedRows, cudaStream_t st, int* outBandRows) {
     int bandRows = ownedRows;
-    if (chunks > 1 && ownedRows > 0) {
+    if ((chunks > 1 || forceAccum) && ownedRows > 0) {
         const size_t rowBytes = (size_t)width * chunks * sizeof(float4), budget = (size_t)1 << 30;
         bandRows = (int)std::min<size_t>((size_t)ownedRows, std::max<size_t>(4, (budget / rowBytes) & ~(size_t)3));
         const size_t need = (size_t)bandRows * rowBytes;
@@ -1275,21 +1358,35 @@ static int prepare_render(tmpt_scene* s, int width, int spp, int ownedRows, cuda
     if (outBandRows) *outBandRows = bandRows;
     return TMPT_OK;
 }
+static int prepare_render(tmpt_scene* s, int width, int spp, int ownedRows, cudaStream_t st, int* outBandRows) {
+    return prepare_render_chunks(s, width, integ::chunk_count(spp), false, ownedRows, st, outBandRows);
+}
+
+// One pass of a progressive render: chunks [chunk0, chunk0 + nChunks) of kMaxChunkSamples samples, added to `sum`.
+struct ProgressivePass {
+    int chunk0, nChunks;
+    float4* sum;
+};
 
 static int launch_render(const tmpt_scene* cs, const tmpt_camera* camera, int width, int height, int spp, int stripeRows, int rank, int world,
                          uint8_t* outStripes, uint8_t* frame, unsigned long long* rayCountDev, cudaStream_t st,
-                         unsigned long long* statsDev = nullptr) {
+                         unsigned long long* statsDev = nullptr, const ProgressivePass* prog = nullptr) {
     tmpt_scene* s = const_cast<tmpt_scene*>(cs);  // scratch buffers only; the scene data is immutable
     RenderParams p;
     p.sc = s->view;
     static_assert(sizeof(integ::Camera) == sizeof(tmpt_camera), "camera layout");
     memcpy(&p.cam, camera, sizeof p.cam);
     p.lightDir = host_light_dir();
-    p.width = width; p.height = height; p.spp = spp;
+    p.width = width; p.height = height;
+    p.spp = prog ? integ::kMaxChunkSamples * (prog->chunk0 + prog->nChunks) : spp;  // (progressive: the samples so far, for the mean)
     p.stripeRows = stripeRows; p.rank = rank; p.world = world;
     p.ownedRows = tmpt_stripe_rows(height, stripeRows, rank, world);
     p.tilesX = div_up(width, 8);
-    p.chunks = integ::chunk_count(spp);
+    p.chunks = prog ? prog->nChunks : integ::chunk_count(spp);
+    p.chunk0 = prog ? prog->chunk0 : 0;
+    p.chunkLen = prog ? integ::kMaxChunkSamples : integ::chunk_len(spp);
+    p.useAccum = (p.chunks > 1 || prog) ? 1 : 0;
+    p.sumBuf = prog ? prog->sum : nullptr;
     p.outStripes = (uchar4*)outStripes;
     p.frame = (uchar4*)frame;
     p.rayCount = rayCountDev;
@@ -1299,7 +1396,7 @@ static int launch_render(const tmpt_scene* cs, const tmpt_camera* camera, int wi
     p.accum = nullptr;
     if (p.ownedRows == 0) return TMPT_OK;
     int bandRows = 0;
-    const int prc = prepare_render(s, width, spp, p.ownedRows, st, &bandRows);
+    const int prc = prepare_render_chunks(s, width, p.chunks, prog != nullptr, p.ownedRows, st, &bandRows);
     if (prc != TMPT_OK) return prc;
     p.accum = s->d_accum;
     // 256 threads x 4 CTAs/SM = 32 warps/SM at 64 registers (sweep in profiles/r1_tuning_sweeps.txt: 24 warps at
@@ -1329,7 +1426,7 @@ static int launch_render(const tmpt_scene* cs, const tmpt_camera* camera, int wi
             return tmpt::fail(TMPT_ERR_ARG, "TMPT_RENDER_KERNEL=%d: no such render kernel", rk);
         } else if (statsDev) LAUNCH((k_render<true, 256, 4>), grid, 256, 0, st, p);
         else LAUNCH((k_render<false, 256, 4>), grid, 256, 0, st, p);
-        if (p.chunks > 1) LAUNCH(k_resolve, div_up((long long)rowsHere * width, 256), 256, 0, st, p, rowsHere);
+        if (p.useAccum) LAUNCH(k_resolve, div_up((long long)rowsHere * width, 256), 256, 0, st, p, rowsHere);
     }
     CU_TRY(cudaGetLastError());
     return TMPT_OK;
@@ -1390,6 +1487,67 @@ extern "C" int tmpt_render(const tmpt_scene* cs, const tmpt_camera* camera, int 
     CU_TRY(cudaEventElapsedTime(&ms, s->ev0, s->ev1));
     if (rayCount) *rayCount = rays;
     if (seconds) *seconds = (double)ms * 1.0e-3;
+    return check_status(s, st);
+}
+
+// Progressive rendering (beyond the reference): the running per-pixel sums live with the scene.
+extern "C" int tmpt_progressive_begin(tmpt_scene* s, int width, int height) {
+    if (!s) return tmpt::fail(TMPT_ERR_ARG, "tmpt_progressive_begin: NULL scene");
+    if (width < 1 || width > 10000 || height < 1 || height > 10000) return tmpt::fail(TMPT_ERR_ARG, "tmpt_progressive_begin: %d x %d out of range", width, height);
+    DeviceGuard guard(s->device);
+    if (!guard.ok) return tmpt::fail(TMPT_ERR_CUDA, "tmpt_progressive_begin: cudaSetDevice(%d) failed", s->device);
+    const size_t need = (size_t)width * height * sizeof(float4);
+    if (s->sumBytes < need) {
+        CU_TRY(cudaStreamSynchronize(s->stream));
+        cudaFree(s->d_sum); s->d_sum = nullptr; s->sumBytes = 0;
+        CU_TRY(cudaMalloc((void**)&s->d_sum, need));
+        s->sumBytes = need;
+    }
+    CU_TRY(cudaMemsetAsync(s->d_sum, 0, need, s->stream));
+    CU_TRY(cudaStreamSynchronize(s->stream));
+    s->progW = width; s->progH = height; s->progChunks = 0;
+    return TMPT_OK;
+}
+
+extern "C" int tmpt_progressive_pass(tmpt_scene* s, const tmpt_camera* camera, int nChunks, int mem, uint8_t* rgba, uint64_t* rayCount,
+                                     double* seconds, int* samplesSoFar, void* stream) {
+    if (!s || !camera || !rgba) return tmpt::fail(TMPT_ERR_ARG, "tmpt_progressive_pass: NULL scene / camera / rgba");
+    if (s->progChunks < 0) return tmpt::fail(TMPT_ERR_ARG, "tmpt_progressive_pass: call tmpt_progressive_begin first");
+    if (mem != TMPT_HOST && mem != TMPT_DEVICE) return tmpt::fail(TMPT_ERR_ARG, "tmpt_progressive_pass: mem %d", mem);
+    if (nChunks < 1 || nChunks > 128 || (long long)(s->progChunks + nChunks) * integ::kMaxChunkSamples > (1 << 24))
+        return tmpt::fail(TMPT_ERR_ARG, "tmpt_progressive_pass: %d chunks after %d", nChunks, s->progChunks);
+    DeviceGuard guard(s->device);
+    if (!guard.ok) return tmpt::fail(TMPT_ERR_CUDA, "tmpt_progressive_pass: cudaSetDevice(%d) failed", s->device);
+    cudaStream_t st = stream ? (cudaStream_t)stream : s->stream;
+    const int width = s->progW, height = s->progH;
+    const size_t bytes = (size_t)width * height * 4;
+    uint8_t* dFrame = rgba;
+    if (mem == TMPT_HOST) {
+        if (s->frameBytes < bytes) {
+            cudaFree(s->d_frame); s->d_frame = nullptr; s->frameBytes = 0;
+            CU_TRY(cudaMalloc((void**)&s->d_frame, bytes));
+            s->frameBytes = bytes;
+        }
+        dFrame = s->d_frame;
+    }
+    const ProgressivePass pass{s->progChunks, nChunks, s->d_sum};
+    int rc = prepare_render_chunks(s, width, nChunks, true, height, st, nullptr);
+    if (rc != TMPT_OK) return rc;
+    CU_TRY(cudaEventRecord(s->ev0, st));
+    CU_TRY(cudaMemsetAsync(s->d_rayCount, 0, sizeof(unsigned long long), st));
+    rc = launch_render(s, camera, width, height, 0, height, 0, 1, nullptr, dFrame, s->d_rayCount, st, nullptr, &pass);
+    if (rc != TMPT_OK) return rc;
+    if (mem == TMPT_HOST) CU_TRY(cudaMemcpyAsync(rgba, dFrame, bytes, cudaMemcpyDeviceToHost, st));
+    CU_TRY(cudaEventRecord(s->ev1, st));
+    unsigned long long rays = 0;
+    CU_TRY(cudaMemcpyAsync(&rays, s->d_rayCount, sizeof rays, cudaMemcpyDeviceToHost, st));
+    CU_TRY(cudaStreamSynchronize(st));
+    float ms = 0.0f;
+    CU_TRY(cudaEventElapsedTime(&ms, s->ev0, s->ev1));
+    s->progChunks += nChunks;
+    if (rayCount) *rayCount = rays;
+    if (seconds) *seconds = (double)ms * 1.0e-3;
+    if (samplesSoFar) *samplesSoFar = s->progChunks * integ::kMaxChunkSamples;
     return check_status(s, st);
 }
 
