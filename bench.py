@@ -379,7 +379,7 @@ def bench_b200(args, scene, w, h, spp, rank, world, local_rank):
             "config": {"workload": f"{scene_label(scene)} {w}x{h} {spp}spp", "rays_per_frame": step_rays[-1] if world == 1 else tot_rays // args.steps,
                        "parallelism": "single GPU" if world == 1 else f"row stripes of {multigpu.DEFAULT_STRIPE_ROWS} over {world} GPUs, BVH replica per GPU, " + (
                            "pixels stored straight into rank 0's frame over NVLink (CUDA IPC peer memory)" if peer else "frame gathered to rank 0 (NCCL)"),
-                       "work_unit": "8x4 pixel tile x chunk of spp/8 (1..8) samples per warp, dynamic fetch",
+                       "work_unit": "8x4 pixel tile x chunk of spp/32 (1..8) samples per warp, dynamic fetch",
                        "l2": "flushed between timed iterations (256 MB write)", "bvh": {k: info[k] for k in ("node_count", "leaf_count", "max_depth", "sah_cost", "build_ms", "device_bytes")},
                        "scene_build_wall_ms": build_wall_ms},
             "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": 88, "d2h_bytes_per_step": w * h * 4 + 8,

@@ -116,7 +116,7 @@ int tmpt_hit_scene(const tmpt_scene* scene, const float* rays6, int64_t nRays, f
  *   rayCount   one count per HitScene-equivalent query (main.cpp:57, 91), 64-bit
  *   seconds    device time of the render window (main.cpp:319-333): kernel(s) plus, for
  *              TMPT_HOST, the device-to-host copy of the frame
- * RNG: one XorShift32 stream (maths.cpp:5-13) per PIXEL and per chunk of spp/8 (clamped to 1..8)
+ * RNG: one XorShift32 stream (maths.cpp:5-13) per PIXEL and per chunk of spp/32 (clamped to 1..8)
  * samples, seeded from (chunk, pixel index) (DESIGN.md "RNG"); the reference seeds one per row (main.cpp:204).
  * A scene renders one frame at a time (its scratch buffers are per scene). */
 int tmpt_render(const tmpt_scene* scene, const tmpt_camera* camera, int width, int height, int spp,
@@ -127,8 +127,8 @@ int tmpt_render(const tmpt_scene* scene, const tmpt_camera* camera, int width, i
  * tmpt_progressive_pass traces `nChunks` (1..128) more chunks of 8 samples per pixel with the SAME camera, adds them to
  * the sums in chunk order and writes the mean over all samples so far (quantised like tmpt_render's frame).  Chunk c of
  * a pixel is the same XorShift32 stream whether it is traced by a one-shot frame or by a pass, so after P chunks in total
- * the frame equals tmpt_render(spp = 8 * P) byte for byte whenever P >= 8 (a one-shot frame uses 8-sample chunks from
- * 64 spp on).  rayCount / seconds: this pass only.  samplesSoFar (may be NULL): 8 * chunks so far.  Single GPU. */
+ * the frame equals tmpt_render(spp = 8 * P) byte for byte whenever P >= 32 (a one-shot frame uses 8-sample chunks from
+ * 256 spp on).  rayCount / seconds: this pass only.  samplesSoFar (may be NULL): 8 * chunks so far.  Single GPU. */
 int tmpt_progressive_begin(tmpt_scene* scene, int width, int height);
 int tmpt_progressive_pass(tmpt_scene* scene, const tmpt_camera* camera, int nChunks, int mem, uint8_t* rgba,
                           uint64_t* rayCount, double* seconds, int* samplesSoFar, void* stream);

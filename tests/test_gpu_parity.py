@@ -162,7 +162,7 @@ def test_edge_cases():
 
 
 @pytest.mark.parametrize("name,w,h,spp", [("cube", 160, 90, 4), ("suzanne", 128, 72, 3), ("teapot", 64, 36, 2), ("triangle", 33, 17, 5),
-                                          ("cube", 70, 41, 20), ("suzanne", 48, 28, 9)])  # the last two: several chunks per pixel (chunk length = spp/8 clamped to 1..8)
+                                          ("cube", 70, 41, 20), ("suzanne", 48, 28, 9)])  # the last two: several chunks per pixel (chunk length = spp/32 clamped to 1..8)
 def test_frame_bit_exact_vs_oracle_pixel_mode(scenes, oracle, name, w, h, spp):
     sc = load_scene(name)
     cam = tm.camera_for_scene(f"{name}.obj", sc["bounds_min"], sc["bounds_max"], w, h)
@@ -579,25 +579,25 @@ def test_refit_moved_vertices(scenes):
 
 def test_progressive_passes_converge_to_the_one_shot_frame(scenes):
     """tmpt_progressive_*: P chunks of 8 samples traced over several passes give, byte for byte, the frame tmpt_render
-    produces at spp = 8 P (P >= 8), and the same number of rays; the frame is rendered in one-chunk and multi-chunk passes."""
+    produces at spp = 8 P (P >= 32), and the same number of rays; the frame is rendered in one-chunk and multi-chunk passes."""
     sc = load_scene("suzanne")
     w, h = 85, 47
     cam = tm.camera_for_scene("suzanne.obj", sc["bounds_min"], sc["bounds_max"], w, h)
     s = scenes("suzanne")
-    want, want_rays, _ = s.render(cam, w, h, 80)
+    want, want_rays, _ = s.render(cam, w, h, 272)
     s.progressive_begin(w, h)
     total, frames = 0, []
-    for n in (1, 3, 2, 1, 3):  # 10 chunks = 80 samples
+    for n in (1, 3, 12, 1, 17):  # 34 chunks = 272 samples
         img, rays, sec, spp = s.progressive_pass(cam, n)
         total += rays
         frames.append(img)
         assert sec > 0 and img[..., 3].min() == 255
-    assert spp == 80 and total == want_rays and (frames[-1] == want).all()
-    # the first 8 chunks are the 64 spp frame; earlier passes are noisier estimates of the same image
-    want64, rays64, _ = s.render(cam, w, h, 64)
+    assert spp == 272 and total == want_rays and (frames[-1] == want).all()
+    # the first 32 chunks are the 256 spp frame; earlier passes are noisier estimates of the same image
+    want256, rays256, _ = s.render(cam, w, h, 256)
     s.progressive_begin(w, h)
-    img, rays, _, spp = s.progressive_pass(cam, 8)
-    assert spp == 64 and rays == rays64 and (img == want64).all()
+    img, rays, _, spp = s.progressive_pass(cam, 32)
+    assert spp == 256 and rays == rays256 and (img == want256).all()
     err = [np.abs(f.astype(np.float64) - want).mean() for f in frames]
     assert err[0] > err[2] > err[-1] == 0.0
     with tm.Scene(sc["tris"]) as fresh:  # a pass without tmpt_progressive_begin is an argument error

@@ -3,5 +3,5 @@
 var=$1; shift
 for v in "$@"; do
   echo -n "$var=$v: "
-  env $var=$v python bench.py --steps 2 --warmup 3 2>/dev/null | tail -1 | python -c "import sys,json; d=json.loads(sys.stdin.read()); print('frame %8.1f Mrays/s  %7.1f ms' % (d['value'], d['ms_per_step']))"
+  env $var=$v python tools/exp_regen.py --scene sponza --width 1920 --height 1080 --spp 64 --reps 1 | sed -e 's/.*rays [0-9]* *//'
 done

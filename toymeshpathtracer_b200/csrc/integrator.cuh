@@ -106,13 +106,16 @@ TMPT_HD ex::V3 trace_path(const Scene& sc, const Camera& cam, ex::V3 o, ex::V3 d
 
 // The unit of parallel work: one CHUNK of a pixel's samples.  A chunk owns an XorShift32 stream
 // seeded from (chunk, pixel) and adds its samples in order; a pixel is the in-order sum of its
-// chunk sums (DESIGN.md "RNG").  The chunk length depends on spp only -- spp/8 clamped to
-// [1, 8] -- so a frame does not depend on how it is split over lanes or GPUs: 8 samples at the
-// headline 64 spp and above, ONE sample at 4 spp, where a 640x360 frame would otherwise have
-// 1.5 work items per resident warp (and 0.2 per warp on each of 8 GPUs).
+// chunk sums (DESIGN.md "RNG").  The chunk length depends on spp only -- spp/32 clamped to
+// [1, 8] -- so a frame does not depend on how it is split over lanes or GPUs.  Short chunks keep
+// the work items short: 2 samples at the headline 64 spp (with 8-sample chunks an item ran for
+// 4.4 ms, and on an 8-GPU split, 60 ms per frame, every GPU lost half an item at the end of its
+// share: 3.4 % of the frame), one sample below 64 spp (a 640x360x4 frame with four-sample items
+// has 1.5 of them per resident warp), 8 samples from 256 spp on, where chunk sums per pixel
+// would otherwise cost more memory than they save time.
 constexpr int kMaxChunkSamples = 8;
 TMPT_HD int chunk_len(int spp) {
-    const int c = spp / 8;
+    const int c = spp / 32;
     return c < 1 ? 1 : c > kMaxChunkSamples ? kMaxChunkSamples : c;
 }
 TMPT_HD int chunk_count(int spp) { const int c = chunk_len(spp); return (spp + c - 1) / c; }

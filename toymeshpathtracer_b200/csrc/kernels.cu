@@ -1340,12 +1340,19 @@ extern "C" int tmpt_stripe_rows(int height, int stripeRows, int rank, int worldS
 static ex::V3 host_light_dir() { return ex::normalize(ex::v3(-0.7f, 1.0f, 0.5f)); }  // main.cpp:36
 
 // Chunk sums go to an accumulation buffer when a pixel has more than one chunk; the frame is rendered in bands of
-// owned rows so that the buffer stays within a fixed budget (a whole 1080p x 64 spp frame is 265 MB).  Allocation
+// owned rows so that the buffer stays within a fixed budget (a whole 1080p x 64 spp frame, 32 chunks per pixel, is 1.06 GB; the budget is 4 GB).  Allocation
 // happens here so that callers can do it before their timed window starts.
+// samples per chunk / chunks per pixel of a one-shot frame (TMPT_CHUNK_LEN: tuning override, changes the RNG layout)
+static int host_chunk_len(int spp) {
+    static const int forced = getenv("TMPT_CHUNK_LEN") ? atoi(getenv("TMPT_CHUNK_LEN")) : 0;
+    return forced > 0 ? std::min(forced, integ::kMaxChunkSamples) : integ::chunk_len(spp);
+}
+static int host_chunk_count(int spp) { const int c = host_chunk_len(spp); return (spp + c - 1) / c; }
+
 static int prepare_render_chunks(tmpt_scene* s, int width, int chunks, bool forceAccum, int ownedRows, cudaStream_t st, int* outBandRows) {
     int bandRows = ownedRows;
     if ((chunks > 1 || forceAccum) && ownedRows > 0) {
-        const size_t rowBytes = (size_t)width * chunks * sizeof(float4), budget = (size_t)1 << 30;
+        const size_t rowBytes = (size_t)width * chunks * sizeof(float4), budget = (size_t)4 << 30;
         bandRows = (int)std::min<size_t>((size_t)ownedRows, std::max<size_t>(4, (budget / rowBytes) & ~(size_t)3));
         const size_t need = (size_t)bandRows * rowBytes;
         if (s->accumBytes < need) {
@@ -1359,7 +1366,7 @@ static int prepare_render_chunks(tmpt_scene* s, int width, int chunks, bool forc
     return TMPT_OK;
 }
 static int prepare_render(tmpt_scene* s, int width, int spp, int ownedRows, cudaStream_t st, int* outBandRows) {
-    return prepare_render_chunks(s, width, integ::chunk_count(spp), false, ownedRows, st, outBandRows);
+    return prepare_render_chunks(s, width, host_chunk_count(spp), false, ownedRows, st, outBandRows);
 }
 
 // One pass of a progressive render: chunks [chunk0, chunk0 + nChunks) of kMaxChunkSamples samples, added to `sum`.
@@ -1382,9 +1389,9 @@ static int launch_render(const tmpt_scene* cs, const tmpt_camera* camera, int wi
     p.stripeRows = stripeRows; p.rank = rank; p.world = world;
     p.ownedRows = tmpt_stripe_rows(height, stripeRows, rank, world);
     p.tilesX = div_up(width, 8);
-    p.chunks = prog ? prog->nChunks : integ::chunk_count(spp);
+    p.chunks = prog ? prog->nChunks : host_chunk_count(spp);
     p.chunk0 = prog ? prog->chunk0 : 0;
-    p.chunkLen = prog ? integ::kMaxChunkSamples : integ::chunk_len(spp);
+    p.chunkLen = prog ? integ::kMaxChunkSamples : host_chunk_len(spp);
     p.useAccum = (p.chunks > 1 || prog) ? 1 : 0;
     p.sumBuf = prog ? prog->sum : nullptr;
     p.outStripes = (uchar4*)outStripes;
