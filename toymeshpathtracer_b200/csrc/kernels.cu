@@ -1005,6 +1005,7 @@ int build_bvh(tmpt_scene* s, unsigned flags) {
         const uint32_t one = 1, zero = 0;
         CU_TRY(cudaMemcpyAsync(d_tqA, &rootTask, sizeof rootTask, cudaMemcpyHostToDevice, st));
         CU_TRY(cudaMemcpyAsync(d_nodeCounter, &one, 4, cudaMemcpyHostToDevice, st));
+        bool sahDone = false;
         if (coop) {
             // one cooperative launch for all levels (k_sah_build); d_qCount = three rotating task counters
             const uint32_t counts0[3] = {1u, 0u, 0u};
@@ -1019,9 +1020,16 @@ int build_bvh(tmpt_scene* s, unsigned flags) {
             int maxLevels = 4096;
             uint32_t* statusP = s->d_status + 1;
             void* args[] = {&t, &pLoP, &pHiP, &idxA, &idxB, &primFinalP, &qA, &qB, &countsP, &nodeCounterP, &sp, &maxLevels, &statusP};
-            CU_TRY(cudaLaunchCooperativeKernel((void*)k_sah_build, dim3(grid), dim3(SAH_THREADS), args, 0, st));
-            tmpt::count_launch();
-        } else {
+            // (a refused cooperative launch -- e.g. the device is shared and the grid cannot be co-resident -- is not an error:
+            //  nothing has run yet, the per-level loop below does the same work)
+            if (cudaLaunchCooperativeKernel((void*)k_sah_build, dim3(grid), dim3(SAH_THREADS), args, 0, st) == cudaSuccess) {
+                tmpt::count_launch();
+                sahDone = true;
+            } else {
+                cudaGetLastError();
+            }
+        }
+        if (!sahDone) {
             uint32_t* idxIn = d_primA; uint32_t* idxOut = d_primB;
             SahTask* qin = d_tqA; SahTask* qout = d_tqB;
             uint32_t count = 1;
@@ -1061,6 +1069,7 @@ int build_bvh(tmpt_scene* s, unsigned flags) {
         CU_TRY(cudaMemcpyAsync(d_qA, &root, sizeof root, cudaMemcpyHostToDevice, st));
         CU_TRY(cudaMemcpyAsync(d_counters, &one, 4, cudaMemcpyHostToDevice, st));   // wide node 0 is taken
         CU_TRY(cudaMemcpyAsync(d_qCount, &one, 4, cudaMemcpyHostToDevice, st));
+        bool collapseDone = false;
         if (coop) {
             const uint32_t counts0[3] = {1u, 0u, 0u};
             CU_TRY(cudaMemcpyAsync(d_qCount, counts0, sizeof counts0, cudaMemcpyHostToDevice, st));
@@ -1070,9 +1079,15 @@ int build_bvh(tmpt_scene* s, unsigned flags) {
             bld::WorkItem* qA = d_qA; bld::WorkItem* qB = d_qB;
             uint32_t* countsP = d_qCount;
             void* args[] = {&t, &w, &qA, &qB, &countsP};
-            CU_TRY(cudaLaunchCooperativeKernel((void*)k_collapse_all, dim3(grid), dim3(128), args, 0, st));
-            tmpt::count_launch();
-        } else {
+            if (cudaLaunchCooperativeKernel((void*)k_collapse_all, dim3(grid), dim3(128), args, 0, st) == cudaSuccess) {
+                tmpt::count_launch();
+                collapseDone = true;
+            } else {
+                cudaGetLastError();
+            }
+        }
+        if (!collapseDone) {
+            CU_TRY(cudaMemcpyAsync(d_qCount, &one, 4, cudaMemcpyHostToDevice, st));
             bld::WorkItem* qin = d_qA; bld::WorkItem* qout = d_qB;
             int cin = 0;
             uint32_t count = 1;
