@@ -1423,17 +1423,27 @@ static int launch_render(const tmpt_scene* cs, const tmpt_camera* camera, int wi
     p.accum = s->d_accum;
     // 256 threads x 4 CTAs/SM = 32 warps/SM at 64 registers (sweep in profiles/r1_tuning_sweeps.txt: 24 warps at
     // 77 registers is 10 % slower, 40 warps at 48 registers spills and is 3 % slower)
-    int perSM = 0;
-    CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, k_render<false, 256, 4>, 256, 0));
+    // 32 warps per SM at 64 registers (sweep in profiles/r1_tuning_sweeps.txt: 24 warps at 77 registers is 10 % slower, 40
+    // warps at 48 registers spills and is 3 % slower), as ONE 1024-thread CTA per SM when the band has work for every SM
+    // several times over (+1.6 % over four 256-thread CTAs: 5016 vs 4937 Mrays/s), as 256-thread CTAs for small frames, whose
+    // few hundred warp items would otherwise land on a few SMs.  TMPT_RENDER_CFG (tuning): 1 = 256 x 4, 2 = 512 x 2, 3 = 1024 x 1.
+    static const int cfgEnv = getenv("TMPT_RENDER_CFG") ? atoi(getenv("TMPT_RENDER_CFG")) : 0;
+    // TMPT_RENDER_KERNEL: 0 = lockstep lanes (k_render), 1.. = per-lane ray regeneration with gate sizes (TA, TB)
+    static const int rk = getenv("TMPT_RENDER_KERNEL") ? atoi(getenv("TMPT_RENDER_KERNEL")) : 0;
+    int perSM256 = 0, perSM512 = 0, perSM1024 = 0;
+    CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM256, k_render<false, 256, 4>, 256, 0));
+    CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM512, k_render<false, 512, 2>, 512, 0));
+    CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM1024, k_render<false, 1024, 1>, 1024, 0));
     for (p.bandRow0 = 0; p.bandRow0 < p.ownedRows; p.bandRow0 += bandRows) {
         const int rowsHere = std::min(bandRows, p.ownedRows - p.bandRow0);
         p.numTiles = p.tilesX * div_up(rowsHere, 4);
         const long long items = (long long)p.numTiles * p.chunks;
         if (items >= 0xFFFFFFFFll) return tmpt::fail(TMPT_ERR_ARG, "render: too many work items in one band");
         CU_TRY(cudaMemsetAsync(s->d_tileCounter, 0, sizeof(uint32_t), st));
-        const int grid = (int)std::min<long long>((long long)s->smCount * std::max(perSM, 1), (items + 7) / 8);
-        // TMPT_RENDER_KERNEL: 0 = lockstep lanes (k_render), 1.. = per-lane ray regeneration with gate sizes (TA, TB)
-        static const int rk = getenv("TMPT_RENDER_KERNEL") ? atoi(getenv("TMPT_RENDER_KERNEL")) : 0;
+        const int cfg = (statsDev || rk > 0) ? 1 : cfgEnv > 0 ? cfgEnv : (items >= (long long)s->smCount * 32 * 8 && perSM1024 > 0) ? 3 : 1;
+        const int threads = cfg == 3 ? 1024 : cfg == 2 ? 512 : 256;
+        const int perSM = cfg == 3 ? perSM1024 : cfg == 2 ? perSM512 : perSM256;
+        const int grid = (int)std::min<long long>((long long)s->smCount * std::max(perSM, 1), (items + threads / 32 - 1) / (threads / 32));
         if (rk > 0 && !statsDev) {
             CU_TRY(cudaMemsetAsync(s->d_fetchCounter, 0, sizeof(unsigned long long), st));
             int perSMr = 0;
@@ -1447,6 +1457,8 @@ static int launch_render(const tmpt_scene* cs, const tmpt_camera* camera, int wi
 #undef REGEN_CASE
             return tmpt::fail(TMPT_ERR_ARG, "TMPT_RENDER_KERNEL=%d: no such render kernel", rk);
         } else if (statsDev) LAUNCH((k_render<true, 256, 4>), grid, 256, 0, st, p);
+        else if (cfg == 3) LAUNCH((k_render<false, 1024, 1>), grid, 1024, 0, st, p);
+        else if (cfg == 2) LAUNCH((k_render<false, 512, 2>), grid, 512, 0, st, p);
         else LAUNCH((k_render<false, 256, 4>), grid, 256, 0, st, p);
         if (p.useAccum) LAUNCH(k_resolve, div_up((long long)rowsHere * width, 256), 256, 0, st, p, rowsHere);
     }
