@@ -353,7 +353,7 @@ def bench_b200(args, scene, w, h, spp, rank, world, local_rank):
         kernel_ms = statistics.mean(step_ms)
         traffic = None
         try:  # dram__bytes_read + dram__bytes_write of this kernel on this workload, from the committed ncu capture
-            tj = json.load(open(os.path.join(ROOT, "profiles", "r1g_traffic.json")))["k_render"]
+            tj = json.load(open(os.path.join(ROOT, "profiles", "r1h_traffic.json")))["k_render"]
             if args.workload == "sponza_1080p_64spp" and world == 1:
                 traffic = tj["dram_bytes_read"] + tj["dram_bytes_write"]
         except (OSError, KeyError, ValueError):

@@ -715,8 +715,8 @@ struct RenderParams {
     int chunk0, chunkLen; // first chunk index (progressive passes continue where the last one stopped), samples per chunk
     int useAccum;        // chunk sums go through `accum` + k_resolve (more than one chunk, or a progressive pass)
     float4* sumBuf;      // progressive: running per-pixel sums of the whole frame (null for a one-shot frame)
-    int bandRow0;        // first owned row of the band being rendered (the accumulation buffer covers one band)
-    float4* accum;       // [bandRows][width][chunks] chunk sums, when chunks > 1
+    int bandRow0, bandRows;  // first owned row and row count of the band being rendered (the accumulation buffer covers one band)
+    float4* accum;       // [chunks][bandRows][width] chunk sums (chunk-major planes: full-line stores, no read-modify-write in HBM)
     uchar4* outStripes;  // packed owned rows, or
     uchar4* frame;       // full frame (possibly peer memory)
     unsigned long long* rayCount;
@@ -748,7 +748,7 @@ __global__ void __launch_bounds__(THREADS, MINB) k_render(const RenderParams p) 
             const int y = owned_row_to_global(r, p.stripeRows, p.rank, p.world);
             const ex::V3 sum = integ::render_chunk<STATS>(p.sc, p.cam, x, y, p.chunk0 + chunk, p.width, p.height, p.spp, p.chunkLen, p.lightDir, rays, &ts);
             if (p.useAccum) {
-                p.accum[((size_t)rb * p.width + x) * p.chunks + chunk] = make_float4(sum.x, sum.y, sum.z, 0.0f);
+                p.accum[((size_t)chunk * p.bandRows + rb) * p.width + x] = make_float4(sum.x, sum.y, sum.z, 0.0f);
             } else {
                 const uchar4 px = integ::resolve_pixel(sum, ex::divf(1.0f, (float)p.spp));
                 if (p.frame) p.frame[(size_t)y * p.width + x] = px;
@@ -821,7 +821,7 @@ __global__ void __launch_bounds__(THREADS, MINB) k_render_regen(const RenderPara
                     sum = ex::add(sum, color);
                     if (++s == sEnd) {
                         if (p.useAccum) {
-                            p.accum[((size_t)rb * p.width + x) * p.chunks + chunk] = make_float4(sum.x, sum.y, sum.z, 0.0f);
+                            p.accum[((size_t)chunk * p.bandRows + rb) * p.width + x] = make_float4(sum.x, sum.y, sum.z, 0.0f);
                         } else {
                             const uchar4 px = integ::resolve_pixel(sum, ex::divf(1.0f, (float)p.spp));
                             if (p.frame) p.frame[(size_t)y * p.width + x] = px;
@@ -893,10 +893,11 @@ __global__ void k_resolve(const RenderParams p, int bandRows) {
     if (i >= (long long)bandRows * p.width) return;
     const int rb = (int)(i / p.width), x = (int)(i - (long long)rb * p.width), r = p.bandRow0 + rb;
     const size_t pix = (size_t)owned_row_to_global(r, p.stripeRows, p.rank, p.world) * p.width + x;
-    const float4* a = p.accum + (size_t)i * p.chunks;
+    const size_t plane = (size_t)bandRows * p.width;  // chunk-major planes: a warp's stores and these loads cover whole lines
+    const float4* a = p.accum + i;
     ex::V3 sum = ex::v3(0.0f, 0.0f, 0.0f);
     if (p.sumBuf) { const float4 v = p.sumBuf[pix]; sum = ex::v3(v.x, v.y, v.z); }  // progressive: the chunks before this pass
-    for (int c = 0; c < p.chunks; ++c) { const float4 v = a[c]; sum = ex::add(sum, ex::v3(v.x, v.y, v.z)); }
+    for (int c = 0; c < p.chunks; ++c) { const float4 v = a[(size_t)c * plane]; sum = ex::add(sum, ex::v3(v.x, v.y, v.z)); }
     if (p.sumBuf) p.sumBuf[pix] = make_float4(sum.x, sum.y, sum.z, 0.0f);
     const uchar4 px = integ::resolve_pixel(sum, ex::divf(1.0f, (float)p.spp));
     if (p.frame) p.frame[pix] = px;
@@ -1436,6 +1437,7 @@ static int launch_render(const tmpt_scene* cs, const tmpt_camera* camera, int wi
     CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM1024, k_render<false, 1024, 1>, 1024, 0));
     for (p.bandRow0 = 0; p.bandRow0 < p.ownedRows; p.bandRow0 += bandRows) {
         const int rowsHere = std::min(bandRows, p.ownedRows - p.bandRow0);
+        p.bandRows = rowsHere;
         p.numTiles = p.tilesX * div_up(rowsHere, 4);
         const long long items = (long long)p.numTiles * p.chunks;
         if (items >= 0xFFFFFFFFll) return tmpt::fail(TMPT_ERR_ARG, "render: too many work items in one band");
