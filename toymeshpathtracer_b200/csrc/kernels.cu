@@ -748,7 +748,7 @@ __global__ void __launch_bounds__(THREADS, MINB) k_render(const RenderParams p) 
             const int y = owned_row_to_global(r, p.stripeRows, p.rank, p.world);
             const ex::V3 sum = integ::render_chunk<STATS>(p.sc, p.cam, x, y, p.chunk0 + chunk, p.width, p.height, p.spp, p.chunkLen, p.lightDir, rays, &ts);
             if (p.useAccum) {
-                p.accum[((size_t)chunk * p.bandRows + rb) * p.width + x] = make_float4(sum.x, sum.y, sum.z, 0.0f);
+                __stcs(&p.accum[((size_t)chunk * p.bandRows + rb) * p.width + x], make_float4(sum.x, sum.y, sum.z, 0.0f));  // streaming: read once, by k_resolve
             } else {
                 const uchar4 px = integ::resolve_pixel(sum, ex::divf(1.0f, (float)p.spp));
                 if (p.frame) p.frame[(size_t)y * p.width + x] = px;
@@ -821,7 +821,7 @@ __global__ void __launch_bounds__(THREADS, MINB) k_render_regen(const RenderPara
                     sum = ex::add(sum, color);
                     if (++s == sEnd) {
                         if (p.useAccum) {
-                            p.accum[((size_t)chunk * p.bandRows + rb) * p.width + x] = make_float4(sum.x, sum.y, sum.z, 0.0f);
+                            __stcs(&p.accum[((size_t)chunk * p.bandRows + rb) * p.width + x], make_float4(sum.x, sum.y, sum.z, 0.0f));  // streaming: read once, by k_resolve
                         } else {
                             const uchar4 px = integ::resolve_pixel(sum, ex::divf(1.0f, (float)p.spp));
                             if (p.frame) p.frame[(size_t)y * p.width + x] = px;
@@ -897,7 +897,7 @@ __global__ void k_resolve(const RenderParams p, int bandRows) {
     const float4* a = p.accum + i;
     ex::V3 sum = ex::v3(0.0f, 0.0f, 0.0f);
     if (p.sumBuf) { const float4 v = p.sumBuf[pix]; sum = ex::v3(v.x, v.y, v.z); }  // progressive: the chunks before this pass
-    for (int c = 0; c < p.chunks; ++c) { const float4 v = a[(size_t)c * plane]; sum = ex::add(sum, ex::v3(v.x, v.y, v.z)); }
+    for (int c = 0; c < p.chunks; ++c) { const float4 v = __ldcs(&a[(size_t)c * plane]); sum = ex::add(sum, ex::v3(v.x, v.y, v.z)); }
     if (p.sumBuf) p.sumBuf[pix] = make_float4(sum.x, sum.y, sum.z, 0.0f);
     const uchar4 px = integ::resolve_pixel(sum, ex::divf(1.0f, (float)p.spp));
     if (p.frame) p.frame[pix] = px;
