@@ -264,6 +264,14 @@ class Scene:
         _check(lib().tmpt_progressive_pass(self._h, _ptr(cam), n_chunks, HOST, _ptr(rgba), C.byref(rays), C.byref(sec), C.byref(spp), None))
         return rgba, rays.value, sec.value, spp.value
 
+    def render_into(self, camera, width: int, height: int, spp: int, host_ptr: int):
+        """One frame into caller-owned HOST memory (w*h*4 bytes, e.g. a pinned buffer) -> (rayCount, seconds): tmpt_render as a
+        C caller uses it, without this binding allocating the frame."""
+        cam = _f32(camera).reshape(22)
+        rays, sec = C.c_uint64(0), C.c_double(0.0)
+        _check(lib().tmpt_render(self._h, _ptr(cam), width, height, spp, HOST, host_ptr, C.byref(rays), C.byref(sec), None))
+        return rays.value, sec.value
+
     def traversal_stats(self, camera, width: int, height: int, spp: int) -> dict:
         """Instrumented render pass -> mean box / triangle tests per ray (bench.py's roofline figures)."""
         cam = _f32(camera).reshape(22)
