@@ -21,7 +21,7 @@
 extern "C" {
 #endif
 
-#define TMPT_ABI_VERSION 1
+#define TMPT_ABI_VERSION 2
 
 typedef enum tmpt_status {
     TMPT_OK = 0,
@@ -168,12 +168,19 @@ int tmpt_frame_close(int device, void* ptr);   /* for pointers from tmpt_frame_o
 int tmpt_frame_free(int device, void* ptr);    /* for pointers from tmpt_frame_alloc */
 
 /* Instrumented passes: the same kernels compiled with work counters, for the roofline's
- * per-ray figures (never part of a timed run).  outStats: [0] rays (HitScene-equivalent
- * queries), [1] wide BVH nodes visited (4 box tests each), [2] exact triangle tests,
- * [3] hits (tmpt_hit_scene_stats only).  rays6Dev is a DEVICE pointer. */
-int tmpt_render_stats(const tmpt_scene* scene, const tmpt_camera* camera, int width, int height, int spp, uint64_t outStats[4]);
+ * per-ray figures (never part of a timed run).  outStats (TMPT_STATS_COUNT entries): [0] rays
+ * (HitScene-equivalent queries), [1] wide BVH nodes visited (4 box tests each), [2] exact
+ * triangle tests, [3] hits (tmpt_hit_scene_stats only), [4] walk iterations summed over lanes,
+ * [5] pops of entries the best t had already culled, [6] lane iterations spent waiting at a
+ * leaf while the parked one was tested, [7] warp iterations with a node step, [8] with a
+ * triangle test, [9] warp iterations in all ([4] / (32 * [9]) = share of lane slots that held
+ * an unfinished ray), [10] rays traced twice because their shared-memory stack overflowed,
+ * [11..15] rays whose stack held more than 4 / 8 / 12 / 16 / 24 entries at some point.
+ * rays6Dev is a DEVICE pointer. */
+#define TMPT_STATS_COUNT 16
+int tmpt_render_stats(const tmpt_scene* scene, const tmpt_camera* camera, int width, int height, int spp, uint64_t outStats[TMPT_STATS_COUNT]);
 int tmpt_hit_scene_stats(const tmpt_scene* scene, const float* rays6Dev, int64_t nRays, float tMin, float tMax, int mode,
-                         uint64_t outStats[4]);
+                         uint64_t outStats[TMPT_STATS_COUNT]);
 
 /* ---- host glue that main() does around the hot path ---- */
 /* LoadScene (main.cpp:122-170): parse the OBJ like external/objparser.cpp, build Triangle[]

@@ -125,6 +125,20 @@ static v3 random_unit_vector(uint32_t* state, int trig) { /* maths.cpp:30-38; kP
  * row seed expression (main.cpp:204) applied to the pixel index, scrambled with
  * Wang's 32-bit hash so neighbouring pixels decorrelate, never 0 (xorshift fixed
  * point).  DESIGN.md "RNG". */
+uint32_t orc_stream_seed(uint64_t streamIndex) {
+    /* The stream index chunk * width * height + pixelIndex needs more than 32 bits for large frames at high spp
+     * (10000 x 10000 from chunk 43 on) and for long progressive renders: the high word is folded in before the
+     * hash, so that streams beyond 2^32 do not repeat the first 2^32 in order; below 2^32 (hi = 0) this is
+     * orc_pixel_seed of the index. */
+    const uint32_t lo = (uint32_t)streamIndex, hi = (uint32_t)(streamIndex >> 32);
+    uint32_t s = (lo * 9781u + 1u) ^ (hi * 0x9E3779B9u);
+    s = (s ^ 61u) ^ (s >> 16);
+    s *= 9u;
+    s ^= s >> 4;
+    s *= 0x27d4eb2du;
+    s ^= s >> 15;
+    return s ? s : 1u;
+}
 uint32_t orc_pixel_seed(uint32_t pixelIndex) {
     uint32_t s = pixelIndex * 9781u + 1u;
     s = (s ^ 61u) ^ (s >> 16);
@@ -379,7 +393,7 @@ static void render_row(render_job* j, int y, int64_t* rayCount) { /* main.cpp:20
         const int chunkLen = j->rngMode == ORC_RNG_PIXEL ? ORC_CHUNK_SAMPLES(j->spp) : j->spp;
         for (int s0 = 0, c = 0; s0 < j->spp; s0 += chunkLen, ++c) {
             if (j->rngMode == ORC_RNG_PIXEL)
-                rng = orc_pixel_seed((uint32_t)c * ((uint32_t)j->w * (uint32_t)j->h) + (uint32_t)y * (uint32_t)j->w + (uint32_t)x);
+                rng = orc_stream_seed((uint64_t)c * ((uint64_t)j->w * (uint64_t)j->h) + (uint64_t)y * (uint64_t)j->w + (uint64_t)x);
             v3 chunk = V(0.0f, 0.0f, 0.0f);
             const int s1 = s0 + chunkLen < j->spp ? s0 + chunkLen : j->spp;
             for (int s = s0; s < s1; ++s) {

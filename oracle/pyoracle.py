@@ -56,6 +56,7 @@ class Oracle:
         L.orc_random_unit_vectors.restype = C.c_uint32
         L.orc_camera_get_rays.restype = C.c_uint32
         L.orc_pixel_seed.restype = C.c_uint32
+        L.orc_stream_seed.restype = C.c_uint32
         L.orc_add_floor.restype = C.c_int
         self.threads = int(os.environ.get("ORACLE_THREADS", os.cpu_count() or 1))
 
@@ -85,6 +86,9 @@ class Oracle:
 
     def pixel_seed(self, idx):
         return self.L.orc_pixel_seed(C.c_uint32(idx))
+
+    def stream_seed(self, idx64):
+        return self.L.orc_stream_seed(C.c_uint64(idx64))
 
     def camera_make(self, frm, at, up, vfov, aspect, aperture, focus):
         out = np.zeros(22, np.float32)

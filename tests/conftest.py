@@ -58,3 +58,18 @@ def bits(a):
 def from_bits(lst, shape=None):
     a = np.array(lst, dtype=np.uint32).view(np.float32)
     return a.reshape(shape) if shape else a
+
+
+_SPONZA = None
+
+
+def sponza_scene(kat=None):
+    """The Sponza stand-in exactly as LoadScene builds it from tools/gen_sponza.py's file (model + the two floor triangles):
+    (tris, boundsMin, boundsMax).  The triangle bytes are pinned by kat.json["sponza"]["tris_sha256"], recorded when the
+    reference itself loaded the same file (oracle/gen_golden.py --sponza)."""
+    global _SPONZA
+    if _SPONZA is None:
+        from oracle.pyoracle import Oracle
+        from tools.gen_sponza import triangles
+        _SPONZA = Oracle().add_floor(triangles())
+    return _SPONZA

@@ -275,4 +275,5 @@ void emu_render_stats(void* h, const float cam22[22], int w, int hgt, int spp, u
 
 void emu_sincos(float a, float* s, float* c) { ex::sincos_spec(a, *s, *c); }
 uint32_t emu_pixel_seed(uint32_t i) { return ex::pixel_seed(i); }
+uint32_t emu_chunk_seed(uint32_t chunk, uint32_t pixel, uint32_t pixels) { return ex::chunk_seed(chunk, pixel, pixels); }
 }

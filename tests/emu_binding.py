@@ -42,6 +42,7 @@ class Emu:
         self.L.emu_scene_create.restype = C.c_void_p
         self.L.emu_scene_create2.restype = C.c_void_p
         self.L.emu_pixel_seed.restype = C.c_uint32
+        self.L.emu_chunk_seed.restype = C.c_uint32
 
     def scene(self, tris, builder=0, c_inner=1.0, c_tri=1.0, max_leaf=8):
         """builder 0 = binned SAH (the default of the product), 1 = LBVH"""

@@ -70,12 +70,14 @@ def lib() -> C.CDLL:
     if _lib is not None:
         return _lib
     from . import build as _build
-    try:
-        _build.build()
-    except Exception:
-        if not os.path.exists(LIB_PATH):
-            raise
-    L = C.CDLL(LIB_PATH)
+    path = os.environ.get("TMPT_LIB") or LIB_PATH  # TMPT_LIB: another build of the same ABI (build.build_variant), for A/B runs
+    if path == LIB_PATH:
+        try:
+            _build.build()
+        except Exception:
+            if not os.path.exists(LIB_PATH):
+                raise
+    L = C.CDLL(path)
     vp, i32, i64, f32 = C.c_void_p, C.c_int, C.c_int64, C.c_float
     L.tmpt_scene_create.argtypes = [vp, i32, i32, C.c_uint, C.POINTER(vp)]
     L.tmpt_scene_destroy.argtypes = [vp]
@@ -118,6 +120,22 @@ def _check(rc):
 
 def _f32(a):
     return np.ascontiguousarray(a, dtype=np.float32)
+
+
+STATS_COUNT = 16  # TMPT_STATS_COUNT
+
+
+def _stats_dict(st) -> dict:
+    """Counters of an instrumented pass (include/tmpt.h) -> per-ray figures and how the warps spent their iterations."""
+    v = [int(x) for x in st]
+    rays, witers = max(v[0], 1), max(v[9], 1)
+    return {"rays": v[0], "node_visits_per_ray": v[1] / rays, "box_tests_per_ray": 4.0 * v[1] / rays, "tri_tests_per_ray": v[2] / rays,
+            "lane_iters_per_ray": v[4] / rays, "culled_pops_per_ray": v[5] / rays, "leaf_waits_per_ray": v[6] / rays,
+            "warp_iters_per_ray": v[9] / rays,
+            "lanes_with_a_ray": v[4] / witers,                       # of 32, averaged over warp iterations
+            "lanes_per_node_step": v[1] / max(v[7], 1), "lanes_per_tri_test": v[2] / max(v[8], 1),
+            "warp_iters_with_node_step": v[7] / witers, "warp_iters_with_tri_test": v[8] / witers,
+            "stack_overflow_rays": v[10] / rays, "stack_deeper_than": {str(k): v[11 + i] / rays for i, k in enumerate((4, 8, 12, 16, 24))}}
 
 
 def _ptr(a):
@@ -275,17 +293,16 @@ class Scene:
     def traversal_stats(self, camera, width: int, height: int, spp: int) -> dict:
         """Instrumented render pass -> mean box / triangle tests per ray (bench.py's roofline figures)."""
         cam = _f32(camera).reshape(22)
-        st = np.zeros(4, np.uint64)
+        st = np.zeros(STATS_COUNT, np.uint64)
         _check(lib().tmpt_render_stats(self._h, _ptr(cam), width, height, spp, _ptr(st)))
-        rays = max(int(st[0]), 1)
-        return {"rays": int(st[0]), "node_visits_per_ray": int(st[1]) / rays, "box_tests_per_ray": 4.0 * int(st[1]) / rays,
-                "tri_tests_per_ray": int(st[2]) / rays}
+        return _stats_dict(st)
 
     def hit_scene_stats(self, rays_ptr: int, n: int, mode: int = HIT_CLOSEST, tMin: float = K_MIN_T, tMax: float = K_MAX_T) -> dict:
-        st = np.zeros(4, np.uint64)
+        st = np.zeros(STATS_COUNT, np.uint64)
         _check(lib().tmpt_hit_scene_stats(self._h, rays_ptr, n, tMin, tMax, mode, _ptr(st)))
-        rays = max(int(st[0]), 1)
-        return {"rays": int(st[0]), "node_visits_per_ray": int(st[1]) / rays, "tri_tests_per_ray": int(st[2]) / rays, "hit_rate": int(st[3]) / rays}
+        d = _stats_dict(st)
+        d["hit_rate"] = int(st[3]) / max(int(st[0]), 1)
+        return d
 
     def render_device(self, camera, width: int, height: int, spp: int, frame_ptr: int, stream: int = 0):
         """One frame into a device buffer (w*h*4 bytes) -> (rayCount, seconds)."""

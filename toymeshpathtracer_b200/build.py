@@ -64,5 +64,23 @@ def build(force: bool = False) -> str:
     return LIB
 
 
+def build_variant(tag: str, defines, force: bool = False) -> str:
+    """A second build of the same sources with compile-time switches -> libtmpt_<tag>.so (selected with TMPT_LIB=<path>).
+    Used for the experiments build (-DTMPT_EXPERIMENTS=1: kernels that were measured and not adopted) and for A/B runs."""
+    lib = os.path.join(HERE, f"libtmpt_{tag}.so")
+    if not force and not _stale(lib):
+        return lib
+    if not os.path.exists(NVCC):
+        raise RuntimeError(f"nvcc not found at {NVCC} and {lib} is missing or stale")
+    obj_dir = os.path.join(HERE, "build")
+    os.makedirs(obj_dir, exist_ok=True)
+    k_o, h_o = os.path.join(obj_dir, f"kernels_{tag}.o"), os.path.join(obj_dir, "host.o")
+    _run([NVCC, *ARCH, *CUFLAGS, *defines, "-c", os.path.join(CSRC, "kernels.cu"), "-o", k_o], log=os.path.join(obj_dir, f"ptxas_{tag}.log"))
+    if not os.path.exists(h_o) or _stale(h_o):
+        _run(["g++", *CXXFLAGS, "-c", os.path.join(CSRC, "host.cpp"), "-o", h_o])
+    _run([NVCC, *ARCH, "-shared", "-cudart", "static", "-o", lib, k_o, h_o])
+    return lib
+
+
 if __name__ == "__main__":
     print(build(force="--force" in sys.argv))

@@ -73,11 +73,28 @@ struct HitRec {
 
 // maths.cpp:339-380 on a precomputed (v0, e1, e2) slot.  Returns true iff the reference's
 // function would return true for [tMin, tMax]; t/u/v get the reference's bits.
+#ifndef TMPT_TRI_FLAT
+#define TMPT_TRI_FLAT 0
+#endif
 TMPT_HD bool mt_exact(ex::V3 o, ex::V3 d, ex::V3 v0, ex::V3 e1, ex::V3 e2, float tMin, float tMax,
                       float& t, float& u, float& v) {
     const float Epsilon = 1e-5f;
     ex::V3 pvec = ex::cross(d, e2);
     float det = ex::dot(e1, pvec);
+#if TMPT_TRI_FLAT
+    // Straight-line form: the reference's four exits (maths.cpp:350-351, 358-359, 365-366, 371) are evaluated on the same
+    // values and OR-ed.  A warp leaves the sequential form early only when EVERY lane fails the same test, which with 5-10
+    // lanes per test almost never happens, so the exits only cost branches and reconvergence points.  Values computed
+    // past a failed test are garbage (possibly NaN / Inf) and never used: the function's result is `false`.
+    const float invDet = ex::rcp(det);
+    const ex::V3 tvec = ex::sub(o, v0);
+    u = ex::mul(ex::dot(tvec, pvec), invDet);
+    const ex::V3 qvec = ex::cross(tvec, e1);
+    v = ex::mul(ex::dot(d, qvec), invDet);
+    t = ex::mul(ex::dot(e2, qvec), invDet);
+    const bool reject = (det > -Epsilon && det < Epsilon) | (u < 0.0f) | (u > 1.0f) | (v < 0.0f) | (ex::add(u, v) > 1.0f);
+    return !reject & (t >= tMin) & (t <= tMax);
+#else
     // The determinant test (maths.cpp:350-351) and the u test (:358-359) share ONE exit: the same values in the
     // same order decide, but v0 is needed before the first branch, so the compiler cannot sink the triangle's
     // first row below it and turn one memory round trip into two dependent ones.  (A near-zero det -- under
@@ -91,6 +108,7 @@ TMPT_HD bool mt_exact(ex::V3 o, ex::V3 d, ex::V3 v0, ex::V3 e1, ex::V3 e2, float
     if (v < 0.0f || ex::add(u, v) > 1.0f) return false;
     t = ex::mul(ex::dot(e2, qvec), invDet);
     return t >= tMin && t <= tMax;
+#endif
 }
 
 // Hit.pos / Hit.normal exactly as maths.cpp:374-375 forms them, from the ORIGINAL vertices.
@@ -117,11 +135,74 @@ TMPT_HD void hit_payload(const SceneView& sc, int id, float u, float v, ex::V3& 
 // test an axis-parallel ray needs.
 TMPT_HD float safe_dir(float d) { return fabsf(d) < 1.0e-20f ? copysignf(1.0e-20f, d) : d; }
 
-// Work counters of an instrumented pass (bench.py's roofline: box and triangle tests per ray).
+// Work counters of an instrumented pass (bench.py's roofline: box and triangle tests per ray; the rest describes how the
+// lanes of a warp spend the iterations of the walk -- DESIGN.md 5).
 struct TravStats {
-    unsigned long long nodes = 0;  // wide nodes visited (4 box tests each)
-    unsigned long long tris = 0;   // exact triangle tests
+    unsigned long long nodes = 0;      // wide nodes visited (4 box tests each)
+    unsigned long long tris = 0;       // exact triangle tests
+    unsigned long long iters = 0;      // walk iterations of this lane (one node step and / or one triangle test and / or one pop each)
+    unsigned long long culledPops = 0; // pops whose entry the current best t had already culled (the lane sits out the next node step)
+    unsigned long long leafWaits = 0;  // iterations in which the lane stood at a leaf while its parked leaf was still being tested
+    unsigned long long nodeWarps = 0;  // iterations in which at least one lane of the warp made a node step (counted by one lane)
+    unsigned long long triWarps = 0;   // ... at least one lane tested a triangle
+    unsigned long long warpIters = 0;  // iterations of the warp (counted by one lane): warpIters * 32 = lane slots issued
+    unsigned long long overflows = 0;  // rays whose short stack (SmemStack) overflowed and were traced again
+    unsigned long long depthOver[5] = {0, 0, 0, 0, 0};  // rays whose stack held more than 4 / 8 / 12 / 16 / 24 entries at some point
+    int maxSp = 0;                     // (scratch: deepest stack of the ray being traced)
 };
+
+// ---- traversal stack -------------------------------------------------------------------------------------------------
+// 64-bit entries, (entry distance bits << 32) | child ref.  LocalStack is a per-thread array (local memory: L1-cached,
+// lane-interleaved); SmemStack is the shared-memory short stack.
+struct LocalStack {
+    static constexpr bool kCanOverflow = false;
+    unsigned long long e[STACK_SIZE];
+    // store entry i if `push`; returns whether the stack grew (the builder guarantees i < STACK_SIZE, kernels.cu: build_bvh)
+    TMPT_HD bool put_if(bool push, int i, unsigned long long v) {
+        if (push) e[i] = v;
+        return push;
+    }
+    TMPT_HD unsigned long long get(int i) const { return *(const volatile unsigned long long*)&e[i]; }  // volatile: issue the load where it is written
+    TMPT_HD bool overflowed() const { return false; }
+    TMPT_HD void reset() {}
+};
+// The short stack north_star names: S entries per lane in SHARED memory, entry-major and lane-interleaved ([entry][thread]:
+// any mix of stack depths in a warp is bank-conflict free; in local memory every distinct depth is another 128-byte line
+// through the L1 data stage, and the stack lines compete with the nodes for L1).  There is no spill path in the walk: a
+// push beyond S entries is DROPPED and remembered, and the ray is then traced again with a LocalStack (traverse_with) --
+// exactness never depends on S, only the share of rays that pay twice does (tmpt_render_stats reports the depth histogram).
+template <int S, int STRIDE>
+struct SmemStack {
+    static constexpr bool kCanOverflow = true;
+    uint32_t col;  // shared-window address of this thread's column: entry i at col + i * STRIDE * 8.  Produced by an opaque
+                   // asm move (make()), because the compiler otherwise recomputes it from %tid and the window base at every
+                   // access -- five instructions per push -- instead of holding one register.
+    bool ovf;
+#ifdef __CUDA_ARCH__
+    static __device__ __forceinline__ SmemStack make(const void* smemBase, uint32_t thread) {
+        uint32_t a = (uint32_t)__cvta_generic_to_shared(smemBase) + thread * 8u, held;
+        asm volatile("mov.u32 %0, %1;" : "=r"(held) : "r"(a));
+        return SmemStack{held, false};
+    }
+    __device__ __forceinline__ bool put_if(bool push, int i, unsigned long long v) {
+        const bool ok = push && i < S;
+        if (ok) asm volatile("st.shared.u64 [%0], %1;" ::"r"(col + (uint32_t)i * (uint32_t)(STRIDE * 8)), "l"(v) : "memory");
+        ovf = ovf || (push && !ok);
+        return ok;
+    }
+    __device__ __forceinline__ unsigned long long get(int i) const {
+        unsigned long long v;
+        asm volatile("ld.shared.u64 %0, [%1];" : "=l"(v) : "r"(col + (uint32_t)i * (uint32_t)(STRIDE * 8)) : "memory");
+        return v;
+    }
+#else
+    bool put_if(bool, int, unsigned long long) { return false; }
+    unsigned long long get(int) const { return 0; }
+#endif
+    TMPT_HD bool overflowed() const { return ovf; }
+    TMPT_HD void reset() { ovf = false; }
+};
+
 
 // 128-bit loads through the read-only path (ld.global.nc), spelled as asm so that every row is one
 // LDG.E.128 exactly where it is written as far as the front end is concerned.  (ptxas still schedules
@@ -188,7 +269,8 @@ TMPT_HD RayCtx make_ray_ctx(ex::V3 o, ex::V3 d) {
 // boolean) cannot depend on the order.
 // The part of a node step that follows the four slab tests: a[k] / b[k] = entry / exit distance of child k (already
 // clipped to [tMin, bestT]), ref[k] its reference.
-TMPT_HD uint32_t enter_and_push(const float (&a)[4], const float (&b)[4], const uint32_t (&ref)[4], unsigned long long* stack, int& sp, bool anyRay) {
+template <class Stack>
+TMPT_HD uint32_t enter_and_push(const float (&a)[4], const float (&b)[4], const uint32_t (&ref)[4], Stack& stack, int& sp, bool anyRay) {
     uint32_t key[4], okey[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
@@ -206,8 +288,7 @@ TMPT_HD uint32_t enter_and_push(const float (&a)[4], const float (&b)[4], const 
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
         const bool push = key[k] != 0xFFFFFFFFu && (uint32_t)k != ks;  // (all keys empty -> nothing is pushed)
-        if (push) stack[sp] = ((unsigned long long)key[k] << 32) | ref[k];
-        sp += push ? 1 : 0;
+        sp += stack.put_if(push, sp, ((unsigned long long)key[k] << 32) | ref[k]) ? 1 : 0;
     }
     // a two-level select: the chain "ks == 0 ? .. : ks == 1 ? .." compiled to branches and a reconvergence point (+2.2 %)
     const uint32_t r01 = (ks & 1u) ? ref[1] : ref[0], r23 = (ks & 1u) ? ref[3] : ref[2];
@@ -215,7 +296,8 @@ TMPT_HD uint32_t enter_and_push(const float (&a)[4], const float (&b)[4], const 
     return kmin == 0xFFFFFFFFu ? NONE : nearest;
 }
 
-TMPT_HD uint32_t wide_node_step(const SceneView& sc, uint32_t node, const RayCtx& r, float tMin, float bestT, unsigned long long* stack, int& sp,
+template <class Stack>
+TMPT_HD uint32_t wide_node_step(const SceneView& sc, uint32_t node, const RayCtx& r, float tMin, float bestT, Stack& stack, int& sp,
                                 bool anyRay) {
     const uint32_t row0 = node * (uint32_t)NODE_F4;
     const float4 nx = ld_row(sc.nodes + (row0 + r.sx)), fx = ld_row(sc.nodes + (row0 + (r.sx ^ 1u)));
@@ -282,7 +364,8 @@ TMPT_HD void qchild(uint32_t one, uint32_t nxw, uint32_t nyw, uint32_t nzw, uint
     a = fmaxf(fmaxf(fmaf_(qbyte_f<K>(nxw, one), ax, cx), fmaf_(qbyte_f<K>(nyw, one), ay, cy)), fmaxf(fmaf_(qbyte_f<K>(nzw, one), az, cz), tMin));
     b = fminf(fminf(fmaf_(qbyte_f<K>(fxw, one), ax, cx), fmaf_(qbyte_f<K>(fyw, one), ay, cy)), fminf(fmaf_(qbyte_f<K>(fzw, one), az, cz), bestT));
 }
-TMPT_HD uint32_t qnode_step(const SceneView& sc, uint32_t node, const RayCtx& r, float tMin, float bestT, unsigned long long* stack, int& sp,
+template <class Stack>
+TMPT_HD uint32_t qnode_step(const SceneView& sc, uint32_t node, const RayCtx& r, float tMin, float bestT, Stack& stack, int& sp,
                             bool anyRay) {
     uint4 h, rf, qa, qb;
     if (QNODE_STRIDE == 4) {
@@ -313,7 +396,8 @@ TMPT_HD uint32_t qnode_step(const SceneView& sc, uint32_t node, const RayCtx& r,
 #define TMPT_QNODES 0
 #endif
 
-TMPT_HD uint32_t node_step(const SceneView& sc, uint32_t node, const RayCtx& r, float tMin, float bestT, unsigned long long* stack, int& sp, bool anyRay) {
+template <class Stack>
+TMPT_HD uint32_t node_step(const SceneView& sc, uint32_t node, const RayCtx& r, float tMin, float bestT, Stack& stack, int& sp, bool anyRay) {
 #if TMPT_QNODES
     return qnode_step(sc, node, r, tMin, bestT, stack, sp, anyRay);
 #else
@@ -361,42 +445,101 @@ TMPT_HD void walk_start(WalkState& w, const SceneView& sc, ex::V3 o, ex::V3 d, f
 // overlap instead of alternating, and nobody loops over a whole leaf while its neighbours
 // wait (+12 % on the frame, profiles/).  The walk runs at most one leaf ahead of the tests, so
 // almost nothing is visited that a tighter best t would have culled.
-template <bool STATS>
-TMPT_HD bool walk_step(WalkState& w, const SceneView& sc, float tMin, float tMax, unsigned long long* stack, TravStats* stats) {
+// warp votes of the instrumented pass (the host emulation has no warps: every "warp" is one lane)
+TMPT_HD bool stats_any(bool pred) {
+#ifdef __CUDA_ARCH__
+    return __any_sync(__activemask(), pred);
+#else
+    return pred;
+#endif
+}
+TMPT_HD bool stats_leader() {
+#ifdef __CUDA_ARCH__
+    const unsigned m = __activemask();
+    unsigned lane;
+    asm("mov.u32 %0, %%laneid;" : "=r"(lane));
+    return (unsigned)(__ffs((int)m) - 1) == lane;
+#else
+    return true;
+#endif
+}
+
+template <bool STATS, class Stack>
+TMPT_HD bool walk_step(WalkState& w, const SceneView& sc, float tMin, float tMax, Stack& stack, TravStats* stats) {
+    if (STATS) {
+        ++stats->iters;
+        const bool nodeAny = stats_any(w.cur != NONE && !ref_is_leaf(w.cur));
+        if (stats_leader()) { ++stats->warpIters; stats->nodeWarps += nodeAny ? 1 : 0; }
+    }
     if (w.cur != NONE && !ref_is_leaf(w.cur)) {
         if (STATS) ++stats->nodes;
         w.cur = node_step(sc, w.cur, w.r, tMin, w.best.t, stack, w.sp, w.any);
+        if (STATS && w.sp > stats->maxSp) stats->maxSp = w.sp;
     }
     if (w.cur != NONE && ref_is_leaf(w.cur) && w.triPos == w.triEnd) {  // park the leaf, free the walker
         w.triPos = leaf_first(w.cur);
         w.triEnd = w.triPos + (uint32_t)leaf_count(w.cur);
         w.cur = NONE;
     }
-    // if a pop is coming, request the top entry now: its local-memory latency hides behind the triangle test
+    if (STATS) {
+        if (w.cur != NONE && ref_is_leaf(w.cur)) ++stats->leafWaits;
+        const bool triAny = stats_any(w.triPos < w.triEnd);
+        if (stats_leader()) stats->triWarps += triAny ? 1 : 0;
+    }
+    // if a pop is coming, request the top entry now: its latency hides behind the triangle test
     // (ncu: the compare after this load was the hottest stall site of the kernel)
     const bool popping = w.cur == NONE && w.sp > 0;
     unsigned long long top = 0;
-    if (popping) top = *(volatile unsigned long long*)&stack[w.sp - 1];
+    if (popping) top = stack.get(w.sp - 1);
     if (w.triPos < w.triEnd) {
         if (STATS) ++stats->tris;
         if (tri_step(sc, w.triPos++, w.o, w.d, tMin, tMax, w.best) && w.any) return true;
     }
     // pop ONE entry per iteration.  If the shrinking best.t has culled it the lane sits out the next node step and pops again
     // behind the next prefetch.  (A loop here that pops until something survives ran in 75 % of the iterations for a single
-    // lane, with its local-memory latency exposed to the whole warp: +3.3 % without it.)
+    // lane, with its stack latency exposed to the whole warp: +3.3 % without it.)
     if (popping) {
         --w.sp;
         if (ex::u2f((uint32_t)(top >> 32)) <= w.best.t) w.cur = (uint32_t)top;
+        else if (STATS) ++stats->culledPops;
     }
-    return w.cur == NONE && w.triPos == w.triEnd && w.sp == 0;
+    const bool done = w.cur == NONE && w.triPos == w.triEnd && w.sp == 0;
+    if (STATS && done) {
+        const int lim[5] = {4, 8, 12, 16, 24};
+        for (int k = 0; k < 5; ++k) stats->depthOver[k] += stats->maxSp > lim[k] ? 1 : 0;
+        stats->maxSp = 0;
+    }
+    return done;
 }
 
 template <bool ANY, bool STATS = false>
 TMPT_HD HitRec traverse(const SceneView& sc, ex::V3 o, ex::V3 d, float tMin, float tMax, TravStats* stats = nullptr) {
-    unsigned long long stack[STACK_SIZE];  // (entry distance bits << 32) | ref
+    LocalStack stack;
     WalkState w;
     walk_start(w, sc, o, d, tMax, ANY);
     while (!walk_step<STATS>(w, sc, tMin, tMax, stack, stats)) {}
+    return w.best;
+}
+// the second attempt of a ray whose short stack overflowed: out of line, so that it costs the walk above it nothing
+template <bool ANY>
+#ifdef __CUDA_ARCH__
+__device__ __noinline__
+#else
+inline
+#endif
+HitRec traverse_again(const SceneView& sc, ex::V3 o, ex::V3 d, float tMin, float tMax) { return traverse<ANY, false>(sc, o, d, tMin, tMax); }
+
+template <bool ANY, bool STATS, class Stack>
+TMPT_HD HitRec traverse_with(Stack& stack, const SceneView& sc, ex::V3 o, ex::V3 d, float tMin, float tMax, TravStats* stats = nullptr) {
+    WalkState w;
+    walk_start(w, sc, o, d, tMax, ANY);
+    while (!walk_step<STATS>(w, sc, tMin, tMax, stack, stats)) {}
+    if (Stack::kCanOverflow && stack.overflowed()) {
+        stack.reset();
+        if (STATS) ++stats->overflows;
+        // (an any-hit answer "hit" stands whatever was dropped; everything else needs the entries that were lost)
+        if (!(ANY && w.best.id >= 0)) return traverse_again<ANY>(sc, o, d, tMin, tMax);
+    }
     return w.best;
 }
 

@@ -115,6 +115,21 @@ TMPT_HD uint32_t pixel_seed(uint32_t pixelIndex) {
     return s ? s : 1u;
 }
 
+// Seed of the stream of chunk `chunk` of pixel `pixel` in a frame of `pixels` pixels: pixel_seed of the stream index
+// chunk * pixels + pixel.  The index is formed in 64 bits (a 10000 x 10000 frame passes 2^32 at chunk 43, a long
+// progressive 1080p render after 2071 chunks) and its high word is folded in before the hash, so that later streams do
+// not repeat the first 2^32 in order; below 2^32 the seeds are exactly pixel_seed(index).
+TMPT_HD uint32_t chunk_seed(uint32_t chunk, uint32_t pixel, uint32_t pixels) {
+    const uint64_t idx = (uint64_t)chunk * (uint64_t)pixels + (uint64_t)pixel;
+    uint32_t s = ((uint32_t)idx * 9781u + 1u) ^ ((uint32_t)(idx >> 32) * 0x9E3779B9u);
+    s = (s ^ 61u) ^ (s >> 16);
+    s *= 9u;
+    s ^= s >> 4;
+    s *= 0x27d4eb2du;
+    s ^= s >> 15;
+    return s ? s : 1u;
+}
+
 // maths.cpp:20-28.  vec3(R(), R(), 0): the reference build (g++) draws the SECOND
 // component first; the oracle pins that order and this follows it.
 TMPT_HD void random_in_unit_disk(uint32_t& state, float& px, float& py) {

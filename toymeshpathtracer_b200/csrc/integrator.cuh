@@ -81,20 +81,20 @@ TMPT_HD uchar4 resolve_pixel(ex::V3 sum, float sppRecip) {
 // One whole pixel, serially: the straightforward form used by the host emulation and by the
 // first (non-wavefront) render kernel.  kk[] holds the per-bounce sun term (0 for a
 // shadowed bounce).
-template <bool STATS = false, class Scene>
-TMPT_HD ex::V3 trace_path(const Scene& sc, const Camera& cam, ex::V3 o, ex::V3 d, ex::V3 lightDir, uint32_t& rng,
+template <bool STATS = false, class Stack, class Scene>
+TMPT_HD ex::V3 trace_path(Stack& stack, const Scene& sc, const Camera& cam, ex::V3 o, ex::V3 d, ex::V3 lightDir, uint32_t& rng,
                           unsigned long long& rays, bvh::TravStats* stats = nullptr) {
     float kk[kMaxDepth];
     int depth = 0;
     ex::V3 color = ex::v3(0.0f, 0.0f, 0.0f);
     while (depth < kMaxDepth) {
         ++rays;
-        const bvh::HitRec h = bvh::traverse<false, STATS>(sc, o, d, kMinT, kMaxT, stats);
+        const bvh::HitRec h = bvh::traverse_with<false, STATS>(stack, sc, o, d, kMinT, kMaxT, stats);
         if (h.id < 0) { color = sky(d); break; }
         ex::V3 pos, normal;
         bvh::hit_payload(sc, h.id, h.u, h.v, pos, normal);
         ++rays;
-        const bvh::HitRec sh = bvh::traverse<true, STATS>(sc, pos, lightDir, kMinT, kMaxT, stats);
+        const bvh::HitRec sh = bvh::traverse_with<true, STATS>(stack, sc, pos, lightDir, kMinT, kMaxT, stats);
         kk[depth] = sh.id < 0 ? sun_term(normal, d, lightDir) : 0.0f;
         d = scatter_dir(pos, normal, rng);
         o = pos;
@@ -121,17 +121,17 @@ TMPT_HD int chunk_len(int spp) {
 TMPT_HD int chunk_count(int spp) { const int c = chunk_len(spp); return (spp + c - 1) / c; }
 
 // `len` = samples per chunk: chunk_len(spp) for a one-shot frame, kMaxChunkSamples for a progressive pass
-template <bool STATS = false, class Scene>
-TMPT_HD ex::V3 render_chunk(const Scene& sc, const Camera& cam, int x, int y, int chunk, int width, int height, int spp, int len, ex::V3 lightDir,
+template <bool STATS = false, class Stack, class Scene>
+TMPT_HD ex::V3 render_chunk(Stack& stack, const Scene& sc, const Camera& cam, int x, int y, int chunk, int width, int height, int spp, int len, ex::V3 lightDir,
                             unsigned long long& rays, bvh::TravStats* stats = nullptr) {
     const float invW = ex::divf(1.0f, (float)width), invH = ex::divf(1.0f, (float)height);
-    uint32_t rng = ex::pixel_seed((uint32_t)chunk * ((uint32_t)width * (uint32_t)height) + (uint32_t)y * (uint32_t)width + (uint32_t)x);
+    uint32_t rng = ex::chunk_seed((uint32_t)chunk, (uint32_t)y * (uint32_t)width + (uint32_t)x, (uint32_t)width * (uint32_t)height);
     ex::V3 sum = ex::v3(0.0f, 0.0f, 0.0f);
     const int s0 = chunk * len, s1 = s0 + len < spp ? s0 + len : spp;
     for (int s = s0; s < s1; ++s) {
         ex::V3 o, d;
         primary_ray(cam, x, y, invW, invH, rng, o, d);
-        sum = ex::add(sum, trace_path<STATS>(sc, cam, o, d, lightDir, rng, rays, stats));
+        sum = ex::add(sum, trace_path<STATS>(stack, sc, cam, o, d, lightDir, rng, rays, stats));
     }
     return sum;
 }
@@ -142,7 +142,8 @@ TMPT_HD uchar4 render_pixel(const Scene& sc, const Camera& cam, int x, int y, in
                             unsigned long long& rays, ex::V3* outLinear = nullptr, bvh::TravStats* stats = nullptr) {
     const float sppRecip = ex::divf(1.0f, (float)spp);
     ex::V3 sum = ex::v3(0.0f, 0.0f, 0.0f);
-    for (int c = 0; c < chunk_count(spp); ++c) sum = ex::add(sum, render_chunk<STATS>(sc, cam, x, y, c, width, height, spp, chunk_len(spp), lightDir, rays, stats));
+    bvh::LocalStack stack;
+    for (int c = 0; c < chunk_count(spp); ++c) sum = ex::add(sum, render_chunk<STATS>(stack, sc, cam, x, y, c, width, height, spp, chunk_len(spp), lightDir, rays, stats));
     if (outLinear) *outLinear = ex::muls(sum, sppRecip);
     return resolve_pixel(sum, sppRecip);
 }

@@ -26,8 +26,15 @@
 #include "build_logic.cuh"
 #include "common.h"
 #include "integrator.cuh"
+// Experimental traversal / render kernels measured in round 1 and not adopted are compiled only with
+// -DTMPT_EXPERIMENTS=1 (tools/exp_*.py); the shipped library does not contain them.
+#ifndef TMPT_EXPERIMENTS
+#define TMPT_EXPERIMENTS 0
+#endif
+#if TMPT_EXPERIMENTS
 #include "warpq.cuh"
 #include "wtrace.cuh"
+#endif
 
 // ------------------------------------------------------------------------------------------
 // error plumbing
@@ -503,10 +510,11 @@ __global__ void k_collapse_root_leaf(bld::BinTree t, bld::WideOut w, int rootNod
 // ------------------------------------------------------------------------------------------
 // K2/K3: batched HitScene
 // ------------------------------------------------------------------------------------------
-// stats[0] rays, [1] wide-node visits, [2] triangle tests, [3] hits
+// stats[0] rays, [1] wide-node visits, [2] triangle tests, [3] hits, [4..9] lane / warp iteration counters (include/tmpt.h)
 __device__ __forceinline__ void flush_stats(unsigned long long* stats, unsigned long long rays, const bvh::TravStats& ts, unsigned long long hits) {
-    unsigned long long v[4] = {rays, ts.nodes, ts.tris, hits};
-    for (int k = 0; k < 4; ++k) {
+    unsigned long long v[16] = {rays, ts.nodes, ts.tris, hits, ts.iters, ts.culledPops, ts.leafWaits, ts.nodeWarps, ts.triWarps, ts.warpIters,
+                                ts.overflows, ts.depthOver[0], ts.depthOver[1], ts.depthOver[2], ts.depthOver[3], ts.depthOver[4]};
+    for (int k = 0; k < 16; ++k) {
         for (int o = 16; o > 0; o >>= 1) v[k] += __shfl_xor_sync(0xffffffffu, v[k], o);
         if ((threadIdx.x & 31) == 0 && v[k]) atomicAdd(&stats[k], v[k]);
     }
@@ -541,6 +549,7 @@ __global__ void __launch_bounds__(128) k_hit_scene(bvh::SceneView sc, const floa
     if (STATS) flush_stats(stats, nr, ts, nh);
 }
 
+#if TMPT_EXPERIMENTS
 // K2/K3 through the warp-synchronous deferred-triangle traversal (wtrace.cuh)
 template <bool STATS, int TRI_MIN, int WALK_MIN>
 __global__ void __launch_bounds__(128) k_hit_scene_wt(bvh::SceneView sc, const float* __restrict__ rays6, long long nRays, float tMin, float tMax,
@@ -696,6 +705,8 @@ __global__ void __launch_bounds__(128) k_hit_scene_wq(bvh::SceneView sc, const f
     if (STATS) flush_stats(stats, nr, ts, nh);
 }
 
+#endif  // TMPT_EXPERIMENTS
+
 // ------------------------------------------------------------------------------------------
 // K4: path tracing.  Work unit = (8x4 pixel tile, one chunk of chunk_len(spp) samples) per warp, fetched from a
 // global counter (persistent CTAs); a lane runs the samples of its pixel's chunk serially
@@ -730,11 +741,33 @@ __device__ __forceinline__ int owned_row_to_global(int r, int stripeRows, int ra
     return (ls * world + rank) * stripeRows + (r - ls * stripeRows);
 }
 
-template <bool STATS, int THREADS, int MINB>
+// SSTACK = traversal-stack entries per lane kept in shared memory (0: the whole stack is a local-memory array); the launch
+// passes SSTACK * THREADS * 8 bytes of dynamic shared memory.
+template <int SSTACK, int THREADS>
+struct RenderStack {
+    using type = bvh::SmemStack<SSTACK, THREADS>;
+    static __device__ __forceinline__ type make() {
+        extern __shared__ unsigned long long smemStack[];
+        return type::make(smemStack, threadIdx.x);
+    }
+};
+template <int THREADS>
+struct RenderStack<0, THREADS> {
+    using type = bvh::LocalStack;
+    static __device__ __forceinline__ type make() { return type(); }
+};
+
+#ifndef TMPT_SSTACK
+#define TMPT_SSTACK 0
+#endif
+constexpr int kSStack = TMPT_SSTACK;
+
+template <bool STATS, int THREADS, int MINB, int SSTACK>
 __global__ void __launch_bounds__(THREADS, MINB) k_render(const RenderParams p) {
     const int lane = threadIdx.x & 31;
     unsigned long long rays = 0;
     bvh::TravStats ts;
+    typename RenderStack<SSTACK, THREADS>::type stack = RenderStack<SSTACK, THREADS>::make();
     for (;;) {
         uint32_t tile = 0;
         if (lane == 0) tile = atomicAdd(p.tileCounter, 1u);
@@ -746,7 +779,7 @@ __global__ void __launch_bounds__(THREADS, MINB) k_render(const RenderParams p) 
         const int x = tx * 8 + (lane & 7), rb = ty * 4 + (lane >> 3), r = p.bandRow0 + rb;
         if (x < p.width && r < p.ownedRows) {
             const int y = owned_row_to_global(r, p.stripeRows, p.rank, p.world);
-            const ex::V3 sum = integ::render_chunk<STATS>(p.sc, p.cam, x, y, p.chunk0 + chunk, p.width, p.height, p.spp, p.chunkLen, p.lightDir, rays, &ts);
+            const ex::V3 sum = integ::render_chunk<STATS>(stack, p.sc, p.cam, x, y, p.chunk0 + chunk, p.width, p.height, p.spp, p.chunkLen, p.lightDir, rays, &ts);
             if (p.useAccum) {
                 __stcs(&p.accum[((size_t)chunk * p.bandRows + rb) * p.width + x], make_float4(sum.x, sum.y, sum.z, 0.0f));  // streaming: read once, by k_resolve
             } else {
@@ -761,6 +794,7 @@ __global__ void __launch_bounds__(THREADS, MINB) k_render(const RenderParams p) 
     if (lane == 0 && rays) atomicAdd(p.rayCount, rays);
 }
 
+#if TMPT_EXPERIMENTS
 // K4': the same frame with per-lane RAY REGENERATION.  In k_render a warp's lanes trace their rays in lockstep: a lane whose
 // ray ends early idles until the warp's longest ray is done (about half of all lane slots of the walk).  Here every lane
 // is a small state machine over its own path -- closest-hit walk -> shade -> shadow walk -> next bounce ... -> next sample
@@ -776,7 +810,7 @@ template <bool STATS, int THREADS, int MINB, int TA, int TB>
 __global__ void __launch_bounds__(THREADS, MINB) k_render_regen(const RenderParams p) {
     constexpr unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31;
-    unsigned long long stack[bvh::STACK_SIZE];
+    bvh::LocalStack stack;
     float kk[integ::kMaxDepth];
     bvh::WalkState w;
     bvh::TravStats ts;
@@ -853,9 +887,10 @@ __global__ void __launch_bounds__(THREADS, MINB) k_render_regen(const RenderPara
                                 const int r = p.bandRow0 + rb;
                                 if (x < p.width && r < p.ownedRows) {  // (an item outside the frame is simply dropped: the lane asks again)
                                     y = owned_row_to_global(r, p.stripeRows, p.rank, p.world);
-                                    rng = ex::pixel_seed((uint32_t)chunk * ((uint32_t)p.width * (uint32_t)p.height) + (uint32_t)y * (uint32_t)p.width + (uint32_t)x);
+                                    const int gchunk = p.chunk0 + chunk;  // progressive passes continue the chunk numbering; `chunk` stays the accum plane
+                                    rng = ex::chunk_seed((uint32_t)gchunk, (uint32_t)y * (uint32_t)p.width + (uint32_t)x, (uint32_t)p.width * (uint32_t)p.height);
                                     const int len = p.chunkLen;
-                                    s = chunk * len;
+                                    s = gchunk * len;
                                     sEnd = s + len < p.spp ? s + len : p.spp;
                                     sum = ex::v3(0.0f, 0.0f, 0.0f);
                                     state = ST_PATH_END;  // marks "has an item, needs a camera ray" for the block below
@@ -886,6 +921,8 @@ __global__ void __launch_bounds__(THREADS, MINB) k_render_regen(const RenderPara
     for (int o = 16; o > 0; o >>= 1) rays += __shfl_xor_sync(FULL, rays, o);
     if (lane == 0 && rays) atomicAdd(p.rayCount, rays);
 }
+
+#endif  // TMPT_EXPERIMENTS
 
 // pixel = in-order sum of its chunk sums, then mean / sqrt / quantise (main.cpp:221-233)
 __global__ void k_resolve(const RenderParams p, int bandRows) {
@@ -1301,6 +1338,7 @@ extern "C" int tmpt_hit_scene(const tmpt_scene* s, const float* rays6, int64_t n
     }
     const int B = 128;
     const int G = (int)std::min<long long>(div_up(nRays, B), (long long)s->smCount * 64);
+#if TMPT_EXPERIMENTS
     // Experimental traversal engines kept for A/B runs (tools/exp_traverse.py; results in profiles/ and DESIGN.md 5):
     // 5 = warp queue (warpq.cuh), 10/11 = warp-synchronous deferred triangle tests, 20 = cooperative leaf phase (wtrace.cuh).
     static const int variant = getenv("TMPT_HIT_KERNEL") ? atoi(getenv("TMPT_HIT_KERNEL")) : 0;
@@ -1327,7 +1365,12 @@ extern "C" int tmpt_hit_scene(const tmpt_scene* s, const float* rays6, int64_t n
             LAUNCH((k_hit_scene_w8<false>), G, B, 0, st, s->view, dRays, (long long)nRays, tMin, tMax, mode == TMPT_HIT_ANY, dID, dT, dPos, dNrm, nullptr);
         } else
         return tmpt::fail(TMPT_ERR_ARG, "TMPT_HIT_KERNEL=%d: no such traversal variant", variant);
-    } else if (mode == TMPT_HIT_CLOSEST) LAUNCH((k_hit_scene<TMPT_HIT_CLOSEST, false>), G, B, 0, st, s->view, dRays, (long long)nRays, tMin, tMax, dID, dT, dPos, dNrm, nullptr);
+    } else
+#else
+    if (getenv("TMPT_HIT_KERNEL") && atoi(getenv("TMPT_HIT_KERNEL")) > 0)
+        return tmpt::fail(TMPT_ERR_ARG, "TMPT_HIT_KERNEL is set, but this library was built without -DTMPT_EXPERIMENTS=1");
+#endif
+    if (mode == TMPT_HIT_CLOSEST) LAUNCH((k_hit_scene<TMPT_HIT_CLOSEST, false>), G, B, 0, st, s->view, dRays, (long long)nRays, tMin, tMax, dID, dT, dPos, dNrm, nullptr);
     else if (mode == TMPT_HIT_ANY) LAUNCH((k_hit_scene<TMPT_HIT_ANY, false>), G, B, 0, st, s->view, dRays, (long long)nRays, tMin, tMax, dID, dT, dPos, dNrm, nullptr);
     else LAUNCH((k_hit_scene<TMPT_HIT_BRUTE, false>), G, B, 0, st, s->view, dRays, (long long)nRays, tMin, tMax, dID, dT, dPos, dNrm, nullptr);
     CU_TRY(cudaGetLastError());
@@ -1422,19 +1465,30 @@ static int launch_render(const tmpt_scene* cs, const tmpt_camera* camera, int wi
     const int prc = prepare_render_chunks(s, width, p.chunks, prog != nullptr, p.ownedRows, st, &bandRows);
     if (prc != TMPT_OK) return prc;
     p.accum = s->d_accum;
-    // 256 threads x 4 CTAs/SM = 32 warps/SM at 64 registers (sweep in profiles/r1_tuning_sweeps.txt: 24 warps at
-    // 77 registers is 10 % slower, 40 warps at 48 registers spills and is 3 % slower)
     // 32 warps per SM at 64 registers (sweep in profiles/r1_tuning_sweeps.txt: 24 warps at 77 registers is 10 % slower, 40
     // warps at 48 registers spills and is 3 % slower), as ONE 1024-thread CTA per SM when the band has work for every SM
     // several times over (+1.6 % over four 256-thread CTAs: 5016 vs 4937 Mrays/s), as 256-thread CTAs for small frames, whose
     // few hundred warp items would otherwise land on a few SMs.  TMPT_RENDER_CFG (tuning): 1 = 256 x 4, 2 = 512 x 2, 3 = 1024 x 1.
     static const int cfgEnv = getenv("TMPT_RENDER_CFG") ? atoi(getenv("TMPT_RENDER_CFG")) : 0;
-    // TMPT_RENDER_KERNEL: 0 = lockstep lanes (k_render), 1.. = per-lane ray regeneration with gate sizes (TA, TB)
+    // TMPT_RENDER_KERNEL (experiments build only): 0 = lockstep lanes (k_render), 1.. = per-lane ray regeneration with gate sizes (TA, TB)
     static const int rk = getenv("TMPT_RENDER_KERNEL") ? atoi(getenv("TMPT_RENDER_KERNEL")) : 0;
+#if !TMPT_EXPERIMENTS
+    if (rk > 0) return tmpt::fail(TMPT_ERR_ARG, "TMPT_RENDER_KERNEL is set, but this library was built without -DTMPT_EXPERIMENTS=1");
+#endif
+    // the shared-memory part of the traversal stacks: kSStack entries x 8 bytes per thread (dynamic shared memory)
+    constexpr size_t smemPerThread = (size_t)kSStack * sizeof(unsigned long long);
+    if (smemPerThread * 256 > 48 * 1024) {  // (function attributes are per device: set on every launch path, it costs microseconds)
+        CU_TRY(cudaFuncSetAttribute(k_render<false, 256, 4, kSStack>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smemPerThread * 256)));
+        CU_TRY(cudaFuncSetAttribute(k_render<true, 256, 4, kSStack>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smemPerThread * 256)));
+    }
+    if (smemPerThread * 512 > 48 * 1024)
+        CU_TRY(cudaFuncSetAttribute(k_render<false, 512, 2, kSStack>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smemPerThread * 512)));
+    if (smemPerThread * 1024 > 48 * 1024)
+        CU_TRY(cudaFuncSetAttribute(k_render<false, 1024, 1, kSStack>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smemPerThread * 1024)));
     int perSM256 = 0, perSM512 = 0, perSM1024 = 0;
-    CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM256, k_render<false, 256, 4>, 256, 0));
-    CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM512, k_render<false, 512, 2>, 512, 0));
-    CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM1024, k_render<false, 1024, 1>, 1024, 0));
+    CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM256, k_render<false, 256, 4, kSStack>, 256, smemPerThread * 256));
+    CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM512, k_render<false, 512, 2, kSStack>, 512, smemPerThread * 512));
+    CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM1024, k_render<false, 1024, 1, kSStack>, 1024, smemPerThread * 1024));
     for (p.bandRow0 = 0; p.bandRow0 < p.ownedRows; p.bandRow0 += bandRows) {
         const int rowsHere = std::min(bandRows, p.ownedRows - p.bandRow0);
         p.bandRows = rowsHere;
@@ -1446,6 +1500,7 @@ static int launch_render(const tmpt_scene* cs, const tmpt_camera* camera, int wi
         const int threads = cfg == 3 ? 1024 : cfg == 2 ? 512 : 256;
         const int perSM = cfg == 3 ? perSM1024 : cfg == 2 ? perSM512 : perSM256;
         const int grid = (int)std::min<long long>((long long)s->smCount * std::max(perSM, 1), (items + threads / 32 - 1) / (threads / 32));
+#if TMPT_EXPERIMENTS
         if (rk > 0 && !statsDev) {
             CU_TRY(cudaMemsetAsync(s->d_fetchCounter, 0, sizeof(unsigned long long), st));
             int perSMr = 0;
@@ -1458,10 +1513,12 @@ static int launch_render(const tmpt_scene* cs, const tmpt_camera* camera, int wi
             REGEN_CASE(1, 8, 4) REGEN_CASE(2, 4, 2) REGEN_CASE(3, 12, 6) REGEN_CASE(4, 16, 4)
 #undef REGEN_CASE
             return tmpt::fail(TMPT_ERR_ARG, "TMPT_RENDER_KERNEL=%d: no such render kernel", rk);
-        } else if (statsDev) LAUNCH((k_render<true, 256, 4>), grid, 256, 0, st, p);
-        else if (cfg == 3) LAUNCH((k_render<false, 1024, 1>), grid, 1024, 0, st, p);
-        else if (cfg == 2) LAUNCH((k_render<false, 512, 2>), grid, 512, 0, st, p);
-        else LAUNCH((k_render<false, 256, 4>), grid, 256, 0, st, p);
+        } else
+#endif
+        if (statsDev) LAUNCH((k_render<true, 256, 4, kSStack>), grid, 256, smemPerThread * 256, st, p);
+        else if (cfg == 3) LAUNCH((k_render<false, 1024, 1, kSStack>), grid, 1024, smemPerThread * 1024, st, p);
+        else if (cfg == 2) LAUNCH((k_render<false, 512, 2, kSStack>), grid, 512, smemPerThread * 512, st, p);
+        else LAUNCH((k_render<false, 256, 4, kSStack>), grid, 256, smemPerThread * 256, st, p);
         if (p.useAccum) LAUNCH(k_resolve, div_up((long long)rowsHere * width, 256), 256, 0, st, p, rowsHere);
     }
     CU_TRY(cudaGetLastError());
@@ -1698,7 +1755,7 @@ extern "C" int tmpt_frame_free(int device, void* ptr) {
 }
 
 // Instrumented passes (same kernels compiled with counters; never part of a timed run).
-extern "C" int tmpt_render_stats(const tmpt_scene* cs, const tmpt_camera* camera, int width, int height, int spp, uint64_t outStats[4]) {
+extern "C" int tmpt_render_stats(const tmpt_scene* cs, const tmpt_camera* camera, int width, int height, int spp, uint64_t outStats[TMPT_STATS_COUNT]) {
     int rc = check_render_args(cs, camera, width, height, spp);
     if (rc != TMPT_OK) return rc;
     if (!outStats) return tmpt::fail(TMPT_ERR_ARG, "tmpt_render_stats: outStats is NULL");
@@ -1710,17 +1767,17 @@ extern "C" int tmpt_render_stats(const tmpt_scene* cs, const tmpt_camera* camera
     DevBuf<uint8_t> frame;
     DevBuf<unsigned long long> stats;
     CU_TRY(frame.alloc(bytes));
-    CU_TRY(stats.alloc(4));
-    CU_TRY(cudaMemsetAsync(stats.p, 0, 4 * sizeof(unsigned long long), st));
+    CU_TRY(stats.alloc(TMPT_STATS_COUNT));
+    CU_TRY(cudaMemsetAsync(stats.p, 0, TMPT_STATS_COUNT * sizeof(unsigned long long), st));
     CU_TRY(cudaMemsetAsync(s->d_rayCount, 0, sizeof(unsigned long long), st));
     rc = launch_render(s, camera, width, height, spp, height, 0, 1, nullptr, frame.p, s->d_rayCount, st, stats.p);
     if (rc != TMPT_OK) return rc;
-    CU_TRY(cudaMemcpyAsync(outStats, stats.p, 4 * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+    CU_TRY(cudaMemcpyAsync(outStats, stats.p, TMPT_STATS_COUNT * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
     CU_TRY(cudaStreamSynchronize(st));
     return TMPT_OK;
 }
 
-extern "C" int tmpt_hit_scene_stats(const tmpt_scene* s, const float* rays6Dev, int64_t nRays, float tMin, float tMax, int mode, uint64_t outStats[4]) {
+extern "C" int tmpt_hit_scene_stats(const tmpt_scene* s, const float* rays6Dev, int64_t nRays, float tMin, float tMax, int mode, uint64_t outStats[TMPT_STATS_COUNT]) {
     if (!s || !rays6Dev || nRays <= 0 || !outStats || (mode != TMPT_HIT_CLOSEST && mode != TMPT_HIT_ANY))
         return tmpt::fail(TMPT_ERR_ARG, "tmpt_hit_scene_stats: bad arguments");
     DeviceGuard guard(s->device);
@@ -1728,15 +1785,15 @@ extern "C" int tmpt_hit_scene_stats(const tmpt_scene* s, const float* rays6Dev, 
     cudaStream_t st = s->stream;
     DevBuf<unsigned long long> stats;
     DevBuf<int> ids;
-    CU_TRY(stats.alloc(4));
+    CU_TRY(stats.alloc(TMPT_STATS_COUNT));
     CU_TRY(ids.alloc((size_t)nRays));
-    CU_TRY(cudaMemsetAsync(stats.p, 0, 4 * sizeof(unsigned long long), st));
+    CU_TRY(cudaMemsetAsync(stats.p, 0, TMPT_STATS_COUNT * sizeof(unsigned long long), st));
     const int B = 128;
     const int G = (int)std::min<long long>(div_up(nRays, B), (long long)s->smCount * 64);
     if (mode == TMPT_HIT_CLOSEST) LAUNCH((k_hit_scene<TMPT_HIT_CLOSEST, true>), G, B, 0, st, s->view, rays6Dev, (long long)nRays, tMin, tMax, ids.p, nullptr, nullptr, nullptr, stats.p);
     else LAUNCH((k_hit_scene<TMPT_HIT_ANY, true>), G, B, 0, st, s->view, rays6Dev, (long long)nRays, tMin, tMax, ids.p, nullptr, nullptr, nullptr, stats.p);
     CU_TRY(cudaGetLastError());
-    CU_TRY(cudaMemcpyAsync(outStats, stats.p, 4 * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+    CU_TRY(cudaMemcpyAsync(outStats, stats.p, TMPT_STATS_COUNT * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
     CU_TRY(cudaStreamSynchronize(st));
     return TMPT_OK;
 }
