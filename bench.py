@@ -48,6 +48,10 @@ WORKLOADS = {
 }
 # bounded CPU samples (about 10-30 s of CPU work on the box's host cores): same scene and camera, fewer pixels / samples
 CPU_SAMPLE = {"sponza": (640, 360, 8), "teapot": (640, 360, 8), "suzanne": (640, 360, 16), "cube": (640, 360, 64)}
+CPU_SAMPLE_1T = {"sponza": (160, 90, 8), "teapot": (160, 90, 8), "suzanne": (320, 180, 8), "cube": (640, 360, 8)}  # one thread: a few seconds
+# BASELINE.json configs 1-4 (config 5 is the headline line itself): reported in the line's "configs" array
+EXTRA_CONFIGS = [("config1", "cube_640x360_4spp"), ("config2", "suzanne_640x360_4spp"), ("config3", "teapot_720p_16spp"),
+                 ("config4", "sponza_640x360_4spp")]
 REF_BIN = os.path.join(ROOT, "oracle", "_ref", "TrimeshTracer")
 
 
@@ -87,13 +91,15 @@ def scene_label(scene: str) -> str:
 # ------------------------------------------------------------------------------------------
 # the reference's CPU program on a bounded sample
 # ------------------------------------------------------------------------------------------
-def run_reference_cpu(scene: str, w: int, h: int, spp: int):
-    """-> (Mrays/s, rays, seconds, kind, cores).  oracle/_ref when built, else the C restatement."""
-    cores = os.cpu_count() or 1
+def run_reference_cpu(scene: str, w: int, h: int, spp: int, threads: int | None = None):
+    """-> (Mrays/s, rays, seconds, kind, cores).  oracle/_ref when built, else the C restatement.  `threads`: worker threads
+    of the reference's row loop (TBB_SHIM_THREADS of oracle/tbb_shim); default = every hardware thread."""
+    cores = threads or os.cpu_count() or 1
     path = scene_obj_path(scene)
     if os.path.exists(REF_BIN):
+        env = dict(os.environ, TBB_SHIM_THREADS=str(threads)) if threads else None
         with tempfile.TemporaryDirectory() as td:
-            out = subprocess.run([REF_BIN, str(w), str(h), str(spp), path], cwd=td, capture_output=True, text=True, check=True).stdout
+            out = subprocess.run([REF_BIN, str(w), str(h), str(spp), path], cwd=td, capture_output=True, text=True, check=True, env=env).stdout
         m = re.search(r"in ([0-9.]+) s\n- ([0-9.]+) K Rays, ([0-9.]+) K Rays/s", out)
         sec, krays, krate = float(m.group(1)), float(m.group(2)), float(m.group(3))
         return krate / 1000.0, krays * 1000.0, sec, "reference", cores
@@ -105,9 +111,9 @@ def run_reference_cpu(scene: str, w: int, h: int, spp: int):
     orc = Oracle()
     rows = (0, max(1, h // 16))
     t0 = time.perf_counter()
-    _, rays = orc.render(tris, cam, w, h, 1, RNG_ROW, TRIG_LIBM, rows=rows)
+    _, rays = orc.render(tris, cam, w, h, 1, RNG_ROW, TRIG_LIBM, rows=rows, threads=threads)
     sec = time.perf_counter() - t0
-    return rays / sec / 1e6, rays, sec, "port", orc.threads
+    return rays / sec / 1e6, rays, sec, "port", threads or orc.threads
 
 
 # ------------------------------------------------------------------------------------------
@@ -190,6 +196,118 @@ class ClockSampler:
         pw = [float(s[6]) for s in self.samples if len(s) > 6 and re.match(r"^[0-9.]+$", s[6])]
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
                 "power_w_max": max(pw) if pw else None, "samples": len(sm), "source": "nvml" if self.nvml else "nvidia-smi"}
+
+
+
+def measure_extra_configs(tm, multigpu, dist, torch, sc_sponza, dev, stream, rank, world, local_rank, flush, peer_enabled):
+    """BASELINE.json configs 1-4 as a `configs` array: Mrays/s and ms/frame of each small workload, timed like the headline
+    (CUDA events around one frame, L2 flushed before each, 3 warm-up + 5 timed frames, max over ranks).  Configs 1-3 name one
+    GPU: they are measured at N = 1 only; config 4 (sponza 640x360 4 spp, "at 1/2/4/8 GPUs") at every N."""
+    out = []
+    for label, wl in EXTRA_CONFIGS:
+        scene, w, h, spp = WORKLOADS[wl]
+        if scene != "sponza" and world > 1:
+            continue
+        peer = None
+        if scene == "sponza":
+            sc, path = sc_sponza, None
+            tris = None
+        else:
+            path = scene_obj_path(scene)
+            tris, mn, mx = tm.load_scene(path)
+            sc = tm.Scene(tris, device=local_rank)
+        if scene == "sponza":
+            path = scene_obj_path(scene) if rank == 0 else None
+            if world > 1:
+                box = [path]
+                dist.broadcast_object_list(box, src=0)
+                path = box[0]
+            _, mn, mx = tm.load_scene(path)
+        cam = tm.camera_for_scene(path, mn, mx, w, h)
+        if world > 1 and peer_enabled:
+            peer = multigpu.PeerFrame(w, h, rank, world, local_rank)
+        ms_list, rays_list = [], []
+        for i in range(3 + 5):
+            if world > 1:
+                dist.barrier()
+            with torch.cuda.stream(stream):
+                flush.zero_()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(stream)
+                _, rays = multigpu.render_frame(sc, cam, w, h, spp, rank, world, group=None, device=dev, peer=peer)
+                e1.record(stream)
+            stream.synchronize()
+            if i >= 3:
+                ms_list.append(e0.elapsed_time(e1))
+                rays_list.append(int(rays.item()))
+        t = torch.tensor([sum(ms_list)], dtype=torch.float64, device=dev)
+        r = torch.tensor([sum(rays_list)], dtype=torch.int64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dist.all_reduce(r, op=dist.ReduceOp.SUM)
+        out.append({"config": label, "workload": f"{scene_label(scene)} {w}x{h} {spp}spp", "n_gpus": world,
+                    "value": int(r.item()) / (float(t.item()) * 1e-3) / 1e6, "unit": "Mrays/s", "ms_per_frame": float(t.item()) / 5,
+                    "rays_per_frame": int(r.item()) // 5, "frames": 5})
+        if peer is not None:
+            dist.barrier()
+            peer.close()
+        if scene != "sponza":
+            sc.close()
+    return out
+
+
+def measure_hit_scene(tm, torch, sc, cam, w, h, dev):
+    """Throughput of the batched HitScene entry (K2 closest hit, K3 any hit) on the rays the headline frame shoots: the camera's
+    primary rays (one per pixel), the diffuse bounce rays leaving their hit points and the shadow rays towards the sun, all
+    generated on the device.  Kernel time only (device pointers, CUDA events, best of 3)."""
+    g = torch.Generator(device=dev)
+    g.manual_seed(1)
+    camt = torch.tensor(cam, device=dev)
+    ys, xs = torch.meshgrid(torch.arange(h, device=dev), torch.arange(w, device=dev), indexing="ij")
+    u = ((xs + torch.rand((h, w), device=dev, generator=g)) / w).reshape(-1, 1)
+    v = ((ys + torch.rand((h, w), device=dev, generator=g)) / h).reshape(-1, 1)
+    origin, llc, hor, ver = camt[0:3], camt[3:6], camt[6:9], camt[9:12]
+    d = llc + u * hor + v * ver - origin
+    d = d / d.norm(dim=1, keepdim=True)
+    rays = torch.cat([origin.expand_as(d), d], 1).contiguous().float()
+    light = torch.tensor([-0.7, 1.0, 0.5], device=dev)
+    light = light / light.norm()
+    st = torch.cuda.Stream(dev)
+
+    def timed(r6, mode):
+        n = r6.shape[0]
+        ids = torch.empty(n, dtype=torch.int32, device=dev)
+        t = torch.empty(n, device=dev)
+        pos = torch.empty((n, 3), device=dev)
+        nrm = torch.empty((n, 3), device=dev)
+        best = 1e30
+        torch.cuda.synchronize(dev)
+        with torch.cuda.stream(st):
+            for _ in range(4):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(st)
+                sc.hit_scene_device(r6.data_ptr(), n, ids.data_ptr(), t.data_ptr(), pos.data_ptr(), nrm.data_ptr(), mode=mode, stream=st.cuda_stream)
+                e1.record(st)
+                st.synchronize()
+                best = min(best, e0.elapsed_time(e1))
+        stats = sc.hit_scene_stats(r6.data_ptr(), n, mode=mode)
+        return ids, pos, nrm, {"rays": n, "ms": best, "value": n / best / 1e3, "unit": "Mrays/s", "node_visits_per_ray": stats["node_visits_per_ray"],
+                               "tri_tests_per_ray": stats["tri_tests_per_ray"], "hit_rate": stats["hit_rate"]}
+
+    out = {}
+    ids, pos, nrm, out["primary_closest"] = timed(rays, tm.HIT_CLOSEST)
+    hit = ids >= 0
+    pos, nrm = pos[hit], nrm[hit]
+    shadow = torch.cat([pos, light.expand_as(pos)], 1).contiguous()
+    _, _, _, out["shadow_any"] = timed(shadow, tm.HIT_ANY)
+    r = torch.randn(pos.shape, device=dev, generator=g)
+    r = r / r.norm(dim=1, keepdim=True)
+    nd = nrm + r
+    nd = nd / nd.norm(dim=1, keepdim=True).clamp_min(1e-20)
+    bounce = torch.cat([pos, nd], 1).contiguous()
+    _, _, _, out["bounce_closest"] = timed(bounce, tm.HIT_CLOSEST)
+    out["ray_set"] = f"{w}x{h} camera rays (jittered, one per pixel), their diffuse bounce rays and sun shadow rays; device-generated, seed 1"
+    return out
 
 
 # ------------------------------------------------------------------------------------------
@@ -331,6 +449,13 @@ def bench_b200(args, scene, w, h, spp, rank, world, local_rank):
         dist.all_reduce(e2e_r, op=dist.ReduceOp.SUM)
     e2e_value = int(e2e_r.item()) / (float(e2e_t.item()) * 1e-3) / 1e6
 
+    # BASELINE configs 1-4 and the HitScene kernels (reported beside the headline; not part of its timed region)
+    extra_configs, hit_scene = [], None
+    if args.workload == "sponza_1080p_64spp" and not args.no_extras:
+        extra_configs = measure_extra_configs(tm, multigpu, dist, torch, sc, dev, stream, rank, world, local_rank, flush, peer is not None)
+        if world == 1:
+            hit_scene = measure_hit_scene(tm, torch, sc, cam, w, h, dev)
+
     line = None
     if rank == 0:
         clk = clocks.summary()
@@ -374,6 +499,10 @@ def bench_b200(args, scene, w, h, spp, rank, world, local_rank):
             mr, crays, csec, kind, cores = run_reference_cpu(scene, cw, ch, cspp)
             cpu = {"value": mr, "unit": "Mrays/s", "cores": cores, "kind": kind,
                    "sample": f"{scene_label(scene)} {cw}x{ch} {cspp}spp (same scene and camera, reduced pixels/spp), {int(crays)} rays in {csec:.2f} s"}
+            ow, oh, ospp = CPU_SAMPLE_1T[scene]
+            mr1, crays1, csec1, _, _ = run_reference_cpu(scene, ow, oh, ospp, threads=1)
+            cpu["one_thread"] = {"value": mr1, "unit": "Mrays/s", "cores": 1,
+                                 "sample": f"{scene_label(scene)} {ow}x{oh} {ospp}spp, {int(crays1)} rays in {csec1:.2f} s"}
         except Exception as e:  # noqa: BLE001
             cpu = {"value": None, "unit": "Mrays/s", "cores": os.cpu_count(), "kind": "unavailable", "sample": repr(e)}
         line = {
@@ -390,6 +519,7 @@ def bench_b200(args, scene, w, h, spp, rank, world, local_rank):
                     "ms_per_step": float(e2e_t.item()) / len(e2e_ms)},
             "gpu_launches": launches2 - launches1,
             "clocks": clk, "roofline": roofline, "cpu_baseline": cpu,
+            "configs": extra_configs, "hit_scene": hit_scene,
         }
         print(json.dumps(line), flush=True)
     sc.close()
@@ -409,6 +539,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="sponza_1080p_64spp", choices=sorted(WORKLOADS))
     ap.add_argument("--gather", default="peer", choices=["nccl", "peer"], help="N>1: how the frame reaches rank 0")
+    ap.add_argument("--no-extras", action="store_true", help="skip the `configs` (BASELINE configs 1-4) and `hit_scene` sections")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

@@ -133,17 +133,24 @@ int tmpt_progressive_begin(tmpt_scene* scene, int width, int height);
 int tmpt_progressive_pass(tmpt_scene* scene, const tmpt_camera* camera, int nChunks, int mem, uint8_t* rgba,
                           uint64_t* rayCount, double* seconds, int* samplesSoFar, void* stream);
 
-/* Multi-GPU form: this rank renders only the row stripes it owns -- stripe k (rows
- * [k*stripeRows, (k+1)*stripeRows)) belongs to rank k % worldSize -- and writes them
- * packed, stripe after stripe, into outStripes (device memory on the scene's device,
- * tmpt_stripe_rows(...) * width * 4 bytes).  Asynchronous on `stream`.  rayCountDev is a
+/* Multi-GPU form: this rank renders only its share of the frame and writes it packed into
+ * outStripes (device memory on the scene's device, tmpt_stripe_rows(...) *
+ * tmpt_local_width(...) * 4 bytes).  Two partitions:
+ *   stripeRows > 0   row stripes: stripe k (rows [k*stripeRows, (k+1)*stripeRows)) belongs to
+ *                    rank k % worldSize; packed = owned rows, stripe after stripe;
+ *   stripeRows == 0  tile interleave (the default of multigpu.py and tmpt_render_multi): the
+ *                    8x4-pixel tile (tx, ty) belongs to rank (tx + ty) % worldSize, so every
+ *                    rank owns 1/worldSize of the tiles spread evenly over the frame; packed =
+ *                    [height][localWidth] with local tile tx / worldSize of each tile row.
+ * The frame does not depend on the partition (per-pixel RNG streams).  Asynchronous on `stream`.  rayCountDev is a
  * device uint64 the kernel adds to.  If peerFrame is non-NULL the pixels are written
  * straight into that full-size frame (width*height*4, possibly peer / IPC-mapped memory
  * on another GPU) instead -- the gather fused into the render epilogue. */
 int tmpt_render_stripes(const tmpt_scene* scene, const tmpt_camera* camera, int width, int height, int spp,
                         int stripeRows, int rank, int worldSize, uint8_t* outStripes, uint8_t* peerFrame,
                         uint64_t* rayCountDev, void* stream);
-int tmpt_stripe_rows(int height, int stripeRows, int rank, int worldSize); /* rows owned by rank */
+int tmpt_stripe_rows(int height, int stripeRows, int rank, int worldSize); /* rows of the rank's packed output */
+int tmpt_local_width(int width, int stripeRows, int worldSize);            /* pixels per row of it */
 /* Rank 0 after a gather: scatter worldSize packed stripe buffers (each padded to
  * maxRowsPerRank*width*4 bytes, rank-major) into the final frame.  Device pointers. */
 int tmpt_unpack_stripes(const uint8_t* gathered, int width, int height, int stripeRows, int worldSize,

@@ -41,13 +41,14 @@ void* emu_scene_create2(const float* tris9, int n, int builder, float cInner, fl
     s->tris9.assign(tris9, tris9 + (size_t)n * 9);
     s->nodes.assign((size_t)std::max(n, 1) * bvh::NODE_F4, make_float4(0, 0, 0, 0));
     s->tris.assign((size_t)std::max(n, 1) * 3, make_float4(0, 0, 0, 0));
-    s->view = bvh::SceneView{s->nodes.data(), s->tris.data(), s->tris9.data(), nullptr, n ? 0u : bvh::NONE, n, &s->status};
+    s->view = bvh::SceneView{s->nodes.data(), s->tris.data(), s->tris9.data(), nullptr, n ? 0u : bvh::NONE, n, &s->status, nullptr, 0.0f};
     if (n == 0) return s;
     // k_prim_bounds
     bld::Box scene{3.0e38f, 3.0e38f, 3.0e38f, -3.0e38f, -3.0e38f, -3.0e38f};
     for (int i = 0; i < n; ++i) scene = bld::box_union(scene, bld::tri_box(tris9 + (size_t)i * 9));
     const float maxAbs = std::max(std::max(std::max(std::fabs(scene.lox), std::fabs(scene.hix)), std::max(std::fabs(scene.loy), std::fabs(scene.hiy))),
                                   std::max(std::fabs(scene.loz), std::fabs(scene.hiz)));
+    s->view.farLimit = 16.0f * maxAbs;  // kernels.cu: bvh_far_limit
     // padded primitive boxes (k_prim_boxes)
     std::vector<bld::Box> pbox(n);
     for (int i = 0; i < n; ++i) {
@@ -96,9 +97,9 @@ void* emu_scene_create2(const float* tris9, int n, int builder, float cInner, fl
         }
     } else {
         // k_sah_level, serially: task = (node, first, count)
-        struct Task { int node, first, count; };
+        struct Task { int node, first, count, depth; };
         for (int i = 0; i < n; ++i) prim[i] = (uint32_t)i;
-        std::vector<Task> q{{0, 0, n}};
+        std::vector<Task> q{{0, 0, n, 0}};
         int nodeCounter = 1;
         std::vector<uint32_t> tmp(n);
         while (!q.empty()) {
@@ -126,7 +127,7 @@ void* emu_scene_create2(const float* tris9, int n, int builder, float cInner, fl
                 float costs[3 * (bld::SAH_BINS - 1)];
                 int lcs[3 * (bld::SAH_BINS - 1)];
                 for (int k = 0; k < 3 * (bld::SAH_BINS - 1); ++k) costs[k] = bld::sah_split_cost(bins[k / (bld::SAH_BINS - 1)], k % (bld::SAH_BINS - 1), &lcs[k]);
-                bld::SahDecision d = tk.count == 1 ? bld::SahDecision{-1, 0, 0} : bld::sah_decide(costs, lcs, tk.count, bld::box_half_area(nb), sp);
+                bld::SahDecision d = tk.count == 1 ? bld::SahDecision{-1, 0, 0} : bld::sah_decide(costs, lcs, tk.count, bld::box_half_area(nb), sp, tk.depth);
                 lo[tk.node] = make_float4(nb.lox, nb.loy, nb.loz, 0.0f);
                 first[tk.node] = tk.first;
                 if (d.axis < 0) {
@@ -144,8 +145,8 @@ void* emu_scene_create2(const float* tris9, int n, int builder, float cInner, fl
                 for (int i = 0; i < tk.count; ++i) prim[tk.first + i] = tmp[tk.first + i];
                 const int base = nodeCounter; nodeCounter += 2;
                 left[tk.node] = base; right[tk.node] = base + 1;
-                next.push_back({base, tk.first, nl});
-                next.push_back({base + 1, tk.first + nl, nr});
+                next.push_back({base, tk.first, nl, tk.depth + 1});
+                next.push_back({base + 1, tk.first + nl, nr, tk.depth + 1});
             }
             q.swap(next);
         }
@@ -197,6 +198,7 @@ void emu_scene_refit(void* h, const float* tris9) {
     for (int i = 0; i < s->n; ++i) scene = bld::box_union(scene, bld::tri_box(tris9 + (size_t)i * 9));
     const float maxAbs = std::max(std::max(std::max(std::fabs(scene.lox), std::fabs(scene.hix)), std::max(std::fabs(scene.loy), std::fabs(scene.hiy))),
                                   std::max(std::fabs(scene.loz), std::fabs(scene.hiz)));
+    s->view.farLimit = 16.0f * maxAbs;
     const float4* nodes = s->nodes.data();
     for (uint32_t i = s->counters[0]; i-- > 0;)
         bld::refit_wide_node(s->nodes.data(), s->tris.data(), s->tris9.data(), i, maxAbs,
@@ -274,6 +276,8 @@ void emu_render_stats(void* h, const float cam22[22], int w, int hgt, int spp, u
 }
 
 void emu_sincos(float a, float* s, float* c) { ex::sincos_spec(a, *s, *c); }
+int emu_sah_must_halve(int depth, int count) { return bld::sah_must_halve(depth, count) ? 1 : 0; }
+int emu_max_tree_depth() { return bvh::MAX_TREE_DEPTH; }
 uint32_t emu_pixel_seed(uint32_t i) { return ex::pixel_seed(i); }
 uint32_t emu_chunk_seed(uint32_t chunk, uint32_t pixel, uint32_t pixels) { return ex::chunk_seed(chunk, pixel, pixels); }
 }

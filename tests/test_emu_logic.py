@@ -264,3 +264,70 @@ def test_sponza_traversal_equals_reference_hits(emu, builder):
     assert (bits(pos)[hit] == bits(g["pos"])[hit]).all() and (bits(nrm)[hit] == bits(g["normal"])[hit]).all()
     aid, *_ = s.hit(g["rays"], mode=1)
     assert ((aid == 1) == hit).all()
+
+
+def test_distant_origins_take_the_exact_scan(emu, oracle):
+    """Host emulation of bvh::ray_is_far: origins from 10 to a million scene sizes away give the oracle's answers."""
+    sc = load_scene("suzanne")
+    rng = np.random.default_rng(42)
+    mn, mx = sc["bounds_min"].astype(np.float64), sc["bounds_max"].astype(np.float64)
+    size = float(np.abs(np.concatenate([mn, mx])).max())
+    n = 4000
+    target = rng.uniform(mn, mx, (n, 3))
+    away = rng.normal(size=(n, 3)); away /= np.linalg.norm(away, axis=1, keepdims=True)
+    o = target + away * size * (10.0 ** rng.uniform(0.3, 6.0, (n, 1)))
+    d = target - o; d /= np.linalg.norm(d, axis=1, keepdims=True)
+    rays = np.concatenate([o, d], 1).astype(np.float32)
+    ids, t, pos, nrm = emu.scene(sc["tris"]).hit(rays, tmax=3.0e38)
+    oid, ot, opos, onrm = oracle.hit_brute(sc["tris"], rays, tmax=3.0e38)
+    hit = oid >= 0
+    assert hit.sum() > 100 and (ids == oid).all() and (bits(t)[hit] == bits(ot)[hit]).all() and (bits(pos)[hit] == bits(opos)[hit]).all()
+
+
+def _graded_mesh(scales=70, per_scale=6, seed=5):
+    """Triangles graded over 70 binary orders of magnitude (2^-35 .. 2^35): binned SAH peels off the largest scale level after
+    level, the lopsided tree the depth guarantee (build_logic.cuh: sah_must_halve) exists for."""
+    rng = np.random.default_rng(seed)
+    tris = []
+    for k in range(scales):
+        s = 2.0 ** (k - scales // 2)
+        for _ in range(per_scale):
+            c = rng.uniform(-1, 1, 3) * s
+            tris.append((c[None, :] + rng.normal(scale=0.2 * s, size=(3, 3))).ravel())
+    return np.asarray(tris, np.float32)
+
+
+def test_sah_depth_guarantee_arithmetic(emu):
+    """bld::sah_must_halve: once depth + ceil(log2(count)) reaches the limit a task is halved by position, and both halves are
+    again at (or one under) the limit with one level more and half the count -- so no leaf can lie deeper than
+    bvh::MAX_TREE_DEPTH, which is what the traversal stack (3 entries per level + 4) holds."""
+    L = emu.L
+    limit = L.emu_max_tree_depth()
+    assert 3 * limit + 4 <= 128 and limit >= 40
+    for count in [2, 3, 9, 100, 66452, 500000, (1 << 28) - 2]:
+        depth = 0
+        while not L.emu_sah_must_halve(depth, count):
+            depth += 1                      # the deepest a SAH split chain can take a task of this size
+        c, d = count, depth
+        while c > 1:                        # from here on: halving only
+            assert L.emu_sah_must_halve(d, c)
+            c, d = (c + 1) // 2, d + 1
+        assert d <= limit
+    assert not L.emu_sah_must_halve(0, 66452) and not L.emu_sah_must_halve(22, 8)   # the Sponza stand-in stays SAH all the way
+
+
+def test_sah_depth_is_bounded_on_a_graded_mesh(emu):
+    tris = _graded_mesh()
+    s = emu.scene(tris)
+    info = s.info()
+    assert info["slots"] == tris.shape[0] and info["max_depth"] <= 41 and info["status"] == 0
+    rng = np.random.default_rng(6)
+    k = rng.integers(0, tris.shape[0], 3000)
+    target = tris.reshape(-1, 3, 3)[k].mean(1).astype(np.float64)
+    scale = np.abs(target).max(1, keepdims=True) + 1e-30
+    o = target + rng.normal(size=target.shape) * scale * 3
+    d = target - o; d /= np.linalg.norm(d, axis=1, keepdims=True)
+    rays = np.concatenate([o, d], 1).astype(np.float32)
+    a, b = s.hit(rays, tmin=0.0, tmax=3.0e38), s.hit(rays, tmin=0.0, tmax=3.0e38, mode=2)
+    hit = b[0] >= 0
+    assert hit.sum() > 500 and (a[0] == b[0]).all() and (bits(a[1])[hit] == bits(b[1])[hit]).all()

@@ -24,6 +24,10 @@ def _free_port():
 def _numpy_unpack(gathered, width, height, stripe, world):
     g = gathered.numpy()
     frame = np.zeros((height, width, 4), np.uint8)
+    if stripe == 0:  # tile interleave: rank (tx + ty) % world, local tile tx // world (k_unpack_stripes)
+        owner, xl = multigpu.tile_owner_maps(width, height, world)
+        ys = np.arange(height)[:, None].repeat(width, 1)
+        return torch.from_numpy(g[owner, ys, xl])
     for r in range(world):
         ys = multigpu.owned_rows(height, stripe, r, world)
         frame[ys] = g[r, : len(ys)]
@@ -39,12 +43,18 @@ def _worker(rank, world, port, width, height, stripe, out):
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
         rows, max_rows = multigpu.stripe_plan(height, stripe, world)
-        assert rows[rank] == tm.stripe_rows(height, stripe, rank, world)  # host plan == C ABI
+        lw = multigpu.local_width(width, stripe, world)
+        assert rows[rank] == tm.stripe_rows(height, stripe, rank, world) and lw == tm.local_width(width, stripe, world)  # host plan == C ABI
         ys = multigpu.owned_rows(height, stripe, rank, world)
         assert len(ys) == rows[rank]
-        packed = np.zeros((max_rows, width, 4), np.uint8)
-        yy, xx = np.meshgrid(ys, np.arange(width), indexing="ij")
-        packed[: len(ys)] = _pixel(yy, xx)
+        packed = np.zeros((max_rows, lw, 4), np.uint8)
+        if stripe == 0:  # what this rank's render kernel would write: its tiles, local tile ltx of tile row ty = frame tile ((rank - ty) % world) + ltx * world
+            yy, xl = np.meshgrid(np.arange(height), np.arange(lw), indexing="ij")
+            xx = (((rank - yy // 4) % world) + (xl // 8) * world) * 8 + xl % 8
+            packed[:] = np.where((xx < width)[..., None], _pixel(yy, np.minimum(xx, width - 1)), 0)
+        else:
+            yy, xx = np.meshgrid(ys, np.arange(width), indexing="ij")
+            packed[: len(ys)] = _pixel(yy, xx)
         frame = multigpu.gather_frame(torch.from_numpy(packed), width, height, stripe, rank, world, unpack=_numpy_unpack)
         rays = torch.tensor([1000 + rank], dtype=torch.int64)
         dist.all_reduce(rays)
@@ -58,7 +68,7 @@ def _worker(rank, world, port, width, height, stripe, out):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world,width,height,stripe", [(2, 64, 36, 4), (2, 33, 13, 4), (3, 16, 50, 8)])
+@pytest.mark.parametrize("world,width,height,stripe", [(2, 64, 36, 4), (2, 33, 13, 4), (3, 16, 50, 8), (2, 64, 36, 0), (3, 50, 23, 0), (2, 7, 3, 0)])
 def test_stripe_gather_over_gloo(world, width, height, stripe):
     ctx = mp.get_context("spawn")
     out = ctx.SimpleQueue()

@@ -1,6 +1,6 @@
 #!/usr/bin/env python
-"""Per-rank work balance of the stripe partition, emulated on ONE GPU: render rank k's stripes of a
-`world`-way split for every k and time each (development tool)."""
+"""Per-rank work balance of a partition (--stripe 0: tile interleave, the default; > 0: row stripes), emulated on ONE GPU:
+render rank k's share of a `world`-way split for every k and time each (development tool)."""
 import argparse, os, sys
 import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))

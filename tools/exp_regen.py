@@ -21,6 +21,7 @@ ap.add_argument("--width", type=int, default=640)
 ap.add_argument("--height", type=int, default=360)
 ap.add_argument("--spp", type=int, default=16)
 ap.add_argument("--reps", type=int, default=2)
+ap.add_argument("--stats", action="store_true", help="also run the instrumented pass and print its counters")
 a = ap.parse_args()
 path = scene_obj_path(a.scene)
 tris, mn, mx = tm.load_scene(path)
@@ -30,5 +31,9 @@ best = 1e30
 for _ in range(a.reps + 1):
     rgba, rays, sec = sc.render(cam, a.width, a.height, a.spp)
     best = min(best, sec)
-print("kernel %s %s %dx%dx%d sha %s rays %d  %.1f Mrays/s (%.2f ms)" % (os.environ.get("TMPT_RENDER_KERNEL", "0"), a.scene, a.width, a.height,
-      a.spp, hashlib.sha256(rgba.tobytes()).hexdigest()[:16], rays, rays / best / 1e6, best * 1e3))
+print("lib %s kernel %s %s %dx%dx%d sha %s rays %d  %.1f Mrays/s (%.2f ms)  build %.2f ms" % (
+      os.path.basename(os.environ.get("TMPT_LIB", "libtmpt.so")), os.environ.get("TMPT_RENDER_KERNEL", "0"), a.scene, a.width, a.height,
+      a.spp, hashlib.sha256(rgba.tobytes()).hexdigest()[:16], rays, rays / best / 1e6, best * 1e3, sc.info()["build_ms"]))
+if a.stats:
+    import json
+    print(json.dumps(sc.traversal_stats(cam, a.width, a.height, a.spp)))

@@ -1,6 +1,8 @@
 #!/usr/bin/env python
-"""Small end-to-end run for compute-sanitizer (development): build (both builders), HitScene, render with several chunks,
-refit, progressive passes.    compute-sanitizer --tool memcheck python tools/san_check.py"""
+"""Small end-to-end run of every entry point (development): build (both builders), HitScene, render with several chunks,
+refit, progressive passes.    python tools/san_check.py
+(Written as the workload for compute-sanitizer's memcheck; this pool's GPU boxes do not allow the sanitizer to attach
+-- gpurun_out/san_memcheck.log -- so it is run plain, as a smoke test of the whole ABI.)"""
 import os
 import sys
 

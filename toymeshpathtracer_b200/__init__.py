@@ -34,7 +34,7 @@ K_MIN_T, K_MAX_T = 0.001, 1.0e7  # main.cpp:30-31
 # every symbol include/tmpt.h declares (tests check the library exports exactly these)
 ABI_SYMBOLS = [
     "tmpt_scene_create", "tmpt_scene_destroy", "tmpt_scene_get_info", "tmpt_hit_scene", "tmpt_render",
-    "tmpt_render_stripes", "tmpt_stripe_rows", "tmpt_unpack_stripes", "tmpt_load_obj", "tmpt_free",
+    "tmpt_render_stripes", "tmpt_stripe_rows", "tmpt_local_width", "tmpt_unpack_stripes", "tmpt_load_obj", "tmpt_free",
     "tmpt_camera_make", "tmpt_camera_for_scene", "tmpt_write_png", "tmpt_main", "tmpt_last_error",
     "tmpt_device_count", "tmpt_launch_count", "tmpt_render_stats", "tmpt_hit_scene_stats",
     "tmpt_frame_alloc", "tmpt_frame_open", "tmpt_frame_close", "tmpt_frame_free", "tmpt_render_multi",
@@ -90,6 +90,7 @@ def lib() -> C.CDLL:
     L.tmpt_progressive_pass.argtypes = [vp, vp, i32, i32, vp, C.POINTER(C.c_uint64), C.POINTER(C.c_double), C.POINTER(i32), vp]
     L.tmpt_render_stripes.argtypes = [vp, vp, i32, i32, i32, i32, i32, i32, vp, vp, vp, vp]
     L.tmpt_stripe_rows.argtypes = [i32, i32, i32, i32]
+    L.tmpt_local_width.argtypes = [i32, i32, i32]
     L.tmpt_unpack_stripes.argtypes = [vp, i32, i32, i32, i32, i32, vp, vp]
     L.tmpt_render_stats.argtypes = [vp, vp, i32, i32, i32, vp]
     L.tmpt_hit_scene_stats.argtypes = [vp, vp, i64, f32, f32, i32, vp]
@@ -185,6 +186,10 @@ def write_png(path: str, rgba: np.ndarray, flip_vertically: bool = True) -> None
 
 def stripe_rows(height: int, stripe: int, rank: int, world: int) -> int:
     return lib().tmpt_stripe_rows(height, stripe, rank, world)
+
+
+def local_width(width: int, stripe: int, world: int) -> int:
+    return lib().tmpt_local_width(width, stripe, world)
 
 
 def main(argv) -> int:

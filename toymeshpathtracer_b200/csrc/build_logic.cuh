@@ -5,7 +5,7 @@
 // rebuilt.  Pipeline (kernels.cu drives it, one launch per stage):
 //   1 prim_bounds   triangle AABBs + scene bounds (atomic min/max on order-preserving ints)
 //   2 morton_keys   63-bit Morton code of the box centre; padded triangle boxes
-//   3 radix sort    (key, prim) pairs, 8 passes of 8 bits            [kernels.cu]
+//   3 radix sort    (key, prim) pairs, 16 passes of 4 bits           [kernels.cu]
 //   4 karras_node   binary radix tree over the sorted keys (Karras 2012), index tie-break
 //   5 refit_up      bottom-up boxes, subtree counts, SAH cost and the leaf decision
 //   6 collapse_node top-down: binary tree -> 4-wide nodes + leaf triangle slots
@@ -170,7 +170,10 @@ TMPT_HD void refit_node(const BinTree& t, int i, const SahParams& sp) {
 }
 
 // ---- binned SAH (top-down builder): per-task logic shared by the kernel and the host emulation ----
-constexpr int SAH_BINS = 16;
+#ifndef TMPT_SAH_BINS
+#define TMPT_SAH_BINS 16
+#endif
+constexpr int SAH_BINS = TMPT_SAH_BINS;
 struct SahBin {
     Box box;
     int count;
@@ -199,13 +202,23 @@ TMPT_HD float sah_split_cost(const SahBin* bins, int split, int* outLeftCount) {
     return box_half_area(l) * (float)nl + box_half_area(r) * (float)nr;
 }
 
+// Depth guarantee.  The traversal stack holds bvh::STACK_SIZE entries, enough for bvh::MAX_TREE_DEPTH levels.  SAH splits can
+// be arbitrarily lopsided (a mesh graded over many scales peels off one triangle per level), so the builder watches
+// depth + ceil(log2(count)) of every task: once that reaches the limit the task is halved by position instead, which keeps the
+// sum constant from there on -- no subtree can end deeper than the limit, whatever the input.  Healthy scenes never get
+// near it (the Sponza stand-in: root 17, deepest task 25 of 40).
+constexpr int SAH_DEPTH_LIMIT = bvh::MAX_TREE_DEPTH - 1;
+TMPT_HD int ceil_log2(int n) { int k = 0; while ((1 << k) < n) ++k; return k; }
+TMPT_HD bool sah_must_halve(int depth, int count) { return depth + ceil_log2(count) >= SAH_DEPTH_LIMIT; }
+
 struct SahDecision {
     int axis;       // -1: make a leaf; 3: median split by position (binning found nothing)
     int split;      // last bin of the left side
     int leftCount;
 };
 // costs[axis * (SAH_BINS-1) + split] as computed by sah_split_cost; nodeArea = half area of the node box
-TMPT_HD SahDecision sah_decide(const float* costs, const int* leftCounts, int count, float nodeArea, const SahParams& sp) {
+TMPT_HD SahDecision sah_decide(const float* costs, const int* leftCounts, int count, float nodeArea, const SahParams& sp, int depth = 0) {
+    if (sah_must_halve(depth, count)) return count <= sp.maxLeaf ? SahDecision{-1, 0, 0} : SahDecision{3, 0, count / 2};
     SahDecision d{-1, 0, 0};
     float best = 3.0e38f;
     for (int k = 0; k < 3 * (SAH_BINS - 1); ++k) {

@@ -45,7 +45,11 @@ constexpr int MAX_LEAF_TRIS = 8;
 constexpr int WIDTH = 4;
 constexpr int NODE_F4 = 7;              // float4 rows per float node (112 bytes)
 constexpr int QNODE_ROWS = 4;           // 16-byte rows per quantised node (64 bytes)
-constexpr int STACK_SIZE = 64;         // entries; the builder reports the depth it needs
+#ifndef TMPT_STACK_SIZE
+#define TMPT_STACK_SIZE 128
+#endif
+constexpr int STACK_SIZE = TMPT_STACK_SIZE;  // entries.  A node step pushes at most 3 and descends one level: a tree of depth D needs 3 D + 4.
+constexpr int MAX_TREE_DEPTH = (STACK_SIZE - 4) / 3;  // 41 levels; the SAH builder never exceeds it (build_logic.cuh: sah_must_halve)
 constexpr uint32_t NONE = 0xFFFFFFFFu;     // empty child / empty stack; no leaf ref reaches it (slots < 2^28 - 1)
 constexpr uint32_t STACK_OVERFLOW = 1;  // bit in the scene's device status word
 
@@ -62,7 +66,8 @@ struct SceneView {
     uint32_t rootRef;     // may itself be a leaf ref for tiny scenes
     int triCount;
     uint32_t* status;     // device status word (STACK_OVERFLOW)
-    const uint4* qnodes;  // QNODE_ROWS rows per node: the quantised form of `nodes` the walk reads (TMPT_QNODES)
+    const uint4* qnodes;  // QNODE_ROWS rows per node: the quantised form of `nodes` (only in a -DTMPT_QNODES=1 build)
+    float farLimit;       // rays whose origin has a component beyond this are answered by the all-triangle scan (ray_is_far); <= 0: no limit
 };
 
 struct HitRec {
@@ -232,6 +237,15 @@ TMPT_HD float fmaf_(float a, float b, float c) {
 // produces them).  Traversal starts from an empty root for these rays.
 TMPT_HD bool ray_has_nan(ex::V3 o, ex::V3 d) { return o.x != o.x || o.y != o.y || o.z != o.z || d.x != d.x || d.y != d.y || d.z != d.z; }
 
+// The boxes are padded for rays that start within a few scene sizes of the scene (build_logic.cuh: pad_for): the slab
+// arithmetic's rounding error grows with |origin| (t = plane / d - origin / d cancels two numbers of that size), the padding does
+// not.  A ray that starts further out than farLimit = 16 x the scene's largest |coordinate| -- 2.5x inside what the padding
+// covers -- is therefore answered by the all-triangle scan, which is exact by definition; the camera and every hit point of a
+// render are far inside the limit, so only tmpt_hit_scene callers with distant origins ever pay for it.
+TMPT_HD bool ray_is_far(const SceneView& sc, ex::V3 o) {
+    return sc.farLimit > 0.0f && fmaxf(fmaxf(fabsf(o.x), fabsf(o.y)), fabsf(o.z)) > sc.farLimit;
+}
+
 // One traversal, closest (ANY=false) or any-hit (ANY=true).
 //
 // Node step: the near / far slab planes are picked by the ray's octant through the LOAD
@@ -315,7 +329,8 @@ TMPT_HD uint32_t wide_node_step(const SceneView& sc, uint32_t node, const RayCtx
     return enter_and_push(a, b, ref, stack, sp, anyRay);
 }
 
-// ---- quantised nodes (TMPT_QNODES, the default): 64 bytes = 4 rows instead of 7 -------------------------------------------
+// ---- quantised nodes (compile-time -DTMPT_QNODES=1; measured 8-14 % slower than the float nodes on B200, NOT the default,
+// DESIGN.md 5): 64 bytes = 4 rows instead of 7 ------------------------------------------------------------------------------
 // The walk is bound by the L1 data stage -- 16-byte rows gathered per ray -- so a node is stored the way
 // Ylitie, Karras & Laine 2017 ("Efficient incoherent ray traversal on GPUs through compressed wide BVHs") store theirs:
 // child planes as 8-bit offsets on a per-node grid, plane = origin + q * 2^e per axis.
@@ -512,8 +527,34 @@ TMPT_HD bool walk_step(WalkState& w, const SceneView& sc, float tMin, float tMax
     return done;
 }
 
+// Upstream's HitScene: every triangle, no tree.  Same candidate rule, so it must agree with
+// traverse<false> bit for bit -- the on-GPU cross-check of box conservativeness at sizes the
+// CPU checker cannot reach (TMPT_HIT_BRUTE) -- and the answer for rays that start too far from the scene for the padded
+// boxes (ray_is_far).  Out of line on the device: it is never part of a hot loop.
+#ifdef __CUDA_ARCH__
+__device__ __noinline__
+#else
+inline
+#endif
+HitRec scan_all(const float4* tris, int triCount, ex::V3 o, ex::V3 d, float tMin, float tMax) {
+    HitRec best;
+    best.id = -1; best.t = tMax; best.u = 0.0f; best.v = 0.0f;
+    for (int k = 0; k < triCount; ++k) {
+        const float4* tp = tris + (size_t)k * 3;
+        const float4 a = TMPT_LDG4(tp + 0), b = TMPT_LDG4(tp + 1), c = TMPT_LDG4(tp + 2);
+        float t, u, v;
+        if (mt_exact(o, d, ex::v3(a.x, a.y, a.z), ex::v3(b.x, b.y, b.z), ex::v3(c.x, c.y, c.z), tMin, tMax, t, u, v)) {
+            const int id = (int)ex::f2u(a.w);
+            if (t < best.t || (t == best.t && best.id >= 0 && id < best.id)) { best.t = t; best.id = id; best.u = u; best.v = v; }
+        }
+    }
+    return best;
+}
+TMPT_HD HitRec brute_force(const SceneView& sc, ex::V3 o, ex::V3 d, float tMin, float tMax) { return scan_all(sc.tris, sc.triCount, o, d, tMin, tMax); }
+
 template <bool ANY, bool STATS = false>
 TMPT_HD HitRec traverse(const SceneView& sc, ex::V3 o, ex::V3 d, float tMin, float tMax, TravStats* stats = nullptr) {
+    if (ray_is_far(sc, o)) return scan_all(sc.tris, sc.triCount, o, d, tMin, tMax);
     LocalStack stack;
     WalkState w;
     walk_start(w, sc, o, d, tMax, ANY);
@@ -529,8 +570,11 @@ inline
 #endif
 HitRec traverse_again(const SceneView& sc, ex::V3 o, ex::V3 d, float tMin, float tMax) { return traverse<ANY, false>(sc, o, d, tMin, tMax); }
 
-template <bool ANY, bool STATS, class Stack>
+// FAR: check ray_is_far.  The batched HitScene kernels always do (the rays are the caller's); the render kernel only in the
+// instantiation launch_render picks when the CAMERA stands beyond the limit -- every other ray of a path starts on a triangle.
+template <bool ANY, bool STATS, bool FAR, class Stack>
 TMPT_HD HitRec traverse_with(Stack& stack, const SceneView& sc, ex::V3 o, ex::V3 d, float tMin, float tMax, TravStats* stats = nullptr) {
+    if (FAR && ray_is_far(sc, o)) return scan_all(sc.tris, sc.triCount, o, d, tMin, tMax);
     WalkState w;
     walk_start(w, sc, o, d, tMax, ANY);
     while (!walk_step<STATS>(w, sc, tMin, tMax, stack, stats)) {}
@@ -541,24 +585,6 @@ TMPT_HD HitRec traverse_with(Stack& stack, const SceneView& sc, ex::V3 o, ex::V3
         if (!(ANY && w.best.id >= 0)) return traverse_again<ANY>(sc, o, d, tMin, tMax);
     }
     return w.best;
-}
-
-// Upstream's HitScene: every triangle, no tree.  Same candidate rule, so it must agree with
-// traverse<false> bit for bit -- the on-GPU cross-check of box conservativeness at sizes the
-// CPU checker cannot reach (TMPT_HIT_BRUTE).
-TMPT_HD HitRec brute_force(const SceneView& sc, ex::V3 o, ex::V3 d, float tMin, float tMax) {
-    HitRec best;
-    best.id = -1; best.t = tMax; best.u = 0.0f; best.v = 0.0f;
-    for (int k = 0; k < sc.triCount; ++k) {
-        const float4* tp = sc.tris + (size_t)k * 3;
-        const float4 a = TMPT_LDG4(tp + 0), b = TMPT_LDG4(tp + 1), c = TMPT_LDG4(tp + 2);
-        float t, u, v;
-        if (mt_exact(o, d, ex::v3(a.x, a.y, a.z), ex::v3(b.x, b.y, b.z), ex::v3(c.x, c.y, c.z), tMin, tMax, t, u, v)) {
-            const int id = (int)ex::f2u(a.w);
-            if (t < best.t || (t == best.t && best.id >= 0 && id < best.id)) { best.t = t; best.id = id; best.u = u; best.v = v; }
-        }
-    }
-    return best;
 }
 
 }  // namespace bvh

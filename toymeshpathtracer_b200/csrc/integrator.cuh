@@ -81,7 +81,7 @@ TMPT_HD uchar4 resolve_pixel(ex::V3 sum, float sppRecip) {
 // One whole pixel, serially: the straightforward form used by the host emulation and by the
 // first (non-wavefront) render kernel.  kk[] holds the per-bounce sun term (0 for a
 // shadowed bounce).
-template <bool STATS = false, class Stack, class Scene>
+template <bool STATS = false, bool FAR = true, class Stack, class Scene>
 TMPT_HD ex::V3 trace_path(Stack& stack, const Scene& sc, const Camera& cam, ex::V3 o, ex::V3 d, ex::V3 lightDir, uint32_t& rng,
                           unsigned long long& rays, bvh::TravStats* stats = nullptr) {
     float kk[kMaxDepth];
@@ -89,12 +89,12 @@ TMPT_HD ex::V3 trace_path(Stack& stack, const Scene& sc, const Camera& cam, ex::
     ex::V3 color = ex::v3(0.0f, 0.0f, 0.0f);
     while (depth < kMaxDepth) {
         ++rays;
-        const bvh::HitRec h = bvh::traverse_with<false, STATS>(stack, sc, o, d, kMinT, kMaxT, stats);
+        const bvh::HitRec h = bvh::traverse_with<false, STATS, FAR>(stack, sc, o, d, kMinT, kMaxT, stats);
         if (h.id < 0) { color = sky(d); break; }
         ex::V3 pos, normal;
         bvh::hit_payload(sc, h.id, h.u, h.v, pos, normal);
         ++rays;
-        const bvh::HitRec sh = bvh::traverse_with<true, STATS>(stack, sc, pos, lightDir, kMinT, kMaxT, stats);
+        const bvh::HitRec sh = bvh::traverse_with<true, STATS, FAR>(stack, sc, pos, lightDir, kMinT, kMaxT, stats);
         kk[depth] = sh.id < 0 ? sun_term(normal, d, lightDir) : 0.0f;
         d = scatter_dir(pos, normal, rng);
         o = pos;
@@ -121,7 +121,7 @@ TMPT_HD int chunk_len(int spp) {
 TMPT_HD int chunk_count(int spp) { const int c = chunk_len(spp); return (spp + c - 1) / c; }
 
 // `len` = samples per chunk: chunk_len(spp) for a one-shot frame, kMaxChunkSamples for a progressive pass
-template <bool STATS = false, class Stack, class Scene>
+template <bool STATS = false, bool FAR = true, class Stack, class Scene>
 TMPT_HD ex::V3 render_chunk(Stack& stack, const Scene& sc, const Camera& cam, int x, int y, int chunk, int width, int height, int spp, int len, ex::V3 lightDir,
                             unsigned long long& rays, bvh::TravStats* stats = nullptr) {
     const float invW = ex::divf(1.0f, (float)width), invH = ex::divf(1.0f, (float)height);
@@ -131,7 +131,7 @@ TMPT_HD ex::V3 render_chunk(Stack& stack, const Scene& sc, const Camera& cam, in
     for (int s = s0; s < s1; ++s) {
         ex::V3 o, d;
         primary_ray(cam, x, y, invW, invH, rng, o, d);
-        sum = ex::add(sum, trace_path<STATS>(stack, sc, cam, o, d, lightDir, rng, rays, stats));
+        sum = ex::add(sum, trace_path<STATS, FAR>(stack, sc, cam, o, d, lightDir, rng, rays, stats));
     }
     return sum;
 }

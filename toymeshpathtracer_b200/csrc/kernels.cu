@@ -15,10 +15,12 @@
 
 #include <atomic>
 #include <chrono>
+#include <cmath>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <new>
 #include <string>
 #include <vector>
@@ -85,8 +87,8 @@ struct tmpt_scene {
     int smCount = 148;
     cudaStream_t stream = nullptr;
     float* d_tris9 = nullptr;      // caller's triangles, original order
-    float4* d_nodes = nullptr;     // wide nodes (float form: builder output, experimental kernels)
-    uint4* d_qnodes = nullptr;     // wide nodes, quantised (what the walk reads)
+    float4* d_nodes = nullptr;     // wide nodes, 7 x float4 each: what the walk reads
+    uint4* d_qnodes = nullptr;     // wide nodes, quantised: only in a -DTMPT_QNODES=1 build (an experiment, not the default)
     float4* d_tris = nullptr;      // leaf-ordered MT slots
     float4* d_hitdata = nullptr;   // per original triangle: vertices + precomputed normal
     uint32_t* d_parent = nullptr;  // per wide node: parent index (refit)
@@ -104,6 +106,13 @@ struct tmpt_scene {
     float4* d_sum = nullptr;       // progressive render: running per-pixel sums
     size_t sumBytes = 0;
     int progW = 0, progH = 0, progChunks = -1;  // -1: no progressive render begun
+    // staging of tmpt_hit_scene(TMPT_HOST): one device and one pinned host buffer per scene, grown on demand and reused (the
+    // entry point is called in a loop by batched-query users: five cudaMalloc / cudaFree pairs and pageable copies per call
+    // cost more than the kernel for batches under a million rays)
+    char* d_stage = nullptr;
+    char* h_stage = nullptr;
+    size_t stageBytes = 0;
+    std::mutex hostCallMutex;      // serialises the entry points that use per-scene scratch (staging, frame, accum, counters)
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     bvh::SceneView view{};
     tmpt_scene_info info{};
@@ -290,7 +299,7 @@ __global__ void k_prim_boxes(const float* __restrict__ tris9, int n, const uint3
 }
 
 struct SahTask {
-    int node, first, count;
+    int node, first, count, depth;
 };
 constexpr int SAH_THREADS = 256;
 
@@ -377,7 +386,7 @@ __device__ __forceinline__ void sah_task(const SahTask tk, const bld::BinTree& t
     }
     __syncthreads();
     if (tid == 0) {
-        const bld::SahDecision d = tk.count == 1 ? bld::SahDecision{-1, 0, 0} : bld::sah_decide(sCost, sLeft, tk.count, bld::box_half_area(nodeBox), sp);
+        const bld::SahDecision d = tk.count == 1 ? bld::SahDecision{-1, 0, 0} : bld::sah_decide(sCost, sLeft, tk.count, bld::box_half_area(nodeBox), sp, tk.depth);
         sDec = d;
         t.lo[tk.node] = make_float4(nodeBox.lox, nodeBox.loy, nodeBox.loz, 0.0f);
         t.first[tk.node] = tk.first;
@@ -389,8 +398,8 @@ __device__ __forceinline__ void sah_task(const SahTask tk, const bld::BinTree& t
             t.left[tk.node] = base;
             t.right[tk.node] = base + 1;
             const uint32_t q = atomicAdd(outCount, 2u);
-            outQ[q] = SahTask{base, tk.first, d.leftCount};
-            outQ[q + 1] = SahTask{base + 1, tk.first + d.leftCount, tk.count - d.leftCount};
+            outQ[q] = SahTask{base, tk.first, d.leftCount, tk.depth + 1};
+            outQ[q + 1] = SahTask{base + 1, tk.first + d.leftCount, tk.count - d.leftCount, tk.depth + 1};
         }
     }
     __syncthreads();
@@ -443,7 +452,7 @@ __global__ void __launch_bounds__(SAH_THREADS) k_sah_build(bld::BinTree t, const
         const SahTask* inQ = (level & 1) ? qB : qA;
         SahTask* outQ = (level & 1) ? qA : qB;
         for (uint32_t k = blockIdx.x; k < cnt; k += gridDim.x) {
-            const SahTask tk{__ldcg(&inQ[k].node), __ldcg(&inQ[k].first), __ldcg(&inQ[k].count)};
+            const SahTask tk{__ldcg(&inQ[k].node), __ldcg(&inQ[k].first), __ldcg(&inQ[k].count), __ldcg(&inQ[k].depth)};
             sah_task(tk, t, pLo, pHi, idxIn, idxOut, primFinal, outQ, &counts[(level + 1) % 3], nodeCounter, sp);
             __syncthreads();  // the task's shared arrays are reused by the next one
         }
@@ -720,7 +729,8 @@ struct RenderParams {
     integ::Camera cam;
     ex::V3 lightDir;
     int width, height, spp;
-    int stripeRows, rank, world, ownedRows;
+    int stripeRows, rank, world, ownedRows;  // stripeRows == 0: tile-interleaved partition (see local_to_global)
+    int localWidth;      // width of this rank's LOCAL image: the frame's width (row stripes) or its share of every row (tile interleave)
     int tilesX, numTiles;
     int chunks;          // sample chunks per pixel rendered by this launch
     int chunk0, chunkLen; // first chunk index (progressive passes continue where the last one stopped), samples per chunk
@@ -739,6 +749,28 @@ struct RenderParams {
 __device__ __forceinline__ int owned_row_to_global(int r, int stripeRows, int rank, int world) {
     const int ls = r / stripeRows;
     return (ls * world + rank) * stripeRows + (r - ls * stripeRows);
+}
+// The two partitions of a frame over `world` ranks, both as a map from a rank's LOCAL image (ownedRows x localWidth, the
+// layout of its accumulation planes and of its packed output) to frame pixels:
+//   row stripes (stripeRows > 0): stripe k = rows [k * stripeRows, (k+1) * stripeRows) belongs to rank k % world; a local row
+//     is an owned row, local x = x.
+//   tile interleave (stripeRows == 0): the 8x4-pixel tile (tx, ty) belongs to rank (tx + ty) % world -- every rank owns every
+//     world-th tile of every tile row, shifted by one from row to row, i.e. exactly 1/world of the tiles, spread evenly over
+//     the frame: the partition is balanced in tile COUNT whatever the frame height (row stripes of four rows give two of
+//     eight ranks 33 instead of 34 stripes of a 1080-row frame) and in COST, because every rank samples the whole frame.
+//     Local row = frame row; local tile ltx of tile row ty is frame tile ((rank - ty) mod world) + ltx * world.
+// Returns false for local pixels that fall outside the frame (the last local tile of a row, when tilesX % world != 0).
+__device__ __forceinline__ bool local_to_global(int xl, int r, int stripeRows, int rank, int world, int width, int& x, int& y) {
+    if (stripeRows > 0) {
+        x = xl;
+        y = owned_row_to_global(r, stripeRows, rank, world);
+        return true;
+    }
+    y = r;
+    int t0 = (rank - (r >> 2)) % world;
+    t0 += t0 < 0 ? world : 0;
+    x = ((t0 + (xl >> 3) * world) << 3) + (xl & 7);
+    return x < width;
 }
 
 // SSTACK = traversal-stack entries per lane kept in shared memory (0: the whole stack is a local-memory array); the launch
@@ -762,7 +794,10 @@ struct RenderStack<0, THREADS> {
 #endif
 constexpr int kSStack = TMPT_SSTACK;
 
-template <bool STATS, int THREADS, int MINB, int SSTACK>
+// FAR = the camera stands beyond the scene's far limit (bvh.cuh: ray_is_far): rays are checked and, if far, answered by the
+// exact all-triangle scan.  Only the 256-thread configuration has that instantiation (a camera sixteen scene sizes away sees
+// a few pixels of scene).
+template <bool STATS, int THREADS, int MINB, int SSTACK, bool FAR = false>
 __global__ void __launch_bounds__(THREADS, MINB) k_render(const RenderParams p) {
     const int lane = threadIdx.x & 31;
     unsigned long long rays = 0;
@@ -776,16 +811,16 @@ __global__ void __launch_bounds__(THREADS, MINB) k_render(const RenderParams p) 
         const int chunk = (int)(tile / (uint32_t)p.numTiles);
         tile -= (uint32_t)chunk * (uint32_t)p.numTiles;
         const int tx = (int)(tile % (uint32_t)p.tilesX), ty = (int)(tile / (uint32_t)p.tilesX);
-        const int x = tx * 8 + (lane & 7), rb = ty * 4 + (lane >> 3), r = p.bandRow0 + rb;
-        if (x < p.width && r < p.ownedRows) {
-            const int y = owned_row_to_global(r, p.stripeRows, p.rank, p.world);
-            const ex::V3 sum = integ::render_chunk<STATS>(stack, p.sc, p.cam, x, y, p.chunk0 + chunk, p.width, p.height, p.spp, p.chunkLen, p.lightDir, rays, &ts);
+        const int xl = tx * 8 + (lane & 7), rb = ty * 4 + (lane >> 3), r = p.bandRow0 + rb;
+        int x, y;
+        if (xl < p.localWidth && r < p.ownedRows && local_to_global(xl, r, p.stripeRows, p.rank, p.world, p.width, x, y)) {
+            const ex::V3 sum = integ::render_chunk<STATS, FAR>(stack, p.sc, p.cam, x, y, p.chunk0 + chunk, p.width, p.height, p.spp, p.chunkLen, p.lightDir, rays, &ts);
             if (p.useAccum) {
-                __stcs(&p.accum[((size_t)chunk * p.bandRows + rb) * p.width + x], make_float4(sum.x, sum.y, sum.z, 0.0f));  // streaming: read once, by k_resolve
+                __stcs(&p.accum[((size_t)chunk * p.bandRows + rb) * p.localWidth + xl], make_float4(sum.x, sum.y, sum.z, 0.0f));  // streaming: read once, by k_resolve
             } else {
                 const uchar4 px = integ::resolve_pixel(sum, ex::divf(1.0f, (float)p.spp));
                 if (p.frame) p.frame[(size_t)y * p.width + x] = px;
-                else p.outStripes[(size_t)r * p.width + x] = px;
+                else p.outStripes[(size_t)r * p.localWidth + xl] = px;
             }
         }
     }
@@ -819,7 +854,7 @@ __global__ void __launch_bounds__(THREADS, MINB) k_render_regen(const RenderPara
     int state = ST_NEED_ITEM;
     bool exhausted = false;
     uint32_t rng = 0;
-    int depth = 0, s = 0, sEnd = 0, x = 0, y = 0, rb = 0, chunk = 0;
+    int depth = 0, s = 0, sEnd = 0, x = 0, y = 0, xl = 0, rb = 0, chunk = 0;
     ex::V3 sum = ex::v3(0.0f, 0.0f, 0.0f), nd = ex::v3(0.0f, 0.0f, 0.0f);
     float sunk = 0.0f;
     const float invW = ex::divf(1.0f, (float)p.width), invH = ex::divf(1.0f, (float)p.height);
@@ -855,11 +890,11 @@ __global__ void __launch_bounds__(THREADS, MINB) k_render_regen(const RenderPara
                     sum = ex::add(sum, color);
                     if (++s == sEnd) {
                         if (p.useAccum) {
-                            __stcs(&p.accum[((size_t)chunk * p.bandRows + rb) * p.width + x], make_float4(sum.x, sum.y, sum.z, 0.0f));  // streaming: read once, by k_resolve
+                            __stcs(&p.accum[((size_t)chunk * p.bandRows + rb) * p.localWidth + xl], make_float4(sum.x, sum.y, sum.z, 0.0f));  // streaming: read once, by k_resolve
                         } else {
                             const uchar4 px = integ::resolve_pixel(sum, ex::divf(1.0f, (float)p.spp));
                             if (p.frame) p.frame[(size_t)y * p.width + x] = px;
-                            else p.outStripes[(size_t)(p.bandRow0 + rb) * p.width + x] = px;
+                            else p.outStripes[(size_t)(p.bandRow0 + rb) * p.localWidth + xl] = px;
                         }
                         state = ST_NEED_ITEM;
                     }
@@ -883,10 +918,9 @@ __global__ void __launch_bounds__(THREADS, MINB) k_render_regen(const RenderPara
                                 chunk = (int)(wi / (uint32_t)p.numTiles);
                                 const uint32_t tile = wi - (uint32_t)chunk * (uint32_t)p.numTiles;
                                 const int tx = (int)(tile % (uint32_t)p.tilesX), ty = (int)(tile / (uint32_t)p.tilesX);
-                                x = tx * 8 + (int)(li & 7u); rb = ty * 4 + (int)(li >> 3);
+                                xl = tx * 8 + (int)(li & 7u); rb = ty * 4 + (int)(li >> 3);
                                 const int r = p.bandRow0 + rb;
-                                if (x < p.width && r < p.ownedRows) {  // (an item outside the frame is simply dropped: the lane asks again)
-                                    y = owned_row_to_global(r, p.stripeRows, p.rank, p.world);
+                                if (xl < p.localWidth && r < p.ownedRows && local_to_global(xl, r, p.stripeRows, p.rank, p.world, p.width, x, y)) {  // (an item outside the frame is simply dropped: the lane asks again)
                                     const int gchunk = p.chunk0 + chunk;  // progressive passes continue the chunk numbering; `chunk` stays the accum plane
                                     rng = ex::chunk_seed((uint32_t)gchunk, (uint32_t)y * (uint32_t)p.width + (uint32_t)x, (uint32_t)p.width * (uint32_t)p.height);
                                     const int len = p.chunkLen;
@@ -927,10 +961,12 @@ __global__ void __launch_bounds__(THREADS, MINB) k_render_regen(const RenderPara
 // pixel = in-order sum of its chunk sums, then mean / sqrt / quantise (main.cpp:221-233)
 __global__ void k_resolve(const RenderParams p, int bandRows) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= (long long)bandRows * p.width) return;
-    const int rb = (int)(i / p.width), x = (int)(i - (long long)rb * p.width), r = p.bandRow0 + rb;
-    const size_t pix = (size_t)owned_row_to_global(r, p.stripeRows, p.rank, p.world) * p.width + x;
-    const size_t plane = (size_t)bandRows * p.width;  // chunk-major planes: a warp's stores and these loads cover whole lines
+    if (i >= (long long)bandRows * p.localWidth) return;
+    const int rb = (int)(i / p.localWidth), xl = (int)(i - (long long)rb * p.localWidth), r = p.bandRow0 + rb;
+    int x, y;
+    if (!local_to_global(xl, r, p.stripeRows, p.rank, p.world, p.width, x, y)) return;
+    const size_t pix = (size_t)y * p.width + x;
+    const size_t plane = (size_t)bandRows * p.localWidth;  // chunk-major planes: a warp's stores and these loads cover whole lines
     const float4* a = p.accum + i;
     ex::V3 sum = ex::v3(0.0f, 0.0f, 0.0f);
     if (p.sumBuf) { const float4 v = p.sumBuf[pix]; sum = ex::v3(v.x, v.y, v.z); }  // progressive: the chunks before this pass
@@ -938,7 +974,7 @@ __global__ void k_resolve(const RenderParams p, int bandRows) {
     if (p.sumBuf) p.sumBuf[pix] = make_float4(sum.x, sum.y, sum.z, 0.0f);
     const uchar4 px = integ::resolve_pixel(sum, ex::divf(1.0f, (float)p.spp));
     if (p.frame) p.frame[pix] = px;
-    else p.outStripes[(size_t)r * p.width + x] = px;
+    else p.outStripes[(size_t)r * p.localWidth + xl] = px;
 }
 
 // K5: rank 0 scatters the gathered, rank-major packed stripes into the frame
@@ -947,6 +983,11 @@ __global__ void k_unpack_stripes(const uchar4* __restrict__ gathered, int width,
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= (long long)width * height) return;
     const int y = (int)(i / width), x = (int)(i - (long long)y * width);
+    if (stripeRows == 0) {  // tile interleave (local_to_global): tile (tx, ty) is local tile tx / world of rank (tx + ty) % world
+        const int tx = x >> 3, ty = y >> 2, rank = (tx + ty) % world, localWidth = ((width + 7) / 8 + world - 1) / world * 8;
+        frame[i] = gathered[((size_t)rank * maxRowsPerRank + y) * localWidth + ((tx / world) << 3) + (x & 7)];
+        return;
+    }
     const int gs = y / stripeRows, rank = gs % world, ls = gs / world;
     const int r = ls * stripeRows + (y - gs * stripeRows);
     frame[i] = gathered[((size_t)rank * maxRowsPerRank + r) * width + x];
@@ -956,12 +997,20 @@ __global__ void k_unpack_stripes(const uchar4* __restrict__ gathered, int width,
 // host side of the build
 // ------------------------------------------------------------------------------------------
 namespace {
+// rays that start beyond 16 x the scene's largest |coordinate| are answered by the all-triangle scan (bvh.cuh: ray_is_far)
+float bvh_far_limit(const tmpt_scene_info& info) {
+    float m = 0.0f;
+    for (int k = 0; k < 3; ++k) m = std::max(m, std::max(std::fabs(info.bounds_min[k]), std::fabs(info.bounds_max[k])));
+    return 16.0f * m;
+}
 template <class T>
 struct DevBuf {
     T* p = nullptr;
     ~DevBuf() { if (p) cudaFree(p); }
     cudaError_t alloc(size_t n) { return cudaMalloc((void**)&p, (n ? n : 1) * sizeof(T)); }
 };
+
+constexpr int kTreeTooDeep = -100;  // internal: tmpt_scene_create falls back to the depth-bounded default builder
 
 int build_bvh(tmpt_scene* s, unsigned flags) {
     const int n = s->triCount;
@@ -1039,7 +1088,7 @@ int build_bvh(tmpt_scene* s, unsigned flags) {
         uint32_t* const d_primFinal = (uint32_t*)primFinal.p; uint32_t* const d_nodeCounter = (uint32_t*)nodeCounter.p;
         SahTask* const d_tqA = (SahTask*)tqA.p; SahTask* const d_tqB = (SahTask*)tqB.p;
         LAUNCH(k_prim_boxes, G, B, 0, st, s->d_tris9, n, d_bounds, d_pLo, d_pHi, d_primA);
-        const SahTask rootTask{0, 0, n};
+        const SahTask rootTask{0, 0, n, 0};
         const uint32_t one = 1, zero = 0;
         CU_TRY(cudaMemcpyAsync(d_tqA, &rootTask, sizeof rootTask, cudaMemcpyHostToDevice, st));
         CU_TRY(cudaMemcpyAsync(d_nodeCounter, &one, 4, cudaMemcpyHostToDevice, st));
@@ -1164,10 +1213,13 @@ int build_bvh(tmpt_scene* s, unsigned flags) {
     CU_TRY(cudaMalloc((void**)&s->d_qnodes, ((size_t)hc[0] * bvh::QNODE_STRIDE) * sizeof(uint4)));
     LAUNCH(k_quantize_nodes, div_up((int)hc[0], 128), 128, 0, st, s->d_nodes, s->d_qnodes, hc[0]);
 #endif
-    // the traversal stack holds at most 3 entries per level (bvh::wide_node_step): refuse what it could not hold
-    if (3 * s->info.max_depth + 4 > bvh::STACK_SIZE)
-        return tmpt::fail(TMPT_ERR_ARG, "BVH is %d levels deep; the traversal stack (%d entries) supports %d", s->info.max_depth, bvh::STACK_SIZE,
-                          (bvh::STACK_SIZE - 4) / 3);
+    // the traversal stack holds at most 3 entries per level (bvh::wide_node_step): refuse what it could not hold.  The default
+    // builder cannot get here (bld::sah_must_halve bounds its depth for any input); a Morton tree over many coincident centres can.
+    if (3 * s->info.max_depth + 4 > bvh::STACK_SIZE) {
+        tmpt::fail(TMPT_ERR_ARG, "BVH is %d levels deep; the traversal stack (%d entries) supports %d", s->info.max_depth, bvh::STACK_SIZE,
+                   (bvh::STACK_SIZE - 4) / 3);
+        return kTreeTooDeep;
+    }
     s->info.device_bytes = (uint64_t)n * 9 * 4 + (uint64_t)hc[0] * (bvh::NODE_F4 + (TMPT_QNODES ? bvh::QNODE_STRIDE : 0)) * 16 + (uint64_t)n * 48 + (uint64_t)n * 48;
     s->view.nodes = s->d_nodes;
     s->view.qnodes = s->d_qnodes;
@@ -1177,6 +1229,7 @@ int build_bvh(tmpt_scene* s, unsigned flags) {
     s->view.rootRef = 0u;
     s->view.triCount = n;
     s->view.status = s->d_status;
+    s->view.farLimit = bvh_far_limit(s->info);
     return TMPT_OK;
 }
 
@@ -1229,10 +1282,17 @@ extern "C" int tmpt_scene_create(const float* tris9, int triCount, int device, u
         if (triCount > 0) {
             CU_TRY(cudaMalloc((void**)&s->d_tris9, (size_t)triCount * 9 * sizeof(float)));
             CU_TRY(cudaMemcpyAsync(s->d_tris9, tris9, (size_t)triCount * 9 * sizeof(float), cudaMemcpyHostToDevice, s->stream));
-            const int brc = build_bvh(s, flags);
-            if (brc != TMPT_OK) return brc;
+            int brc = build_bvh(s, flags);
+            if (brc == kTreeTooDeep && (flags & TMPT_BUILD_LBVH)) {
+                // a Morton tree can be arbitrarily deep (many coincident centres); the SAH builder bounds its depth for any input
+                CU_TRY(cudaStreamSynchronize(s->stream));
+                cudaFree(s->d_nodes); s->d_nodes = nullptr;
+                cudaFree(s->d_qnodes); s->d_qnodes = nullptr;
+                brc = build_bvh(s, flags & ~(unsigned)TMPT_BUILD_LBVH);
+            }
+            if (brc != TMPT_OK) return brc == kTreeTooDeep ? TMPT_ERR_ARG : brc;
         } else {
-            s->view = bvh::SceneView{nullptr, nullptr, nullptr, nullptr, bvh::NONE, 0, s->d_status};
+            s->view = bvh::SceneView{nullptr, nullptr, nullptr, nullptr, bvh::NONE, 0, s->d_status, nullptr, 0.0f};
         }
         CU_TRY(cudaEventRecord(s->ev1, s->stream));
         CU_TRY(cudaStreamSynchronize(s->stream));
@@ -1279,6 +1339,7 @@ extern "C" int tmpt_scene_refit(tmpt_scene* s, const float* tris9, int triCount,
         s->info.bounds_min[k] = bld::ordered_to_float(hb[k]);
         s->info.bounds_max[k] = bld::ordered_to_float(hb[3 + k]);
     }
+    s->view.farLimit = bvh_far_limit(s->info);
     float ms = 0.0f;
     CU_TRY(cudaEventElapsedTime(&ms, s->ev0, s->ev1));
     if (seconds) *seconds = ms * 1e-3;
@@ -1291,6 +1352,8 @@ extern "C" void tmpt_scene_destroy(tmpt_scene* s) {
     if (s->stream) cudaStreamSynchronize(s->stream);
     cudaFree(s->d_tris9); cudaFree(s->d_nodes); cudaFree(s->d_qnodes); cudaFree(s->d_status);  // (d_tris, d_hitdata live inside d_nodes)
     cudaFree(s->d_tileCounter); cudaFree(s->d_rayCount); cudaFree(s->d_fetchCounter); cudaFree(s->d_frame); cudaFree(s->d_accum); cudaFree(s->d_sum);
+    cudaFree(s->d_stage);
+    if (s->h_stage) cudaFreeHost(s->h_stage);
     if (s->ev0) cudaEventDestroy(s->ev0);
     if (s->ev1) cudaEventDestroy(s->ev1);
     if (s->stream) cudaStreamDestroy(s->stream);
@@ -1325,16 +1388,34 @@ extern "C" int tmpt_hit_scene(const tmpt_scene* s, const float* rays6, int64_t n
     cudaStream_t st = stream ? (cudaStream_t)stream : s->stream;
 
     const float* dRays = rays6; int* dID = outID; float* dT = outT; float* dPos = outPos3; float* dNrm = outNormal3;
-    DevBuf<float> bRays, bT, bPos, bNrm;
-    DevBuf<int> bID;
+    // TMPT_HOST: [rays 6n | id n | t n | pos 3n | normal 3n] floats / ints in the scene's staging buffers.  The outputs start
+    // from the caller's contents, because entries of rays that miss must stay untouched (scene.cpp:86-97 writes outHit only on a hit).
+    std::unique_lock<std::mutex> lock(const_cast<tmpt_scene*>(s)->hostCallMutex, std::defer_lock);
+    const size_t n = (size_t)nRays;
+    const size_t offID = 6 * n * 4, offT = offID + n * 4, offPos = offT + (outT ? n * 4 : 0), offNrm = offPos + (outPos3 ? 3 * n * 4 : 0),
+                 total = offNrm + (outNormal3 ? 3 * n * 4 : 0);
     if (mem == TMPT_HOST) {
-        CU_TRY(bRays.alloc((size_t)nRays * 6)); CU_TRY(bID.alloc((size_t)nRays));
-        CU_TRY(cudaMemcpyAsync(bRays.p, rays6, (size_t)nRays * 6 * sizeof(float), cudaMemcpyHostToDevice, st));
-        dRays = bRays.p; dID = bID.p;
-        // outputs for misses must stay untouched: start from the caller's contents
-        if (outT) { CU_TRY(bT.alloc((size_t)nRays)); CU_TRY(cudaMemcpyAsync(bT.p, outT, (size_t)nRays * 4, cudaMemcpyHostToDevice, st)); dT = bT.p; }
-        if (outPos3) { CU_TRY(bPos.alloc((size_t)nRays * 3)); CU_TRY(cudaMemcpyAsync(bPos.p, outPos3, (size_t)nRays * 12, cudaMemcpyHostToDevice, st)); dPos = bPos.p; }
-        if (outNormal3) { CU_TRY(bNrm.alloc((size_t)nRays * 3)); CU_TRY(cudaMemcpyAsync(bNrm.p, outNormal3, (size_t)nRays * 12, cudaMemcpyHostToDevice, st)); dNrm = bNrm.p; }
+        lock.lock();
+        tmpt_scene* ms = const_cast<tmpt_scene*>(s);  // scratch only
+        if (ms->stageBytes < total) {
+            CU_TRY(cudaStreamSynchronize(ms->stream));
+            cudaFree(ms->d_stage); ms->d_stage = nullptr;
+            if (ms->h_stage) { cudaFreeHost(ms->h_stage); ms->h_stage = nullptr; }
+            ms->stageBytes = 0;
+            const size_t cap = total + total / 4;
+            CU_TRY(cudaMalloc((void**)&ms->d_stage, cap));
+            CU_TRY(cudaHostAlloc((void**)&ms->h_stage, cap, cudaHostAllocDefault));
+            ms->stageBytes = cap;
+        }
+        char* h = ms->h_stage; char* d = ms->d_stage;
+        memcpy(h, rays6, 6 * n * 4);
+        if (outT) memcpy(h + offT, outT, n * 4);
+        if (outPos3) memcpy(h + offPos, outPos3, 3 * n * 4);
+        if (outNormal3) memcpy(h + offNrm, outNormal3, 3 * n * 4);
+        CU_TRY(cudaMemcpyAsync(d, h, 6 * n * 4, cudaMemcpyHostToDevice, st));                                     // rays
+        if (total > offT) CU_TRY(cudaMemcpyAsync(d + offT, h + offT, total - offT, cudaMemcpyHostToDevice, st));  // outputs' initial contents
+        dRays = (const float*)d; dID = (int*)(d + offID);
+        dT = outT ? (float*)(d + offT) : nullptr; dPos = outPos3 ? (float*)(d + offPos) : nullptr; dNrm = outNormal3 ? (float*)(d + offNrm) : nullptr;
     }
     const int B = 128;
     const int G = (int)std::min<long long>(div_up(nRays, B), (long long)s->smCount * 64);
@@ -1375,11 +1456,13 @@ extern "C" int tmpt_hit_scene(const tmpt_scene* s, const float* rays6, int64_t n
     else LAUNCH((k_hit_scene<TMPT_HIT_BRUTE, false>), G, B, 0, st, s->view, dRays, (long long)nRays, tMin, tMax, dID, dT, dPos, dNrm, nullptr);
     CU_TRY(cudaGetLastError());
     if (mem == TMPT_HOST) {
-        CU_TRY(cudaMemcpyAsync(outID, dID, (size_t)nRays * 4, cudaMemcpyDeviceToHost, st));
-        if (outT) CU_TRY(cudaMemcpyAsync(outT, dT, (size_t)nRays * 4, cudaMemcpyDeviceToHost, st));
-        if (outPos3) CU_TRY(cudaMemcpyAsync(outPos3, dPos, (size_t)nRays * 12, cudaMemcpyDeviceToHost, st));
-        if (outNormal3) CU_TRY(cudaMemcpyAsync(outNormal3, dNrm, (size_t)nRays * 12, cudaMemcpyDeviceToHost, st));
+        const char* d = s->d_stage; char* h = s->h_stage;
+        CU_TRY(cudaMemcpyAsync(h + offID, d + offID, total - offID, cudaMemcpyDeviceToHost, st));  // id | t | pos | normal in one copy
         CU_TRY(cudaStreamSynchronize(st));
+        memcpy(outID, h + offID, n * 4);
+        if (outT) memcpy(outT, h + offT, n * 4);
+        if (outPos3) memcpy(outPos3, h + offPos, 3 * n * 4);
+        if (outNormal3) memcpy(outNormal3, h + offNrm, 3 * n * 4);
         return check_status(s, st);
     }
     return TMPT_OK;
@@ -1388,8 +1471,13 @@ extern "C" int tmpt_hit_scene(const tmpt_scene* s, const float* rays6, int64_t n
 // ------------------------------------------------------------------------------------------
 // C ABI: render
 // ------------------------------------------------------------------------------------------
+extern "C" int tmpt_local_width(int width, int stripeRows, int worldSize) {
+    if (width <= 0 || stripeRows < 0 || worldSize <= 0) return 0;
+    return stripeRows > 0 ? width : ((width + 7) / 8 + worldSize - 1) / worldSize * 8;
+}
 extern "C" int tmpt_stripe_rows(int height, int stripeRows, int rank, int worldSize) {
-    if (height <= 0 || stripeRows <= 0 || worldSize <= 0 || rank < 0 || rank >= worldSize) return 0;
+    if (height <= 0 || stripeRows < 0 || worldSize <= 0 || rank < 0 || rank >= worldSize) return 0;
+    if (stripeRows == 0) return height;  // tile interleave: every rank owns tiles in every row
     const int stripes = (height + stripeRows - 1) / stripeRows;
     int rows = 0;
     for (int k = rank; k < stripes; k += worldSize) rows += std::min(stripeRows, height - k * stripeRows);
@@ -1447,7 +1535,8 @@ static int launch_render(const tmpt_scene* cs, const tmpt_camera* camera, int wi
     p.spp = prog ? integ::kMaxChunkSamples * (prog->chunk0 + prog->nChunks) : spp;  // (progressive: the samples so far, for the mean)
     p.stripeRows = stripeRows; p.rank = rank; p.world = world;
     p.ownedRows = tmpt_stripe_rows(height, stripeRows, rank, world);
-    p.tilesX = div_up(width, 8);
+    p.localWidth = tmpt_local_width(width, stripeRows, world);
+    p.tilesX = div_up(p.localWidth, 8);
     p.chunks = prog ? prog->nChunks : host_chunk_count(spp);
     p.chunk0 = prog ? prog->chunk0 : 0;
     p.chunkLen = prog ? integ::kMaxChunkSamples : host_chunk_len(spp);
@@ -1462,7 +1551,7 @@ static int launch_render(const tmpt_scene* cs, const tmpt_camera* camera, int wi
     p.accum = nullptr;
     if (p.ownedRows == 0) return TMPT_OK;
     int bandRows = 0;
-    const int prc = prepare_render_chunks(s, width, p.chunks, prog != nullptr, p.ownedRows, st, &bandRows);
+    const int prc = prepare_render_chunks(s, p.localWidth, p.chunks, prog != nullptr, p.ownedRows, st, &bandRows);
     if (prc != TMPT_OK) return prc;
     p.accum = s->d_accum;
     // 32 warps per SM at 64 registers (sweep in profiles/r1_tuning_sweeps.txt: 24 warps at 77 registers is 10 % slower, 40
@@ -1485,6 +1574,12 @@ static int launch_render(const tmpt_scene* cs, const tmpt_camera* camera, int wi
         CU_TRY(cudaFuncSetAttribute(k_render<false, 512, 2, kSStack>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smemPerThread * 512)));
     if (smemPerThread * 1024 > 48 * 1024)
         CU_TRY(cudaFuncSetAttribute(k_render<false, 1024, 1, kSStack>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smemPerThread * 1024)));
+    // (lens offsets are at most lensRadius from the origin: add it to the test)
+    const bool farCamera = s->view.farLimit > 0.0f &&
+        std::max(std::max(std::fabs(camera->origin[0]), std::fabs(camera->origin[1])), std::fabs(camera->origin[2])) + std::fabs(camera->lensRadius) >
+            0.5f * s->view.farLimit;
+    if (farCamera && smemPerThread * 256 > 48 * 1024)
+        CU_TRY(cudaFuncSetAttribute(k_render<false, 256, 4, kSStack, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smemPerThread * 256)));
     int perSM256 = 0, perSM512 = 0, perSM1024 = 0;
     CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM256, k_render<false, 256, 4, kSStack>, 256, smemPerThread * 256));
     CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM512, k_render<false, 512, 2, kSStack>, 512, smemPerThread * 512));
@@ -1496,7 +1591,7 @@ static int launch_render(const tmpt_scene* cs, const tmpt_camera* camera, int wi
         const long long items = (long long)p.numTiles * p.chunks;
         if (items >= 0xFFFFFFFFll) return tmpt::fail(TMPT_ERR_ARG, "render: too many work items in one band");
         CU_TRY(cudaMemsetAsync(s->d_tileCounter, 0, sizeof(uint32_t), st));
-        const int cfg = (statsDev || rk > 0) ? 1 : cfgEnv > 0 ? cfgEnv : (items >= (long long)s->smCount * 32 * 8 && perSM1024 > 0) ? 3 : 1;
+        const int cfg = (statsDev || rk > 0 || farCamera) ? 1 : cfgEnv > 0 ? cfgEnv : (items >= (long long)s->smCount * 32 * 8 && perSM1024 > 0) ? 3 : 1;
         const int threads = cfg == 3 ? 1024 : cfg == 2 ? 512 : 256;
         const int perSM = cfg == 3 ? perSM1024 : cfg == 2 ? perSM512 : perSM256;
         const int grid = (int)std::min<long long>((long long)s->smCount * std::max(perSM, 1), (items + threads / 32 - 1) / (threads / 32));
@@ -1515,11 +1610,12 @@ static int launch_render(const tmpt_scene* cs, const tmpt_camera* camera, int wi
             return tmpt::fail(TMPT_ERR_ARG, "TMPT_RENDER_KERNEL=%d: no such render kernel", rk);
         } else
 #endif
-        if (statsDev) LAUNCH((k_render<true, 256, 4, kSStack>), grid, 256, smemPerThread * 256, st, p);
+        if (farCamera && !statsDev) LAUNCH((k_render<false, 256, 4, kSStack, true>), grid, 256, smemPerThread * 256, st, p);
+        else if (statsDev) LAUNCH((k_render<true, 256, 4, kSStack>), grid, 256, smemPerThread * 256, st, p);
         else if (cfg == 3) LAUNCH((k_render<false, 1024, 1, kSStack>), grid, 1024, smemPerThread * 1024, st, p);
         else if (cfg == 2) LAUNCH((k_render<false, 512, 2, kSStack>), grid, 512, smemPerThread * 512, st, p);
         else LAUNCH((k_render<false, 256, 4, kSStack>), grid, 256, smemPerThread * 256, st, p);
-        if (p.useAccum) LAUNCH(k_resolve, div_up((long long)rowsHere * width, 256), 256, 0, st, p, rowsHere);
+        if (p.useAccum) LAUNCH(k_resolve, div_up((long long)rowsHere * p.localWidth, 256), 256, 0, st, p, rowsHere);
     }
     CU_TRY(cudaGetLastError());
     return TMPT_OK;
@@ -1537,7 +1633,7 @@ extern "C" int tmpt_render_stripes(const tmpt_scene* s, const tmpt_camera* camer
                                    int worldSize, uint8_t* outStripes, uint8_t* peerFrame, uint64_t* rayCountDev, void* stream) {
     int rc = check_render_args(s, camera, width, height, spp);
     if (rc != TMPT_OK) return rc;
-    if (stripeRows < 1 || worldSize < 1 || rank < 0 || rank >= worldSize || (!outStripes && !peerFrame) || !rayCountDev)
+    if (stripeRows < 0 || worldSize < 1 || rank < 0 || rank >= worldSize || (!outStripes && !peerFrame) || !rayCountDev)
         return tmpt::fail(TMPT_ERR_ARG, "tmpt_render_stripes: bad stripe arguments");
     DeviceGuard guard(s->device);
     if (!guard.ok) return tmpt::fail(TMPT_ERR_CUDA, "tmpt_render_stripes: cudaSetDevice(%d) failed", s->device);
@@ -1552,6 +1648,7 @@ extern "C" int tmpt_render(const tmpt_scene* cs, const tmpt_camera* camera, int 
     if (!rgba) return tmpt::fail(TMPT_ERR_ARG, "tmpt_render: rgba is NULL");
     if (mem != TMPT_HOST && mem != TMPT_DEVICE) return tmpt::fail(TMPT_ERR_ARG, "tmpt_render: mem %d", mem);
     tmpt_scene* s = const_cast<tmpt_scene*>(cs);  // scratch buffers only; the scene data is immutable
+    std::lock_guard<std::mutex> lock(s->hostCallMutex);  // concurrent callers take turns (the reference's HitScene is lock-free const; a frame here owns the scene's scratch)
     DeviceGuard guard(s->device);
     if (!guard.ok) return tmpt::fail(TMPT_ERR_CUDA, "tmpt_render: cudaSetDevice(%d) failed", s->device);
     cudaStream_t st = stream ? (cudaStream_t)stream : s->stream;
@@ -1607,6 +1704,7 @@ extern "C" int tmpt_progressive_pass(tmpt_scene* s, const tmpt_camera* camera, i
     if (!s || !camera || !rgba) return tmpt::fail(TMPT_ERR_ARG, "tmpt_progressive_pass: NULL scene / camera / rgba");
     if (s->progChunks < 0) return tmpt::fail(TMPT_ERR_ARG, "tmpt_progressive_pass: call tmpt_progressive_begin first");
     if (mem != TMPT_HOST && mem != TMPT_DEVICE) return tmpt::fail(TMPT_ERR_ARG, "tmpt_progressive_pass: mem %d", mem);
+    std::lock_guard<std::mutex> lock(s->hostCallMutex);
     if (nChunks < 1 || nChunks > 128 || (long long)(s->progChunks + nChunks) * integ::kMaxChunkSamples > (1 << 24))
         return tmpt::fail(TMPT_ERR_ARG, "tmpt_progressive_pass: %d chunks after %d", nChunks, s->progChunks);
     DeviceGuard guard(s->device);
@@ -1682,7 +1780,7 @@ extern "C" int tmpt_render_multi(tmpt_scene* const* scenes, int nScenes, const t
         }
         counters[i] = scenes[i]->d_rayCount;
         CU_TRY(cudaMemsetAsync(counters[i], 0, sizeof(unsigned long long), scenes[i]->stream));
-        const int prc = prepare_render(scenes[i], width, spp, tmpt_stripe_rows(height, 4, i, nScenes), scenes[i]->stream, nullptr);
+        const int prc = prepare_render(scenes[i], tmpt_local_width(width, 0, nScenes), spp, height, scenes[i]->stream, nullptr);  // tile interleave
         if (prc != TMPT_OK) return prc;
         CU_TRY(cudaStreamSynchronize(scenes[i]->stream));
     }
@@ -1692,7 +1790,7 @@ extern "C" int tmpt_render_multi(tmpt_scene* const* scenes, int nScenes, const t
     const auto t0 = std::chrono::steady_clock::now();
     for (int i = 0; i < nScenes; ++i) {
         CU_TRY(cudaSetDevice(scenes[i]->device));
-        const int rc = launch_render(scenes[i], camera, width, height, spp, 4, i, nScenes, nullptr, s0->d_frame, counters[i], scenes[i]->stream);
+        const int rc = launch_render(scenes[i], camera, width, height, spp, 0, i, nScenes, nullptr, s0->d_frame, counters[i], scenes[i]->stream);
         if (rc != TMPT_OK) return rc;
     }
     unsigned long long total = 0;
@@ -1760,6 +1858,7 @@ extern "C" int tmpt_render_stats(const tmpt_scene* cs, const tmpt_camera* camera
     if (rc != TMPT_OK) return rc;
     if (!outStats) return tmpt::fail(TMPT_ERR_ARG, "tmpt_render_stats: outStats is NULL");
     tmpt_scene* s = const_cast<tmpt_scene*>(cs);
+    std::lock_guard<std::mutex> lock(s->hostCallMutex);
     DeviceGuard guard(s->device);
     if (!guard.ok) return tmpt::fail(TMPT_ERR_CUDA, "tmpt_render_stats: cudaSetDevice(%d) failed", s->device);
     cudaStream_t st = s->stream;
@@ -1800,12 +1899,12 @@ extern "C" int tmpt_hit_scene_stats(const tmpt_scene* s, const float* rays6Dev, 
 
 extern "C" int tmpt_unpack_stripes(const uint8_t* gathered, int width, int height, int stripeRows, int worldSize, int device, uint8_t* frame,
                                    void* stream) {
-    if (!gathered || !frame || width < 1 || height < 1 || stripeRows < 1 || worldSize < 1)
+    if (!gathered || !frame || width < 1 || height < 1 || stripeRows < 0 || worldSize < 1)
         return tmpt::fail(TMPT_ERR_ARG, "tmpt_unpack_stripes: bad arguments");
     DeviceGuard guard(device);
     if (!guard.ok) return tmpt::fail(TMPT_ERR_CUDA, "tmpt_unpack_stripes: cudaSetDevice(%d) failed", device);
     int maxRows = 0;
-    for (int r = 0; r < worldSize; ++r) maxRows = std::max(maxRows, tmpt_stripe_rows(height, stripeRows, r, worldSize));
+    for (int r = 0; r < worldSize; ++r) maxRows = std::max(maxRows, tmpt_stripe_rows(height, stripeRows, r, worldSize));  // (tile interleave: height)
     const long long n = (long long)width * height;
     LAUNCH(k_unpack_stripes, div_up(n, 256), 256, 0, (cudaStream_t)stream, (const uchar4*)gathered, width, height, stripeRows, worldSize, maxRows,
            (uchar4*)frame);
