@@ -24,6 +24,8 @@ def main():
     ap.add_argument("--bounces", type=int, default=5)
     ap.add_argument("--reps", type=int, default=3)
     ap.add_argument("--flags", type=int, default=0)
+    ap.add_argument("--sort", default="none", choices=["none", "origin", "origin_dir", "dir_origin"],
+                    help="reorder every wave of rays before tracing it: Morton code of the origin (10 bits per axis), optionally with the direction octant")
     args = ap.parse_args()
     dev = torch.device("cuda", 0)
     path = scene_obj_path(args.scene)
@@ -43,7 +45,36 @@ def main():
     light = torch.tensor([-0.7, 1.0, 0.5], device=dev); light = light / light.norm()
     st = torch.cuda.Stream()
 
+    lo_t = torch.tensor(mn, device=dev, dtype=torch.float32)
+    ext_t = torch.tensor(mx - mn, device=dev, dtype=torch.float32).clamp_min(1e-20)
+
+    def part1by2(v):
+        v = v & 0x3FF
+        v = (v | (v << 16)) & 0x030000FF
+        v = (v | (v << 8)) & 0x0300F00F
+        v = (v | (v << 4)) & 0x030C30C3
+        v = (v | (v << 2)) & 0x09249249
+        return v
+
+    def reorder(rays):
+        if args.sort == "none":
+            return rays, 0.0
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        q = (((rays[:, 0:3] - lo_t) / ext_t).clamp(0, 0.999999) * 1024).to(torch.int64)
+        key = (part1by2(q[:, 0]) << 2) | (part1by2(q[:, 1]) << 1) | part1by2(q[:, 2])
+        octant = ((rays[:, 3] < 0).to(torch.int64) << 2) | ((rays[:, 4] < 0).to(torch.int64) << 1) | (rays[:, 5] < 0).to(torch.int64)
+        if args.sort == "origin_dir":
+            key = (key << 3) | octant
+        elif args.sort == "dir_origin":
+            key = (octant << 30) | key
+        out = rays[torch.argsort(key)].contiguous()
+        e1.record()
+        torch.cuda.synchronize()
+        return out, e0.elapsed_time(e1)
+
     def timed(rays, mode):
+        rays, sort_ms = reorder(rays)
         n = rays.shape[0]
         ids = torch.empty(n, dtype=torch.int32, device=dev)
         t = torch.empty(n, device=dev); pos = torch.empty((n, 3), device=dev); nrm = torch.empty((n, 3), device=dev)
@@ -57,6 +88,7 @@ def main():
                 st.synchronize()
                 best = min(best, e0.elapsed_time(e1))
         stats = sc.hit_scene_stats(rays.data_ptr(), n, mode=mode)
+        stats["sort_ms"] = sort_ms
         return ids, pos, nrm, best, stats
 
     tot_rays, tot_ms = 0, 0.0
@@ -65,7 +97,8 @@ def main():
         ids, pos, nrm, ms, stats = timed(rays, tm.HIT_CLOSEST)
         n = rays.shape[0]
         tot_rays += n; tot_ms += ms
-        print(f"bounce {b}: closest {n:8d} rays {ms:8.3f} ms {n / ms / 1e3:8.1f} Mrays/s  nodes/ray {stats['node_visits_per_ray']:.1f} tris/ray {stats['tri_tests_per_ray']:.1f} hit {stats['hit_rate']:.2f}")
+        print(f"bounce {b}: closest {n:8d} rays {ms:8.3f} ms {n / ms / 1e3:8.1f} Mrays/s  nodes/ray {stats['node_visits_per_ray']:.1f} tris/ray {stats['tri_tests_per_ray']:.1f} hit {stats['hit_rate']:.2f}"
+              f"  lanes/iter {stats['lanes_with_a_ray']:.1f} lanes/node {stats['lanes_per_node_step']:.1f} lanes/tri {stats['lanes_per_tri_test']:.1f}  (torch sort {stats['sort_ms']:.2f} ms)")
         hit = ids >= 0
         pos, nrm = pos[hit], nrm[hit]
         if pos.shape[0] == 0:
@@ -73,7 +106,8 @@ def main():
         srays = torch.cat([pos, light.expand_as(pos)], 1).contiguous()
         _, _, _, ms, stats = timed(srays, tm.HIT_ANY)
         tot_rays += srays.shape[0]; tot_ms += ms
-        print(f"          shadow  {srays.shape[0]:8d} rays {ms:8.3f} ms {srays.shape[0] / ms / 1e3:8.1f} Mrays/s  nodes/ray {stats['node_visits_per_ray']:.1f} tris/ray {stats['tri_tests_per_ray']:.1f} hit {stats['hit_rate']:.2f}")
+        print(f"          shadow  {srays.shape[0]:8d} rays {ms:8.3f} ms {srays.shape[0] / ms / 1e3:8.1f} Mrays/s  nodes/ray {stats['node_visits_per_ray']:.1f} tris/ray {stats['tri_tests_per_ray']:.1f} hit {stats['hit_rate']:.2f}"
+              f"  lanes/iter {stats['lanes_with_a_ray']:.1f} lanes/node {stats['lanes_per_node_step']:.1f} lanes/tri {stats['lanes_per_tri_test']:.1f}")
         r = torch.randn(pos.shape, device=dev, generator=g); r = r / r.norm(dim=1, keepdim=True)
         nd = nrm + r
         nd = nd / nd.norm(dim=1, keepdim=True).clamp_min(1e-20)

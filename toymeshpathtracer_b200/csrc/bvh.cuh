@@ -81,6 +81,12 @@ struct HitRec {
 #ifndef TMPT_TRI_FLAT
 #define TMPT_TRI_FLAT 0
 #endif
+#ifndef TMPT_POP2
+#define TMPT_POP2 0
+#endif
+#ifndef TMPT_LEAF2
+#define TMPT_LEAF2 0
+#endif
 TMPT_HD bool mt_exact(ex::V3 o, ex::V3 d, ex::V3 v0, ex::V3 e1, ex::V3 e2, float tMin, float tMax,
                       float& t, float& u, float& v) {
     const float Epsilon = 1e-5f;
@@ -310,6 +316,24 @@ TMPT_HD uint32_t enter_and_push(const float (&a)[4], const float (&b)[4], const 
     return kmin == 0xFFFFFFFFu ? NONE : nearest;
 }
 
+// Blackwell's packed FP32 pair instructions (FFMA2: two fused multiply-adds per lane in ONE issue slot; the scalar operands are
+// broadcast by the instruction itself).  The walk is bound by instruction issue, not by the FMA pipe (28 % busy), so pairing the
+// 24 slab FMAs of a node step frees 12 issue slots.  Each half is the same correctly rounded fma as the scalar form: the
+// distances, and therefore the walk, are bit-identical.
+#ifndef TMPT_FMA2
+#define TMPT_FMA2 1   // measured: +3.9 % on the headline frame (5043 -> 5240 Mrays/s, same bytes), profiles/r2_tuning_sweeps.txt
+#endif
+#if defined(__CUDA_ARCH__) && TMPT_FMA2
+__device__ __forceinline__ void fma2_bcast(float a0, float a1, float m, float c, float& r0, float& r1) {
+    unsigned long long a, mm, cc, r;
+    asm("mov.b64 %0, {%1,%2};" : "=l"(a) : "f"(a0), "f"(a1));
+    asm("mov.b64 %0, {%1,%1};" : "=l"(mm) : "f"(m));
+    asm("mov.b64 %0, {%1,%1};" : "=l"(cc) : "f"(c));
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(mm), "l"(cc));
+    asm("mov.b64 {%0,%1}, %2;" : "=f"(r0), "=f"(r1) : "l"(r));
+}
+#endif
+
 template <class Stack>
 TMPT_HD uint32_t wide_node_step(const SceneView& sc, uint32_t node, const RayCtx& r, float tMin, float bestT, Stack& stack, int& sp,
                                 bool anyRay) {
@@ -320,12 +344,28 @@ TMPT_HD uint32_t wide_node_step(const SceneView& sc, uint32_t node, const RayCtx
     const float4 rf = ld_row(sc.nodes + (row0 + 6u));
     float a[4], b[4];
     uint32_t ref[4];
+#if defined(__CUDA_ARCH__) && TMPT_FMA2
+    float tnx[4], tny[4], tnz[4], tfx[4], tfy[4], tfz[4];
+    fma2_bcast(nx.x, nx.y, r.idx, -r.ox, tnx[0], tnx[1]); fma2_bcast(nx.z, nx.w, r.idx, -r.ox, tnx[2], tnx[3]);
+    fma2_bcast(ny.x, ny.y, r.idy, -r.oy, tny[0], tny[1]); fma2_bcast(ny.z, ny.w, r.idy, -r.oy, tny[2], tny[3]);
+    fma2_bcast(nz.x, nz.y, r.idz, -r.oz, tnz[0], tnz[1]); fma2_bcast(nz.z, nz.w, r.idz, -r.oz, tnz[2], tnz[3]);
+    fma2_bcast(fx.x, fx.y, r.idx, -r.ox, tfx[0], tfx[1]); fma2_bcast(fx.z, fx.w, r.idx, -r.ox, tfx[2], tfx[3]);
+    fma2_bcast(fy.x, fy.y, r.idy, -r.oy, tfy[0], tfy[1]); fma2_bcast(fy.z, fy.w, r.idy, -r.oy, tfy[2], tfy[3]);
+    fma2_bcast(fz.x, fz.y, r.idz, -r.oz, tfz[0], tfz[1]); fma2_bcast(fz.z, fz.w, r.idz, -r.oz, tfz[2], tfz[3]);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        a[k] = fmaxf(fmaxf(tnx[k], tny[k]), fmaxf(tnz[k], tMin));
+        b[k] = fminf(fminf(tfx[k], tfy[k]), fminf(tfz[k], bestT));
+        ref[k] = ex::f2u(f4c(rf, k));
+    }
+#else
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
         a[k] = fmaxf(fmaxf(fmaf_(f4c(nx, k), r.idx, -r.ox), fmaf_(f4c(ny, k), r.idy, -r.oy)), fmaxf(fmaf_(f4c(nz, k), r.idz, -r.oz), tMin));
         b[k] = fminf(fminf(fmaf_(f4c(fx, k), r.idx, -r.ox), fmaf_(f4c(fy, k), r.idy, -r.oy)), fminf(fmaf_(f4c(fz, k), r.idz, -r.oz), bestT));
         ref[k] = ex::f2u(f4c(rf, k));
     }
+#endif
     return enter_and_push(a, b, ref, stack, sp, anyRay);
 }
 
@@ -441,6 +481,9 @@ struct WalkState {
     ex::V3 o, d;
     HitRec best;
     uint32_t cur, triPos, triEnd;
+#if TMPT_LEAF2
+    uint32_t triPos2, triEnd2;  // a second parked leaf: a lane that reaches a leaf while the first is still being tested keeps walking
+#endif
     int sp;
     bool any;
 };
@@ -450,6 +493,9 @@ TMPT_HD void walk_start(WalkState& w, const SceneView& sc, ex::V3 o, ex::V3 d, f
     w.best.id = -1; w.best.t = tMax; w.best.u = 0.0f; w.best.v = 0.0f;
     w.cur = ray_has_nan(o, d) ? NONE : sc.rootRef;
     w.triPos = 0; w.triEnd = 0;
+#if TMPT_LEAF2
+    w.triPos2 = 0; w.triEnd2 = 0;
+#endif
     w.sp = 0;
     w.any = any;
 }
@@ -496,6 +542,13 @@ TMPT_HD bool walk_step(WalkState& w, const SceneView& sc, float tMin, float tMax
         w.triEnd = w.triPos + (uint32_t)leaf_count(w.cur);
         w.cur = NONE;
     }
+#if TMPT_LEAF2
+    if (w.cur != NONE && ref_is_leaf(w.cur) && w.triPos2 == w.triEnd2) {  // the first slot is busy: park in the second
+        w.triPos2 = leaf_first(w.cur);
+        w.triEnd2 = w.triPos2 + (uint32_t)leaf_count(w.cur);
+        w.cur = NONE;
+    }
+#endif
     if (STATS) {
         if (w.cur != NONE && ref_is_leaf(w.cur)) ++stats->leafWaits;
         const bool triAny = stats_any(w.triPos < w.triEnd);
@@ -506,18 +559,38 @@ TMPT_HD bool walk_step(WalkState& w, const SceneView& sc, float tMin, float tMax
     const bool popping = w.cur == NONE && w.sp > 0;
     unsigned long long top = 0;
     if (popping) top = stack.get(w.sp - 1);
+#if TMPT_POP2
+    // ... and the entry under it: one pop in thirteen finds an entry that the shrinking best t has culled (0.98 per ray,
+    // tmpt_render_stats), and the lane then sits out a whole iteration; with both entries at hand it takes the second instead
+    const bool popping2 = popping && w.sp > 1;
+    unsigned long long second = 0;
+    if (popping2) second = stack.get(w.sp - 2);
+#endif
     if (w.triPos < w.triEnd) {
         if (STATS) ++stats->tris;
         if (tri_step(sc, w.triPos++, w.o, w.d, tMin, tMax, w.best) && w.any) return true;
+#if TMPT_LEAF2
+        if (w.triPos == w.triEnd) { w.triPos = w.triPos2; w.triEnd = w.triEnd2; w.triPos2 = 0; w.triEnd2 = 0; }
+#endif
     }
     // pop ONE entry per iteration.  If the shrinking best.t has culled it the lane sits out the next node step and pops again
     // behind the next prefetch.  (A loop here that pops until something survives ran in 75 % of the iterations for a single
     // lane, with its stack latency exposed to the whole warp: +3.3 % without it.)
+#if TMPT_POP2
+    if (popping) {
+        const bool ok1 = ex::u2f((uint32_t)(top >> 32)) <= w.best.t;
+        const bool ok2 = popping2 && ex::u2f((uint32_t)(second >> 32)) <= w.best.t;
+        w.sp -= (ok1 || !popping2) ? 1 : 2;
+        w.cur = ok1 ? (uint32_t)top : ok2 ? (uint32_t)second : NONE;
+        if (STATS && !ok1 && !ok2) ++stats->culledPops;
+    }
+#else
     if (popping) {
         --w.sp;
         if (ex::u2f((uint32_t)(top >> 32)) <= w.best.t) w.cur = (uint32_t)top;
         else if (STATS) ++stats->culledPops;
     }
+#endif
     const bool done = w.cur == NONE && w.triPos == w.triEnd && w.sp == 0;
     if (STATS && done) {
         const int lim[5] = {4, 8, 12, 16, 24};
