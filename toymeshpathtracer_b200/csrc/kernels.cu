@@ -28,14 +28,11 @@
 #include "build_logic.cuh"
 #include "common.h"
 #include "integrator.cuh"
-// Experimental traversal / render kernels measured in round 1 and not adopted are compiled only with
-// -DTMPT_EXPERIMENTS=1 (tools/exp_*.py); the shipped library does not contain them.
+// The render kernel with per-lane ray regeneration (k_render_regen: measured in rounds 1 and 2, 31 % slower) is
+// compiled only with -DTMPT_EXPERIMENTS=1; the shipped library does not contain it.  (Round 1's three experimental HitScene
+// kernels -- warp queue, deferred triangle tests, cooperative leaf phase -- were removed in round 2: git history, profiles/r1_*.)
 #ifndef TMPT_EXPERIMENTS
 #define TMPT_EXPERIMENTS 0
-#endif
-#if TMPT_EXPERIMENTS
-#include "warpq.cuh"
-#include "wtrace.cuh"
 #endif
 
 // ------------------------------------------------------------------------------------------
@@ -558,163 +555,6 @@ __global__ void __launch_bounds__(128) k_hit_scene(bvh::SceneView sc, const floa
     if (STATS) flush_stats(stats, nr, ts, nh);
 }
 
-#if TMPT_EXPERIMENTS
-// K2/K3 through the warp-synchronous deferred-triangle traversal (wtrace.cuh)
-template <bool STATS, int TRI_MIN, int WALK_MIN>
-__global__ void __launch_bounds__(128) k_hit_scene_wt(bvh::SceneView sc, const float* __restrict__ rays6, long long nRays, float tMin, float tMax,
-                                                       int anyHit, int* __restrict__ outID, float* __restrict__ outT, float* __restrict__ outPos,
-                                                       float* __restrict__ outNormal, unsigned long long* __restrict__ stats) {
-    bvh::TravStats ts;
-    unsigned long long nr = 0, nh = 0;
-    const long long stride = (long long)gridDim.x * blockDim.x;
-    const long long rounds = (nRays + stride - 1) / stride;
-    for (long long rnd = 0; rnd < rounds; ++rnd) {
-        const long long i = rnd * stride + (long long)blockIdx.x * blockDim.x + threadIdx.x;
-        const bool active = i < nRays;
-        ex::V3 o = ex::v3(0, 0, 0), d = ex::v3(0, 0, 1);
-        if (active) { const float* r = rays6 + i * 6; o = ex::v3(r[0], r[1], r[2]); d = ex::v3(r[3], r[4], r[5]); }
-        const bvh::HitRec h = wt::traverse_warp<STATS, TRI_MIN, WALK_MIN>(sc, o, d, tMin, tMax, anyHit != 0, active, &ts);
-        if (!active) continue;
-        if (STATS) { ++nr; nh += h.id >= 0; }
-        if (anyHit) { outID[i] = h.id < 0 ? -1 : 1; continue; }
-        outID[i] = h.id;
-        if (h.id >= 0) {
-            if (outT) outT[i] = h.t;
-            if (outPos || outNormal) {
-                ex::V3 pos, nrm;
-                bvh::hit_payload(sc, h.id, h.u, h.v, pos, nrm);
-                if (outPos) { outPos[i * 3] = pos.x; outPos[i * 3 + 1] = pos.y; outPos[i * 3 + 2] = pos.z; }
-                if (outNormal) { outNormal[i * 3] = nrm.x; outNormal[i * 3 + 1] = nrm.y; outNormal[i * 3 + 2] = nrm.z; }
-            }
-        }
-    }
-    if (STATS) flush_stats(stats, nr, ts, nh);
-}
-
-// K2/K3 with the cooperative leaf phase (wtrace.cuh: traverse_warp8)
-template <bool STATS>
-__global__ void __launch_bounds__(128) k_hit_scene_w8(bvh::SceneView sc, const float* __restrict__ rays6, long long nRays, float tMin, float tMax,
-                                                       int anyHit, int* __restrict__ outID, float* __restrict__ outT, float* __restrict__ outPos,
-                                                       float* __restrict__ outNormal, unsigned long long* __restrict__ stats) {
-    bvh::TravStats ts;
-    unsigned long long nr = 0, nh = 0;
-    const long long stride = (long long)gridDim.x * blockDim.x;
-    const long long rounds = (nRays + stride - 1) / stride;
-    for (long long rnd = 0; rnd < rounds; ++rnd) {
-        const long long i = rnd * stride + (long long)blockIdx.x * blockDim.x + threadIdx.x;
-        const bool active = i < nRays;
-        ex::V3 o = ex::v3(0, 0, 0), d = ex::v3(0, 0, 1);
-        if (active) { const float* r = rays6 + i * 6; o = ex::v3(r[0], r[1], r[2]); d = ex::v3(r[3], r[4], r[5]); }
-        const unsigned long long key = wt::traverse_warp8<STATS>(sc, o, d, tMin, tMax, anyHit != 0, active, &ts);
-        if (!active) continue;
-        const int id = (int)(uint32_t)key;
-        if (STATS) { ++nr; nh += id >= 0; }
-        if (anyHit) { outID[i] = id < 0 ? -1 : 1; continue; }
-        outID[i] = id;
-        if (id >= 0) {
-            if (outT) outT[i] = wt::key_t(key);
-            if (outPos || outNormal) {
-                const float* q = sc.tris9 + (size_t)id * 9;
-                const ex::V3 v0 = ex::v3(q[0], q[1], q[2]), v1 = ex::v3(q[3], q[4], q[5]), v2 = ex::v3(q[6], q[7], q[8]);
-                float t, u, v;
-                bvh::mt_exact(o, d, v0, ex::sub(v1, v0), ex::sub(v2, v0), tMin, tMax, t, u, v);
-                ex::V3 pos, nrm;
-                bvh::hit_payload(sc, id, u, v, pos, nrm);
-                if (outPos) { outPos[i * 3] = pos.x; outPos[i * 3 + 1] = pos.y; outPos[i * 3 + 2] = pos.z; }
-                if (outNormal) { outNormal[i * 3] = nrm.x; outNormal[i * 3 + 1] = nrm.y; outNormal[i * 3 + 2] = nrm.z; }
-            }
-        }
-    }
-    if (STATS) flush_stats(stats, nr, ts, nh);
-}
-
-// Warp-queue form of K2/K3 (warpq.cuh): lanes walk inner nodes, triangles are tested 32 pairs
-// at a time by the whole warp, finished lanes are refilled from the global ray counter.
-template <bool STATS, int REFILL_MIN, int NODE_MIN>
-__global__ void __launch_bounds__(128) k_hit_scene_wq(bvh::SceneView sc, const float* __restrict__ rays6, long long nRays, float tMin, float tMax,
-                                                       int anyHit, int* __restrict__ outID, float* __restrict__ outT, float* __restrict__ outPos,
-                                                       float* __restrict__ outNormal, unsigned long long* __restrict__ counter,
-                                                       unsigned long long* __restrict__ stats) {
-    __shared__ wq::WarpShared shared[4];
-    wq::WarpShared& ws = shared[threadIdx.x >> 5];
-    const unsigned FULL = wq::FULL;
-    const int lane = threadIdx.x & 31;
-    uint32_t stackRef[wq::STACK];
-    float stackT[wq::STACK];
-    wq::Lane L;
-    L.cur = bvh::NONE; L.sp = 0; L.lastTail = 0; L.any = anyHit != 0;
-    uint32_t head = 0, tail = 0;  // ring positions (warp-uniform)
-    const unsigned anyMask = anyHit ? FULL : 0u;
-    long long ray = -1;
-    bool exhausted = false;
-    bvh::TravStats ts;
-    unsigned long long nr = 0, nh = 0;
-    for (;;) {
-        // ---- A. retire finished lanes, refill idle ones
-        if (ray >= 0 && L.cur == bvh::NONE && L.sp == 0 && (int)(head - L.lastTail) >= 0) {
-            const unsigned long long key = ws.best[lane];
-            const int id = wq::key_id(key);
-            const bool hit = anyHit ? key == 0ull : id >= 0;
-            if (STATS) { ++nr; nh += hit; }
-            if (anyHit) outID[ray] = hit ? 1 : -1;
-            else {
-                outID[ray] = id;
-                if (hit) {
-                    if (outT) outT[ray] = wq::key_t(key);
-                    if (outPos || outNormal) {
-                        // u, v of the winning triangle: the exact test once more, on the original vertices (same bits)
-                        const float* q = sc.tris9 + (size_t)id * 9;
-                        const ex::V3 v0 = ex::v3(q[0], q[1], q[2]), v1 = ex::v3(q[3], q[4], q[5]), v2 = ex::v3(q[6], q[7], q[8]);
-                        float t, u, v;
-                        bvh::mt_exact(ex::v3(ws.ox[lane], ws.oy[lane], ws.oz[lane]), ex::v3(ws.dx[lane], ws.dy[lane], ws.dz[lane]), v0,
-                                      ex::sub(v1, v0), ex::sub(v2, v0), tMin, tMax, t, u, v);
-                        ex::V3 pos, nrm;
-                        bvh::hit_payload(sc, id, u, v, pos, nrm);
-                        if (outPos) { outPos[ray * 3] = pos.x; outPos[ray * 3 + 1] = pos.y; outPos[ray * 3 + 2] = pos.z; }
-                        if (outNormal) { outNormal[ray * 3] = nrm.x; outNormal[ray * 3 + 1] = nrm.y; outNormal[ray * 3 + 2] = nrm.z; }
-                    }
-                }
-            }
-            ray = -1;
-        }
-        const unsigned idle = __ballot_sync(FULL, ray < 0);
-        if (!exhausted && (__popc(idle) >= REFILL_MIN || idle == FULL)) {
-            const int cnt = __popc(idle);
-            unsigned long long base = 0;
-            if (lane == 0) base = atomicAdd(counter, (unsigned long long)cnt);
-            base = __shfl_sync(FULL, base, 0);
-            if (ray < 0) {
-                const long long i = (long long)base + __popc(idle & ((1u << lane) - 1u));
-                if (i < nRays) {
-                    const float* r = rays6 + i * 6;
-                    wq::lane_start(L, ws, lane, ex::v3(r[0], r[1], r[2]), ex::v3(r[3], r[4], r[5]), tMax, anyHit != 0, sc.rootRef, tail);
-                    ray = i;
-                }
-            }
-            exhausted = (long long)base + cnt >= nRays;
-        }
-        __syncwarp();
-        if (__all_sync(FULL, ray < 0)) break;  // nothing in flight and nothing left to fetch
-        // ---- B. one inner-node step per lane that has one
-        const float bestT = ray >= 0 ? wq::key_t(ws.best[lane]) : 0.0f;
-        if (ray >= 0) {
-            if (L.cur == bvh::NONE) L.cur = wq::pop(L, stackRef, stackT, bestT);
-            if (L.cur != bvh::NONE && !bvh::ref_is_leaf(L.cur)) wq::node_step<STATS>(L, sc, stackRef, stackT, tMin, bestT, &ts);
-        }
-        // ---- C. lanes standing at a leaf queue its triangles and move on
-        const bool atLeaf = ray >= 0 && L.cur != bvh::NONE && bvh::ref_is_leaf(L.cur);
-        if (__any_sync(FULL, atLeaf)) {
-            wq::enqueue_leaves<STATS>(ws, sc, lane, atLeaf, L.cur, head, tail, L.lastTail, tMin, tMax, anyMask, &ts);
-            if (atLeaf) L.cur = bvh::NONE;  // popped at the top of the next iteration, against a fresher best t
-        }
-        // ---- D. exact tests: full passes, or a partial one when too few lanes have node work left
-        const int walkers = __popc(__ballot_sync(FULL, ray >= 0 && (L.cur != bvh::NONE || L.sp > 0)));
-        while (tail - head >= 32u || (tail != head && walkers < NODE_MIN)) wq::tri_pass<STATS>(ws, sc, lane, head, tail, tMin, tMax, anyMask, &ts);
-    }
-    if (STATS) flush_stats(stats, nr, ts, nh);
-}
-
-#endif  // TMPT_EXPERIMENTS
 
 // ------------------------------------------------------------------------------------------
 // K4: path tracing.  Work unit = (8x4 pixel tile, one chunk of chunk_len(spp) samples) per warp, fetched from a
@@ -791,6 +631,9 @@ struct RenderStack<0, THREADS> {
 
 #ifndef TMPT_SSTACK
 #define TMPT_SSTACK 0
+#endif
+#ifndef TMPT_TUNE_CFG
+#define TMPT_TUNE_CFG 0
 #endif
 constexpr int kSStack = TMPT_SSTACK;
 
@@ -1419,38 +1262,8 @@ extern "C" int tmpt_hit_scene(const tmpt_scene* s, const float* rays6, int64_t n
     }
     const int B = 128;
     const int G = (int)std::min<long long>(div_up(nRays, B), (long long)s->smCount * 64);
-#if TMPT_EXPERIMENTS
-    // Experimental traversal engines kept for A/B runs (tools/exp_traverse.py; results in profiles/ and DESIGN.md 5):
-    // 5 = warp queue (warpq.cuh), 10/11 = warp-synchronous deferred triangle tests, 20 = cooperative leaf phase (wtrace.cuh).
-    static const int variant = getenv("TMPT_HIT_KERNEL") ? atoi(getenv("TMPT_HIT_KERNEL")) : 0;
-    if (variant > 0 && mode != TMPT_HIT_BRUTE) {
-        int perSM = 0;
-        CU_TRY(cudaMemsetAsync(s->d_fetchCounter, 0, sizeof(unsigned long long), st));
-#define WQ_CASE(V, R, N)                                                                                                        \
-        if (variant == V) {                                                                                                     \
-            CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, k_hit_scene_wq<false, R, N>, B, 0));                       \
-            const int GP = (int)std::min<long long>(div_up(nRays, B), (long long)s->smCount * std::max(perSM, 1));              \
-            LAUNCH((k_hit_scene_wq<false, R, N>), GP, B, 0, st, s->view, dRays, (long long)nRays, tMin, tMax, mode == TMPT_HIT_ANY, dID, dT, \
-                   dPos, dNrm, s->d_fetchCounter, nullptr);                                                                     \
-        } else
-        WQ_CASE(5, 8, 12)
-#undef WQ_CASE
-#define WT_CASE(V, T, W)                                                                                                        \
-        if (variant == V) {                                                                                                     \
-            LAUNCH((k_hit_scene_wt<false, T, W>), G, B, 0, st, s->view, dRays, (long long)nRays, tMin, tMax, mode == TMPT_HIT_ANY, dID, dT, dPos, \
-                   dNrm, nullptr);                                                                                              \
-        } else
-        WT_CASE(10, 16, 8) WT_CASE(11, 8, 8)
-#undef WT_CASE
-        if (variant == 20) {
-            LAUNCH((k_hit_scene_w8<false>), G, B, 0, st, s->view, dRays, (long long)nRays, tMin, tMax, mode == TMPT_HIT_ANY, dID, dT, dPos, dNrm, nullptr);
-        } else
-        return tmpt::fail(TMPT_ERR_ARG, "TMPT_HIT_KERNEL=%d: no such traversal variant", variant);
-    } else
-#else
     if (getenv("TMPT_HIT_KERNEL") && atoi(getenv("TMPT_HIT_KERNEL")) > 0)
-        return tmpt::fail(TMPT_ERR_ARG, "TMPT_HIT_KERNEL is set, but this library was built without -DTMPT_EXPERIMENTS=1");
-#endif
+        return tmpt::fail(TMPT_ERR_ARG, "TMPT_HIT_KERNEL: the experimental HitScene kernels of round 1 were removed (see profiles/r1_hit_scene_variants_ncu.txt)");
     if (mode == TMPT_HIT_CLOSEST) LAUNCH((k_hit_scene<TMPT_HIT_CLOSEST, false>), G, B, 0, st, s->view, dRays, (long long)nRays, tMin, tMax, dID, dT, dPos, dNrm, nullptr);
     else if (mode == TMPT_HIT_ANY) LAUNCH((k_hit_scene<TMPT_HIT_ANY, false>), G, B, 0, st, s->view, dRays, (long long)nRays, tMin, tMax, dID, dT, dPos, dNrm, nullptr);
     else LAUNCH((k_hit_scene<TMPT_HIT_BRUTE, false>), G, B, 0, st, s->view, dRays, (long long)nRays, tMin, tMax, dID, dT, dPos, dNrm, nullptr);
@@ -1580,6 +1393,24 @@ static int launch_render(const tmpt_scene* cs, const tmpt_camera* camera, int wi
             0.5f * s->view.farLimit;
     if (farCamera && smemPerThread * 256 > 48 * 1024)
         CU_TRY(cudaFuncSetAttribute(k_render<false, 256, 4, kSStack, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smemPerThread * 256)));
+#if TMPT_TUNE_CFG
+    if (cfgEnv >= 4 && cfgEnv <= 8) {  // tuning only (-DTMPT_TUNE_CFG=1): other resident-warp / register-budget points
+        for (p.bandRow0 = 0; p.bandRow0 < p.ownedRows; p.bandRow0 += bandRows) {
+            const int rowsHere = std::min(bandRows, p.ownedRows - p.bandRow0);
+            p.bandRows = rowsHere;
+            p.numTiles = p.tilesX * div_up(rowsHere, 4);
+            CU_TRY(cudaMemsetAsync(s->d_tileCounter, 0, sizeof(uint32_t), st));
+            if (cfgEnv == 4) LAUNCH((k_render<false, 768, 1, 0>), s->smCount, 768, 0, st, p);           // 24 warps, 85 registers
+            else if (cfgEnv == 5) LAUNCH((k_render<false, 576, 2, 0>), 2 * s->smCount, 576, 0, st, p);  // 36 warps, 56 registers
+            else if (cfgEnv == 6) LAUNCH((k_render<false, 640, 2, 0>), 2 * s->smCount, 640, 0, st, p);  // 40 warps, 48 registers
+            else if (cfgEnv == 7) LAUNCH((k_render<false, 896, 1, 0>), s->smCount, 896, 0, st, p);      // 28 warps, 72 registers
+            else LAUNCH((k_render<false, 384, 3, 0>), 3 * s->smCount, 384, 0, st, p);                    // 36 warps, 56 registers, three CTAs
+            if (p.useAccum) LAUNCH(k_resolve, div_up((long long)rowsHere * p.localWidth, 256), 256, 0, st, p, rowsHere);
+        }
+        CU_TRY(cudaGetLastError());
+        return TMPT_OK;
+    }
+#endif
     int perSM256 = 0, perSM512 = 0, perSM1024 = 0;
     CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM256, k_render<false, 256, 4, kSStack>, 256, smemPerThread * 256));
     CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM512, k_render<false, 512, 2, kSStack>, 512, smemPerThread * 512));
