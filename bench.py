@@ -438,9 +438,10 @@ def bench_b200(args, scene, w, h, spp, rank, world, local_rank):
                     img = host_frame
             stream.synchronize()
             rays = int(rr.item())
-        barrier()
+        dt = (time.perf_counter() - t0) * 1e3  # this rank's work is done: kernels, the frame's all-reduce and (rank 0) the copy to host memory
+        barrier()                               # (the frame time of the job is the MAX over ranks, taken below)
         if i > 0:
-            e2e_ms.append((time.perf_counter() - t0) * 1e3)
+            e2e_ms.append(dt)
             e2e_rays.append(rays)
     e2e_t = torch.tensor([sum(e2e_ms)], dtype=torch.float64, device=dev)
     e2e_r = torch.tensor([sum(e2e_rays)], dtype=torch.int64, device=dev)
@@ -477,22 +478,25 @@ def bench_b200(args, scene, w, h, spp, rank, world, local_rank):
         stats = sc.traversal_stats(cam, w, h, spp) if hasattr(sc, "traversal_stats") else None
         flops_per_ray = (stats["box_tests_per_ray"] * 18 + stats["tri_tests_per_ray"] * 46) if stats else None
         kernel_ms = statistics.mean(step_ms)
-        traffic = None
-        try:  # dram__bytes_read + dram__bytes_write of this kernel on this workload, from the committed ncu capture
-            tj = json.load(open(os.path.join(ROOT, "profiles", "r1h_traffic.json")))["k_render"]
+        traffic, traffic_source = None, None
+        try:  # dram__bytes_read + dram__bytes_write of this kernel on this workload: NOT measured in this run (ncu cannot run inside a
+            # timed bench), read from the committed ncu --set full capture of the same instantiation and labelled as such
+            tj = json.load(open(os.path.join(ROOT, "profiles", "r2_traffic.json")))["k_render"]
             if args.workload == "sponza_1080p_64spp" and world == 1:
                 traffic = tj["dram_bytes_read"] + tj["dram_bytes_write"]
+                traffic_source = "from file profiles/r2_traffic.json (" + tj["source"] + "), not measured in this run"
         except (OSError, KeyError, ValueError):
             pass
         achieved = (value / world) * 1e6 * flops_per_ray / 1e12 if flops_per_ray else None
         roofline = {
             "bound": "fp32_issue (L2-resident traversal; neither hbm nor tensor, SURVEY.md 8(d))",
             "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s", "frac": (achieved / fp32_peak) if achieved else None,
-            "traffic": traffic, "per_ray": stats, "flops_per_ray": flops_per_ray,
+            "traffic": traffic, "traffic_source": traffic_source, "per_ray": stats, "flops_per_ray": flops_per_ray,
             "peak_source": peak_source,
             "hbm_context": {"algorithmic_bytes_per_frame": int(tris.size * 4 + w * h * 4), "hbm_peak_gbs_measured": peaks.get("hbm_gbs"),
                             "hbm_frac": (tris.size * 4 + w * h * 4) / (kernel_ms * 1e-3) / 1e9 / peaks["hbm_gbs"] if peaks.get("hbm_gbs") else None},
             "kernel": "k_render", "kernel_ms": kernel_ms,
+            "limiter": "L1 data stage (l1tex__data_pipe_lsu_wavefronts 85 % of peak) and issue slots (69 %), profiles/r2_k_render_ncu_summary.txt",
         }
         cw, ch, cspp = CPU_SAMPLE[scene]
         try:
@@ -510,7 +514,8 @@ def bench_b200(args, scene, w, h, spp, rank, world, local_rank):
             "warmup": args.warmup, "ms_per_step": tot_ms / args.steps, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": f"{scene_label(scene)} {w}x{h} {spp}spp", "rays_per_frame": step_rays[-1] if world == 1 else tot_rays // args.steps,
-                       "parallelism": "single GPU" if world == 1 else f"row stripes of {multigpu.DEFAULT_STRIPE_ROWS} over {world} GPUs, BVH replica per GPU, " + (
+                       "parallelism": "single GPU" if world == 1 else (f"8x4-pixel tiles interleaved ((tx + ty) % {world}) over {world} GPUs" if multigpu.DEFAULT_STRIPE_ROWS == 0 else
+                                                                        f"row stripes of {multigpu.DEFAULT_STRIPE_ROWS} over {world} GPUs") + ", BVH replica per GPU, " + (
                            "pixels stored straight into rank 0's frame over NVLink (CUDA IPC peer memory)" if peer else "frame gathered to rank 0 (NCCL)"),
                        "work_unit": "8x4 pixel tile x chunk of spp/32 (1..8) samples per warp, dynamic fetch",
                        "l2": "flushed between timed iterations (256 MB write)", "bvh": {k: info[k] for k in ("node_count", "leaf_count", "max_depth", "sah_cost", "build_ms", "device_bytes")},
