@@ -60,15 +60,14 @@ REF_BIN = os.path.join(ROOT, "oracle", "_ref", "TrimeshTracer")
 # ------------------------------------------------------------------------------------------
 def scene_obj_path(scene: str) -> str:
     """An .obj file for `scene` in a scratch directory (the CLI and the reference binary take files)."""
+    if scene == "sponza" and _real_sponza():
+        return _real_sponza()  # the reference's own data/sponza.obj, when the caller has it: takes precedence over the stand-in
     d = os.path.join(tempfile.gettempdir(), "tmpt_bench_%d" % os.getuid())
     os.makedirs(d, exist_ok=True)
     path = os.path.join(d, f"{scene}.obj")
     if os.path.exists(path):
         return path
     if scene == "sponza":
-        real = os.environ.get("TMPT_SPONZA_OBJ")
-        if real and os.path.exists(real):
-            return real
         from tools.gen_sponza import write_obj
         write_obj(path)
         return path
@@ -82,9 +81,14 @@ def scene_obj_path(scene: str) -> str:
     return path
 
 
+def _real_sponza():
+    real = os.environ.get("TMPT_SPONZA_OBJ")
+    return real if real and os.path.exists(real) else None
+
+
 def scene_label(scene: str) -> str:
     if scene == "sponza":
-        return "sponza.obj (real)" if os.environ.get("TMPT_SPONZA_OBJ") else "sponza stand-in (tools/gen_sponza.py, 66452 tris)"
+        return "sponza.obj (real)" if _real_sponza() else "sponza stand-in (tools/gen_sponza.py, 66452 tris)"
     return f"{scene}.obj"
 
 
