@@ -200,7 +200,9 @@ def test_edge_cases():
 
 @pytest.mark.parametrize("name,w,h,spp", [("cube", 160, 90, 4), ("suzanne", 128, 72, 3), ("teapot", 64, 36, 2), ("triangle", 33, 17, 5),
                                           ("cube", 70, 41, 20), ("suzanne", 48, 28, 9),  # several chunks per pixel (chunk length = spp/32 clamped to 1..8)
-                                          ("cube", 640, 360, 8)])  # 57 600 warp items: launch_render picks the 1024-thread instantiation the bench times
+                                          ("cube", 640, 360, 8),   # 57 600 warp items: launch_render picks the 1024-thread instantiation the bench times
+                                          ("cube", 640, 360, 4),   # BASELINE config 1 at its full size
+                                          ("suzanne", 640, 360, 4)])  # BASELINE config 2 at its full size (the oracle scans 970 triangles per ray: ~10 s)
 def test_frame_bit_exact_vs_oracle_pixel_mode(scenes, oracle, name, w, h, spp):
     sc = load_scene(name)
     cam = tm.camera_for_scene(f"{name}.obj", sc["bounds_min"], sc["bounds_max"], w, h)
