@@ -143,11 +143,12 @@ TMPT_HD bool mt_exact(ex::V3 o, ex::V3 d, ex::V3 v0, ex::V3 e1, ex::V3 e2, float
 
 // Hit.pos / Hit.normal exactly as maths.cpp:374-375 forms them, from the ORIGINAL vertices.
 TMPT_HD ex::V3 tri_normal(ex::V3 v0, ex::V3 v1, ex::V3 v2) { return ex::normalize(ex::cross(ex::sub(v1, v0), ex::sub(v2, v0))); }
+TMPT_HD float4 ld_row_payload(const float4* p);  // (defined below, with the other row loads)
 TMPT_HD void hit_payload(const SceneView& sc, int id, float u, float v, ex::V3& pos, ex::V3& normal) {
     ex::V3 v0, v1, v2;
     if (sc.hitdata) {
         const float4* h = sc.hitdata + (size_t)id * 3;
-        const float4 a = h[0], b = h[1], c = h[2];
+        const float4 a = ld_row_payload(h), b = ld_row_payload(h + 1), c = ld_row_payload(h + 2);
         v0 = ex::v3(a.x, a.y, a.z); v1 = ex::v3(b.x, b.y, b.z); v2 = ex::v3(c.x, c.y, c.z);
         normal = ex::v3(a.w, b.w, c.w);
     } else {
@@ -242,6 +243,51 @@ TMPT_HD float4 ld_row(const float4* p) {
     float4 v;
     asm volatile("ld.global.nc.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
     return v;
+#else
+    return *p;
+#endif
+}
+// the same load with an L1 eviction-priority hint.  Node rows are re-used (the top of the tree by every ray), triangle rows and the
+// hit payload are read once per test / per hit: nodes evict_last, the other two evict_first.  TMPT_CACHE_HINTS is a bit mask:
+// 1 node rows evict_last, 2 triangle rows evict_first, 4 triangle rows no_allocate, 8 payload rows evict_first, 16 payload rows
+// no_allocate.  Measured on the headline frame (profiles/r2_tuning_sweeps.txt): 0: 5225-5238, 1: 5238, 2: 5267, 3: 5269, 5: 5256,
+// 11: 5278 (+0.9 %, the default), 19: 5267, 21: 5257 Mrays/s.
+#ifndef TMPT_CACHE_HINTS
+#define TMPT_CACHE_HINTS 11
+#endif
+#ifdef __CUDA_ARCH__
+#define TMPT_LD_HINT(name, hint)                                                                                                      \
+    __device__ __forceinline__ float4 name(const float4* p) {                                                                        \
+        float4 v;                                                                                                                     \
+        asm volatile("ld.global.nc." hint ".v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p)); \
+        return v;                                                                                                                     \
+    }
+TMPT_LD_HINT(ld_row_evict_last, "L1::evict_last")
+TMPT_LD_HINT(ld_row_evict_first, "L1::evict_first")
+TMPT_LD_HINT(ld_row_no_allocate, "L1::no_allocate")
+#undef TMPT_LD_HINT
+#endif
+TMPT_HD float4 ld_row_node(const float4* p) {
+#if defined(__CUDA_ARCH__) && (TMPT_CACHE_HINTS & 1)
+    return ld_row_evict_last(p);
+#else
+    return ld_row(p);
+#endif
+}
+TMPT_HD float4 ld_row_tri(const float4* p) {
+#if defined(__CUDA_ARCH__) && (TMPT_CACHE_HINTS & 2)
+    return ld_row_evict_first(p);
+#elif defined(__CUDA_ARCH__) && (TMPT_CACHE_HINTS & 4)
+    return ld_row_no_allocate(p);
+#else
+    return ld_row(p);
+#endif
+}
+TMPT_HD float4 ld_row_payload(const float4* p) {
+#if defined(__CUDA_ARCH__) && (TMPT_CACHE_HINTS & 8)
+    return ld_row_evict_first(p);
+#elif defined(__CUDA_ARCH__) && (TMPT_CACHE_HINTS & 16)
+    return ld_row_no_allocate(p);
 #else
     return *p;
 #endif
@@ -357,10 +403,10 @@ template <class Stack>
 TMPT_HD uint32_t wide_node_step(const SceneView& sc, uint32_t node, const RayCtx& r, float tMin, float bestT, Stack& stack, int& sp,
                                 bool anyRay) {
     const uint32_t row0 = node * (uint32_t)NODE_F4;
-    const float4 nx = ld_row(sc.nodes + (row0 + r.sx)), fx = ld_row(sc.nodes + (row0 + (r.sx ^ 1u)));
-    const float4 ny = ld_row(sc.nodes + (row0 + 2u + r.sy)), fy = ld_row(sc.nodes + (row0 + 2u + (r.sy ^ 1u)));
-    const float4 nz = ld_row(sc.nodes + (row0 + 4u + r.sz)), fz = ld_row(sc.nodes + (row0 + 4u + (r.sz ^ 1u)));
-    const float4 rf = ld_row(sc.nodes + (row0 + 6u));
+    const float4 nx = ld_row_node(sc.nodes + (row0 + r.sx)), fx = ld_row_node(sc.nodes + (row0 + (r.sx ^ 1u)));
+    const float4 ny = ld_row_node(sc.nodes + (row0 + 2u + r.sy)), fy = ld_row_node(sc.nodes + (row0 + 2u + (r.sy ^ 1u)));
+    const float4 nz = ld_row_node(sc.nodes + (row0 + 4u + r.sz)), fz = ld_row_node(sc.nodes + (row0 + 4u + (r.sz ^ 1u)));
+    const float4 rf = ld_row_node(sc.nodes + (row0 + 6u));
     float a[4], b[4];
     uint32_t ref[4];
 #if defined(__CUDA_ARCH__) && TMPT_FMA2
@@ -482,7 +528,7 @@ TMPT_HD uint32_t node_step(const SceneView& sc, uint32_t node, const RayCtx& r, 
 // One exact test of triangle slot `slot`; returns true when `best` improved.
 TMPT_HD bool tri_step(const SceneView& sc, uint32_t slot, ex::V3 o, ex::V3 d, float tMin, float tMax, HitRec& best) {
     const uint32_t row0 = slot * 3u;  // 32-bit row index: slot < 2^27
-    const float4 a = ld_row(sc.tris + row0), b = ld_row(sc.tris + (row0 + 1u)), c = ld_row(sc.tris + (row0 + 2u));
+    const float4 a = ld_row_tri(sc.tris + row0), b = ld_row_tri(sc.tris + (row0 + 1u)), c = ld_row_tri(sc.tris + (row0 + 2u));
     float t, u, v;
     if (mt_exact(o, d, ex::v3(a.x, a.y, a.z), ex::v3(b.x, b.y, b.z), ex::v3(c.x, c.y, c.z), tMin, tMax, t, u, v)) {
         const int id = (int)ex::f2u(a.w);
