@@ -502,6 +502,14 @@ def bench_b200(args, scene, w, h, spp, rank, world, local_rank):
             "kernel": "k_render", "kernel_ms": kernel_ms,
             "limiter": "L1 data stage (l1tex__data_pipe_lsu_wavefronts 85 % of peak) and issue slots (69 %), profiles/r2_k_render_ncu_summary.txt",
         }
+        if stats:
+            # the limiter in the kernel's own units: 16-byte rows gathered per clock and SM (7 per node step, 3 per triangle test), against
+            # the rate a divergent 128-bit gather reaches when every row hits L1 (tools/microbench/gather2.cu, profiles/r1_microbench_peaks.txt)
+            rows_per_ray = 7.0 * stats["node_visits_per_ray"] + 3.0 * stats["tri_tests_per_ray"]
+            rows_rate = (value / world) * 1e6 * rows_per_ray / (sm_count * sm_mhz * 1e6)
+            roofline["l1_gather"] = {"rows_per_ray": rows_per_ray, "rows_per_clk_per_sm": rows_rate, "peak_rows_per_clk_per_sm_all_l1_hits": 2.9,
+                                     "frac": rows_rate / 2.9, "l1_hit_rate_ncu": 0.70,
+                                     "note": "misses cost about twice a hit in the data stage (1.3-1.5 rows/clk): ncu puts the stage at 85 % of its wavefront peak"}
         cw, ch, cspp = CPU_SAMPLE[scene]
         try:
             mr, crays, csec, kind, cores = run_reference_cpu(scene, cw, ch, cspp)
