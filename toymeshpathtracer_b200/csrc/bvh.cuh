@@ -78,53 +78,13 @@ struct HitRec {
 
 // maths.cpp:339-380 on a precomputed (v0, e1, e2) slot.  Returns true iff the reference's
 // function would return true for [tMin, tMax]; t/u/v get the reference's bits.
-#ifndef TMPT_TRI_FLAT
-#define TMPT_TRI_FLAT 0
-#endif
-#ifndef TMPT_POP2
-#define TMPT_POP2 0
-#endif
-#ifndef TMPT_TRI_PREFILTER
-#define TMPT_TRI_PREFILTER 0   // measured in round 2 (the review's "two-stage test"): -DTMPT_TRI_PREFILTER=1, not the default
-#endif
-#ifndef TMPT_LEAF2
-#define TMPT_LEAF2 0
-#endif
-TMPT_HD float fmaf_(float a, float b, float c);  // (defined below)
-// Stage one of a two-stage test (experiment): the determinant and u in FUSED arithmetic (12 instructions instead of 22, no
-// division), with a slack of 1e-3 |det| + 1e-6 around [0, 1] -- three orders of magnitude more than the two forms of the same
-// expression can differ -- so that it only rejects what the exact test rejects too.  Survivors take the exact test.
-TMPT_HD bool mt_prefilter_rejects(ex::V3 o, ex::V3 d, ex::V3 v0, ex::V3 e1, ex::V3 e2) {
-    const float px = fmaf_(d.y, e2.z, -(e2.y * d.z)), py = fmaf_(d.z, e2.x, -(e2.z * d.x)), pz = fmaf_(d.x, e2.y, -(e2.x * d.y));
-    const float det = fmaf_(e1.z, pz, fmaf_(e1.y, py, e1.x * px));
-    const float tx = o.x - v0.x, ty = o.y - v0.y, tz = o.z - v0.z;
-    const float un = fmaf_(tz, pz, fmaf_(ty, py, tx * px));
-    const float ad = fabsf(det), us = det < 0.0f ? -un : un, slack = fmaf_(1.0e-3f, ad, 1.0e-6f);
-    return us < -slack || us > ad + slack;
-}
+
 
 TMPT_HD bool mt_exact(ex::V3 o, ex::V3 d, ex::V3 v0, ex::V3 e1, ex::V3 e2, float tMin, float tMax,
                       float& t, float& u, float& v) {
     const float Epsilon = 1e-5f;
-#if TMPT_TRI_PREFILTER
-    if (mt_prefilter_rejects(o, d, v0, e1, e2)) return false;
-#endif
     ex::V3 pvec = ex::cross(d, e2);
     float det = ex::dot(e1, pvec);
-#if TMPT_TRI_FLAT
-    // Straight-line form: the reference's four exits (maths.cpp:350-351, 358-359, 365-366, 371) are evaluated on the same
-    // values and OR-ed.  A warp leaves the sequential form early only when EVERY lane fails the same test, which with 5-10
-    // lanes per test almost never happens, so the exits only cost branches and reconvergence points.  Values computed
-    // past a failed test are garbage (possibly NaN / Inf) and never used: the function's result is `false`.
-    const float invDet = ex::rcp(det);
-    const ex::V3 tvec = ex::sub(o, v0);
-    u = ex::mul(ex::dot(tvec, pvec), invDet);
-    const ex::V3 qvec = ex::cross(tvec, e1);
-    v = ex::mul(ex::dot(d, qvec), invDet);
-    t = ex::mul(ex::dot(e2, qvec), invDet);
-    const bool reject = (det > -Epsilon && det < Epsilon) | (u < 0.0f) | (u > 1.0f) | (v < 0.0f) | (ex::add(u, v) > 1.0f);
-    return !reject & (t >= tMin) & (t <= tMax);
-#else
     // The determinant test (maths.cpp:350-351) and the u test (:358-359) share ONE exit: the same values in the
     // same order decide, but v0 is needed before the first branch, so the compiler cannot sink the triangle's
     // first row below it and turn one memory round trip into two dependent ones.  (A near-zero det -- under
@@ -138,7 +98,6 @@ TMPT_HD bool mt_exact(ex::V3 o, ex::V3 d, ex::V3 v0, ex::V3 e1, ex::V3 e2, float
     if (v < 0.0f || ex::add(u, v) > 1.0f) return false;
     t = ex::mul(ex::dot(e2, qvec), invDet);
     return t >= tMin && t <= tMax;
-#endif
 }
 
 // Hit.pos / Hit.normal exactly as maths.cpp:374-375 forms them, from the ORIGINAL vertices.
@@ -546,9 +505,6 @@ struct WalkState {
     ex::V3 o, d;
     HitRec best;
     uint32_t cur, triPos, triEnd;
-#if TMPT_LEAF2
-    uint32_t triPos2, triEnd2;  // a second parked leaf: a lane that reaches a leaf while the first is still being tested keeps walking
-#endif
     int sp;
     bool any;
 };
@@ -558,9 +514,6 @@ TMPT_HD void walk_start(WalkState& w, const SceneView& sc, ex::V3 o, ex::V3 d, f
     w.best.id = -1; w.best.t = tMax; w.best.u = 0.0f; w.best.v = 0.0f;
     w.cur = ray_has_nan(o, d) ? NONE : sc.rootRef;
     w.triPos = 0; w.triEnd = 0;
-#if TMPT_LEAF2
-    w.triPos2 = 0; w.triEnd2 = 0;
-#endif
     w.sp = 0;
     w.any = any;
 }
@@ -607,13 +560,6 @@ TMPT_HD bool walk_step(WalkState& w, const SceneView& sc, float tMin, float tMax
         w.triEnd = w.triPos + (uint32_t)leaf_count(w.cur);
         w.cur = NONE;
     }
-#if TMPT_LEAF2
-    if (w.cur != NONE && ref_is_leaf(w.cur) && w.triPos2 == w.triEnd2) {  // the first slot is busy: park in the second
-        w.triPos2 = leaf_first(w.cur);
-        w.triEnd2 = w.triPos2 + (uint32_t)leaf_count(w.cur);
-        w.cur = NONE;
-    }
-#endif
     if (STATS) {
         if (w.cur != NONE && ref_is_leaf(w.cur)) ++stats->leafWaits;
         const bool triAny = stats_any(w.triPos < w.triEnd);
@@ -624,38 +570,18 @@ TMPT_HD bool walk_step(WalkState& w, const SceneView& sc, float tMin, float tMax
     const bool popping = w.cur == NONE && w.sp > 0;
     unsigned long long top = 0;
     if (popping) top = stack.get(w.sp - 1);
-#if TMPT_POP2
-    // ... and the entry under it: one pop in thirteen finds an entry that the shrinking best t has culled (0.98 per ray,
-    // tmpt_render_stats), and the lane then sits out a whole iteration; with both entries at hand it takes the second instead
-    const bool popping2 = popping && w.sp > 1;
-    unsigned long long second = 0;
-    if (popping2) second = stack.get(w.sp - 2);
-#endif
     if (w.triPos < w.triEnd) {
         if (STATS) ++stats->tris;
         if (tri_step(sc, w.triPos++, w.o, w.d, tMin, tMax, w.best) && w.any) return true;
-#if TMPT_LEAF2
-        if (w.triPos == w.triEnd) { w.triPos = w.triPos2; w.triEnd = w.triEnd2; w.triPos2 = 0; w.triEnd2 = 0; }
-#endif
     }
     // pop ONE entry per iteration.  If the shrinking best.t has culled it the lane sits out the next node step and pops again
     // behind the next prefetch.  (A loop here that pops until something survives ran in 75 % of the iterations for a single
     // lane, with its stack latency exposed to the whole warp: +3.3 % without it.)
-#if TMPT_POP2
-    if (popping) {
-        const bool ok1 = ex::u2f((uint32_t)(top >> 32)) <= w.best.t;
-        const bool ok2 = popping2 && ex::u2f((uint32_t)(second >> 32)) <= w.best.t;
-        w.sp -= (ok1 || !popping2) ? 1 : 2;
-        w.cur = ok1 ? (uint32_t)top : ok2 ? (uint32_t)second : NONE;
-        if (STATS && !ok1 && !ok2) ++stats->culledPops;
-    }
-#else
     if (popping) {
         --w.sp;
         if (ex::u2f((uint32_t)(top >> 32)) <= w.best.t) w.cur = (uint32_t)top;
         else if (STATS) ++stats->culledPops;
     }
-#endif
     const bool done = w.cur == NONE && w.triPos == w.triEnd && w.sp == 0;
     if (STATS && done) {
         const int lim[5] = {4, 8, 12, 16, 24};
