@@ -366,15 +366,6 @@ TMPT_HD uint32_t wide_node_step(const SceneView& sc, uint32_t node, const RayCtx
     const float4 ny = ld_row_node(sc.nodes + (row0 + 2u + r.sy)), fy = ld_row_node(sc.nodes + (row0 + 2u + (r.sy ^ 1u)));
     const float4 nz = ld_row_node(sc.nodes + (row0 + 4u + r.sz)), fz = ld_row_node(sc.nodes + (row0 + 4u + (r.sz ^ 1u)));
     const float4 rf = ld_row_node(sc.nodes + (row0 + 6u));
-#ifdef TMPT_PROBE_EXTRA_ROWS
-    {   // PROBE (never shipped): how sensitive is the frame time to L1 rows?  n more loads of rows of the same node (L1 hits), kept alive
-        // through one LOP3 each and a store that never happens
-        uint32_t acc = 0;
-#pragma unroll
-        for (int k = 0; k < TMPT_PROBE_EXTRA_ROWS; ++k) acc ^= ex::f2u(ld_row_node(sc.nodes + (row0 + (uint32_t)k)).x);
-        if (acc == 0x7FC12345u) *sc.status = acc;
-    }
-#endif
     float a[4], b[4];
     uint32_t ref[4];
 #if defined(__CUDA_ARCH__) && TMPT_FMA2
