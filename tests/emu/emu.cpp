@@ -275,6 +275,21 @@ void emu_render_stats(void* h, const float cam22[22], int w, int hgt, int spp, u
     out[0] = rays; out[1] = nodes; out[2] = tris;
 }
 
+// walk iterations of each ray (development: distribution of ray lengths, tools/sim_pool.py)
+void emu_ray_iters(void* h, const float* rays6, long n, float tMin, float tMax, int anyHit, int* outIters) {
+    EmuScene* s = (EmuScene*)h;
+#pragma omp parallel for schedule(dynamic, 256)
+    for (long i = 0; i < n; ++i) {
+        const float* r = rays6 + i * 6;
+        bvh::LocalStack stack;
+        bvh::WalkState w;
+        bvh::walk_start(w, s->view, ex::v3(r[0], r[1], r[2]), ex::v3(r[3], r[4], r[5]), tMax, anyHit != 0);
+        int it = 1;
+        while (!bvh::walk_step<false>(w, s->view, tMin, tMax, stack, nullptr)) ++it;
+        outIters[i] = it;
+    }
+}
+
 void emu_sincos(float a, float* s, float* c) { ex::sincos_spec(a, *s, *c); }
 int emu_sah_must_halve(int depth, int count) { return bld::sah_must_halve(depth, count) ? 1 : 0; }
 int emu_max_tree_depth() { return bvh::MAX_TREE_DEPTH; }
