@@ -207,12 +207,12 @@ TMPT_HD float4 ld_row(const float4* p) {
 #endif
 }
 // the same load with an L1 eviction-priority hint.  Node rows are re-used (the top of the tree by every ray), triangle rows and the
-// hit payload are read once per test / per hit: nodes evict_last, the other two evict_first.  TMPT_CACHE_HINTS is a bit mask:
+// hit payload are read once per test / per hit: nodes evict_last, the other two evict_first in L1.  TMPT_CACHE_HINTS is a bit mask:
 // 1 node rows evict_last, 2 triangle rows evict_first, 4 triangle rows no_allocate, 8 payload rows evict_first, 16 payload rows
-// no_allocate.  Measured on the headline frame (profiles/r2_tuning_sweeps.txt): 0: 5225-5238, 1: 5238, 2: 5267, 3: 5269, 5: 5256,
-// 11: 5278 (+0.9 %, the default), 19: 5267, 21: 5257 Mrays/s.
+// no_allocate, 32 the evict_first loads carry an L2 evict_last policy.  Measured on the headline frame (profiles/r2_tuning_sweeps.txt):
+// 0: 5219-5238 Mrays/s, 0.06 GB of DRAM reads per frame | 3: 5273, 0.90 GB | 11: 5277, 2.54 GB | 43 (the default): 5279, 0.06 GB.
 #ifndef TMPT_CACHE_HINTS
-#define TMPT_CACHE_HINTS 11
+#define TMPT_CACHE_HINTS 43
 #endif
 #ifdef __CUDA_ARCH__
 #define TMPT_LD_HINT(name, hint)                                                                                                      \
@@ -222,7 +222,19 @@ TMPT_HD float4 ld_row(const float4* p) {
         return v;                                                                                                                     \
     }
 TMPT_LD_HINT(ld_row_evict_last, "L1::evict_last")
+#if TMPT_CACHE_HINTS & 32
+// evict_first in L1 only: without an L2 policy the line is the first to leave L2 as well, and the 3 MB of triangle rows and hit payload are
+// re-read from DRAM all frame long (ncu: dram__bytes_read 0.06 -> 2.5 GB per frame).  The L2 cache-hint operand keeps them resident there.
+__device__ __forceinline__ float4 ld_row_evict_first(const float4* p) {
+    float4 v;
+    unsigned long long pol;
+    asm("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+    asm volatile("ld.global.nc.L1::evict_first.L2::cache_hint.v4.f32 {%0,%1,%2,%3}, [%4], %5;" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p), "l"(pol));
+    return v;
+}
+#else
 TMPT_LD_HINT(ld_row_evict_first, "L1::evict_first")
+#endif
 TMPT_LD_HINT(ld_row_no_allocate, "L1::no_allocate")
 #undef TMPT_LD_HINT
 #endif
