@@ -500,7 +500,7 @@ def bench_b200(args, scene, w, h, spp, rank, world, local_rank):
             "hbm_context": {"algorithmic_bytes_per_frame": int(tris.size * 4 + w * h * 4), "hbm_peak_gbs_measured": peaks.get("hbm_gbs"),
                             "hbm_frac": (tris.size * 4 + w * h * 4) / (kernel_ms * 1e-3) / 1e9 / peaks["hbm_gbs"] if peaks.get("hbm_gbs") else None},
             "kernel": "k_render", "kernel_ms": kernel_ms,
-            "limiter": "L1 data stage (l1tex__data_pipe_lsu_wavefronts 85 % of peak) and issue slots (69 %), profiles/r2_k_render_ncu_summary.txt",
+            "limiter": "L1 data stage (l1tex__data_pipe_lsu_wavefronts 84 % of peak) and issue slots (69 %), profiles/r2c_k_render_ncu_summary.txt",
         }
         if stats:
             # the limiter in the kernel's own units: 16-byte rows gathered per clock and SM (7 per node step, 3 per triangle test), against
@@ -509,7 +509,7 @@ def bench_b200(args, scene, w, h, spp, rank, world, local_rank):
             rows_rate = (value / world) * 1e6 * rows_per_ray / (sm_count * sm_mhz * 1e6)
             roofline["l1_gather"] = {"rows_per_ray": rows_per_ray, "rows_per_clk_per_sm": rows_rate, "peak_rows_per_clk_per_sm_all_l1_hits": 2.9,
                                      "frac": rows_rate / 2.9, "l1_hit_rate_ncu": 0.70,
-                                     "note": "misses cost about twice a hit in the data stage (1.3-1.5 rows/clk): ncu puts the stage at 85 % of its wavefront peak"}
+                                     "note": "misses cost about twice a hit in the data stage (1.3-1.5 rows/clk): ncu puts the stage at 84 % of its wavefront peak"}
         cw, ch, cspp = CPU_SAMPLE[scene]
         try:
             mr, crays, csec, kind, cores = run_reference_cpu(scene, cw, ch, cspp)
