@@ -199,3 +199,27 @@ def test_real_sponza_override(tmp_path, monkeypatch):
     assert tris.shape == (3, 9)  # the triangle + the two floor triangles LoadScene adds
     monkeypatch.delenv("TMPT_SPONZA_OBJ")
     assert "stand-in" in bench.scene_label("sponza")
+
+
+def test_build_staleness_is_by_content_and_safe_under_concurrency(tmp_path):
+    """toymeshpathtracer_b200.build decides by a hash of the source CONTENTS (a `git checkout` or the copy to a GPU box changes
+    mtimes without changing a byte; a spurious rebuild under torchrun would be eight ranks rewriting libtmpt.so at once -- that
+    happened once on an 8-GPU box) and builds under a file lock.  Touching a source must not trigger a rebuild; several processes
+    asking at once must all get the library."""
+    import subprocess
+    import sys
+    import time
+    from toymeshpathtracer_b200 import build as tb
+    tb.build()                                   # up to date from here on
+    before = os.path.getmtime(tb.LIB)
+    src = os.path.join(tb.CSRC, "bvh.cuh")
+    os.utime(src)                                # newer mtime, same bytes
+    code = "import toymeshpathtracer_b200.build as b, toymeshpathtracer_b200 as tm; b.build(); print(len(tm.ABI_SYMBOLS), tm.lib().tmpt_device_count() >= 0)"
+    t0 = time.time()
+    procs = [subprocess.Popen([sys.executable, "-c", code], cwd=os.path.dirname(tb.HERE), stdout=subprocess.PIPE, text=True) for _ in range(4)]
+    outs = [p.communicate(timeout=300)[0] for p in procs]
+    assert all(p.returncode == 0 for p in procs) and all(o.strip().endswith("True") for o in outs)
+    assert os.path.getmtime(tb.LIB) == before and time.time() - t0 < 60   # nobody rebuilt
+    assert not tb._stale(tb.LIB)
+    with open(tb._stamp(tb.LIB)) as f:
+        assert f.read().strip() == tb._source_hash()
