@@ -556,6 +556,59 @@ __global__ void __launch_bounds__(128) k_hit_scene(bvh::SceneView sc, const floa
 }
 
 
+#if TMPT_EXPERIMENTS
+// K2/K3 with per-lane ray REFILL (experiment: -DTMPT_EXPERIMENTS=1 and TMPT_HIT_REFILL=gate; measured in round 2: 5244 -> 4843 Mrays/s
+// at the best gate, profiles/r2_tuning_sweeps.txt): a lane whose ray has ended takes the next ray of the batch instead of
+// waiting for the warp's longest ray; the fetch code runs when at least GATE lanes are idle (or nothing else is left to do).
+template <int MODE, int GATE>
+__global__ void __launch_bounds__(128) k_hit_scene_refill(bvh::SceneView sc, const float* __restrict__ rays6, long long nRays, float tMin, float tMax,
+                                                           int* __restrict__ outID, float* __restrict__ outT, float* __restrict__ outPos,
+                                                           float* __restrict__ outNormal, unsigned long long* __restrict__ counter) {
+    constexpr unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    bvh::LocalStack stack;
+    bvh::WalkState w;
+    long long ray = -1;
+    bool exhausted = false;
+    for (;;) {
+        const unsigned idle = __ballot_sync(FULL, ray < 0);
+        if (idle && !exhausted && (__popc(idle) >= GATE || idle == FULL)) {
+            const int cnt = __popc(idle);
+            unsigned long long base = 0;
+            if (lane == 0) base = atomicAdd(counter, (unsigned long long)cnt);
+            base = __shfl_sync(FULL, base, 0);
+            exhausted = base + (unsigned long long)cnt >= (unsigned long long)nRays;
+            if (ray < 0) {
+                const long long i = (long long)base + __popc(idle & ((1u << lane) - 1u));
+                if (i < nRays) {
+                    const float* r = rays6 + i * 6;
+                    bvh::walk_start(w, sc, ex::v3(r[0], r[1], r[2]), ex::v3(r[3], r[4], r[5]), tMax, MODE == TMPT_HIT_ANY);
+                    ray = i;
+                }
+            }
+        }
+        if (__all_sync(FULL, ray < 0)) break;
+        if (ray >= 0 && bvh::walk_step<false>(w, sc, tMin, tMax, stack, nullptr)) {
+            const bvh::HitRec h = w.best;
+            if (MODE == TMPT_HIT_ANY) outID[ray] = h.id < 0 ? -1 : 1;
+            else {
+                outID[ray] = h.id;
+                if (h.id >= 0) {
+                    if (outT) outT[ray] = h.t;
+                    if (outPos || outNormal) {
+                        ex::V3 pos, nrm;
+                        bvh::hit_payload(sc, h.id, h.u, h.v, pos, nrm);
+                        if (outPos) { outPos[ray * 3] = pos.x; outPos[ray * 3 + 1] = pos.y; outPos[ray * 3 + 2] = pos.z; }
+                        if (outNormal) { outNormal[ray * 3] = nrm.x; outNormal[ray * 3 + 1] = nrm.y; outNormal[ray * 3 + 2] = nrm.z; }
+                    }
+                }
+            }
+            ray = -1;
+        }
+    }
+}
+#endif  // TMPT_EXPERIMENTS
+
 // ------------------------------------------------------------------------------------------
 // K4: path tracing.  Work unit = (8x4 pixel tile, one chunk of chunk_len(spp) samples) per warp, fetched from a
 // global counter (persistent CTAs); a lane runs the samples of its pixel's chunk serially
@@ -1264,6 +1317,23 @@ extern "C" int tmpt_hit_scene(const tmpt_scene* s, const float* rays6, int64_t n
     const int G = (int)std::min<long long>(div_up(nRays, B), (long long)s->smCount * 64);
     if (getenv("TMPT_HIT_KERNEL") && atoi(getenv("TMPT_HIT_KERNEL")) > 0)
         return tmpt::fail(TMPT_ERR_ARG, "TMPT_HIT_KERNEL: the experimental HitScene kernels of round 1 were removed (see profiles/r1_hit_scene_variants_ncu.txt)");
+#if TMPT_EXPERIMENTS
+    static const int refillGate = getenv("TMPT_HIT_REFILL") ? atoi(getenv("TMPT_HIT_REFILL")) : 0;
+    if (refillGate > 0 && mode != TMPT_HIT_BRUTE) {
+        CU_TRY(cudaMemsetAsync(s->d_fetchCounter, 0, sizeof(unsigned long long), st));
+        int perSM = 0;
+#define REFILL_CASE(M, GT)                                                                                                     \
+        if (mode == M && refillGate == GT) {                                                                                   \
+            CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, k_hit_scene_refill<M, GT>, B, 0));                    \
+            const int GP = (int)std::min<long long>(div_up(nRays, B), (long long)s->smCount * std::max(perSM, 1));            \
+            LAUNCH((k_hit_scene_refill<M, GT>), GP, B, 0, st, s->view, dRays, (long long)nRays, tMin, tMax, dID, dT, dPos, dNrm, s->d_fetchCounter); \
+        } else
+        REFILL_CASE(TMPT_HIT_CLOSEST, 1) REFILL_CASE(TMPT_HIT_CLOSEST, 4) REFILL_CASE(TMPT_HIT_CLOSEST, 8) REFILL_CASE(TMPT_HIT_CLOSEST, 16)
+        REFILL_CASE(TMPT_HIT_ANY, 1) REFILL_CASE(TMPT_HIT_ANY, 4) REFILL_CASE(TMPT_HIT_ANY, 8) REFILL_CASE(TMPT_HIT_ANY, 16)
+#undef REFILL_CASE
+        return tmpt::fail(TMPT_ERR_ARG, "TMPT_HIT_REFILL=%d: gates are 1, 4, 8, 16", refillGate);
+    } else
+#endif
     if (mode == TMPT_HIT_CLOSEST) LAUNCH((k_hit_scene<TMPT_HIT_CLOSEST, false>), G, B, 0, st, s->view, dRays, (long long)nRays, tMin, tMax, dID, dT, dPos, dNrm, nullptr);
     else if (mode == TMPT_HIT_ANY) LAUNCH((k_hit_scene<TMPT_HIT_ANY, false>), G, B, 0, st, s->view, dRays, (long long)nRays, tMin, tMax, dID, dT, dPos, dNrm, nullptr);
     else LAUNCH((k_hit_scene<TMPT_HIT_BRUTE, false>), G, B, 0, st, s->view, dRays, (long long)nRays, tMin, tMax, dID, dT, dPos, dNrm, nullptr);
