@@ -1,13 +1,15 @@
 // kernels.cu -- CUDA kernels (sm_100a) and the compute half of the C ABI (include/tmpt.h).
 //
-//   K1  BVH build      k_prim_bounds, k_prim_boxes, k_sah_level (binned SAH, default) or k_morton, k_radix_sort,
-//                      k_leaf_boxes, k_karras, k_refit (LBVH); then k_collapse to 4-wide nodes
+//   K1  BVH build      k_prim_bounds, k_prim_boxes, k_sah_build (binned SAH, all levels in one cooperative launch; default) or
+//                      k_morton, k_radix_sort, k_leaf_boxes, k_karras, k_refit (LBVH); then k_collapse_all to 4-wide nodes
 //                      (replaces Scene::BuildOctree, scene.cpp:75-160)
 //   K2  closest hit    k_hit_scene<CLOSEST>   (Scene::HitScene, scene.cpp:86-97, batched)
 //   K3  any hit        k_hit_scene<ANY>       (the shadow query of Scatter, main.cpp:59)
 //       brute force    k_hit_scene<BRUTE>     (upstream's all-triangle scan; cross-check only)
 //   K4  path tracing   k_render, k_resolve    (TraceImageBody / Trace / Scatter, main.cpp:44-119, 192-238)
-//   K5  stripe gather  k_unpack_stripes       (rank 0 after the multi-GPU gather)
+//   K5  share gather   k_unpack_stripes       (rank 0 after the multi-GPU gather; the default multi-GPU path has no gather:
+//                                              every rank's k_render stores its pixels into rank 0's frame over NVLink)
+//   K6  refit          k_refit_pending, k_refit_wide  (tmpt_scene_refit: moved vertices, same topology)
 //
 // There is no CPU fallback in this file: every entry point needs a CUDA device.
 #include <cooperative_groups.h>
