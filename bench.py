@@ -203,6 +203,12 @@ class ClockSampler:
 
 
 
+def _kernel_name(sc):
+    """The render kernel the scene's last frame ran (chosen per frame by a probe: kernels.cu choose_render_kernel)."""
+    k, esc = sc.render_kernel_choice()
+    return {"kernel": {0: "k_render", 1: "k_render_paths"}.get(k, "?"), "probe_escape_fraction": round(esc, 4)}
+
+
 def measure_extra_configs(tm, multigpu, dist, torch, sc_sponza, dev, stream, rank, world, local_rank, flush, peer_enabled):
     """BASELINE.json configs 1-4 as a `configs` array: Mrays/s and ms/frame of each small workload, timed like the headline
     (CUDA events around one frame, L2 flushed before each, 3 warm-up + 5 timed frames, max over ranks).  Configs 1-3 name one
@@ -251,7 +257,7 @@ def measure_extra_configs(tm, multigpu, dist, torch, sc_sponza, dev, stream, ran
             dist.all_reduce(r, op=dist.ReduceOp.SUM)
         out.append({"config": label, "workload": f"{scene_label(scene)} {w}x{h} {spp}spp", "n_gpus": world,
                     "value": int(r.item()) / (float(t.item()) * 1e-3) / 1e6, "unit": "Mrays/s", "ms_per_frame": float(t.item()) / 5,
-                    "rays_per_frame": int(r.item()) // 5, "frames": 5})
+                    "rays_per_frame": int(r.item()) // 5, "frames": 5, "render_kernel": _kernel_name(sc)})
         if peer is not None:
             dist.barrier()
             peer.close()
@@ -530,6 +536,7 @@ def bench_b200(args, scene, w, h, spp, rank, world, local_rank):
                                                                         f"row stripes of {multigpu.DEFAULT_STRIPE_ROWS} over {world} GPUs") + ", BVH replica per GPU, " + (
                            "pixels stored straight into rank 0's frame over NVLink (CUDA IPC peer memory)" if peer else "frame gathered to rank 0 (NCCL)"),
                        "work_unit": "8x4 pixel tile x chunk of spp/32 (1..8) samples per warp, dynamic fetch",
+                       "render_kernel": _kernel_name(sc),
                        "l2": "flushed between timed iterations (256 MB write)", "bvh": {k: info[k] for k in ("node_count", "leaf_count", "max_depth", "sah_cost", "build_ms", "device_bytes")},
                        "scene_build_wall_ms": build_wall_ms},
             "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": 88, "d2h_bytes_per_step": w * h * 4 + 8,

@@ -207,6 +207,13 @@ int tmpt_write_png(const char* path, int width, int height, const uint8_t* rgba,
  * three report lines; returns the process exit code. */
 int tmpt_main(int argc, const char** argv);
 
+/* Which render kernel the last frame of this scene used (kernels.cu: choose_render_kernel):
+ * *kernel = 0 lockstep tiles (k_render), 1 path regeneration (k_render_paths, frames whose paths
+ * leave the scene early), -1 no frame decided yet; *escapeFraction = the probe's measure, the
+ * share of first diffuse bounces that reach the sky.  Both kernels produce the same bytes.  Either
+ * pointer may be NULL. */
+int tmpt_render_kernel_choice(const tmpt_scene* scene, int* kernel, float* escapeFraction);
+
 const char* tmpt_last_error(void);
 int tmpt_device_count(void);
 /* kernels launched by this library since load (bench.py's gpu_launches evidence) */

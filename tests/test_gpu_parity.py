@@ -639,6 +639,40 @@ def test_large_random_scene(oracle):
             assert (a[0] >= 0).sum() > 1000
 
 
+def test_path_regeneration_kernel_is_bit_exact_and_chosen_for_open_frames(tmp_path, oracle):
+    """k_render_paths (lanes take their next sample at bounce boundaries) against the oracle and against k_render:
+    TMPT_RENDER_PATHS=1 / 0 force either kernel -- same bytes, same ray count, one-shot and over progressive passes, on an open
+    scene (suzanne, vs the oracle) and a closed one (sponza).  Left alone, the probe picks k_render_paths for the open frame and
+    k_render for the hall."""
+    import sys
+
+    def run(name, w, h, spp, paths, extra=()):
+        out = str(tmp_path / f"{name}_{paths}_{len(extra)}.npz")
+        env = dict(os.environ)
+        env.pop("TMPT_RENDER_PATHS", None)
+        if paths is not None:
+            env["TMPT_RENDER_PATHS"] = paths
+        r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "render_probe.py"), name, str(w), str(h), str(spp), out, *extra],
+                           env=env, capture_output=True, text=True, timeout=900)
+        assert r.returncode == 0, r.stderr[-2000:]
+        z = np.load(out)
+        return z["img"], int(z["rays"]), int(z["kernel"]), float(z["escape"])
+
+    name, w, h, spp = "suzanne", 200, 120, 6
+    sc = load_scene(name)
+    cam = tm.camera_for_scene(f"{name}.obj", sc["bounds_min"], sc["bounds_max"], w, h)
+    oimg, orays = oracle.render(sc["tris"], cam, w, h, spp)
+    for paths, want in (("0", 0), ("1", 1), (None, 1)):
+        img, rays, kernel, escape = run(name, w, h, spp, paths)
+        assert kernel == want and rays == orays and (img == oimg).all(), (paths, kernel, escape)
+    assert escape > 0.3  # (an object on a floor under the sky)
+    prog = [run(name, 101, 57, 20, paths, ("2", "1", "3")) for paths in ("0", "1")]
+    assert prog[0][2] == 0 and prog[1][2] == 1 and prog[0][1] == prog[1][1] and (prog[0][0] == prog[1][0]).all()
+    hall = [run("sponza", 240, 136, 4, paths) for paths in ("0", "1", None)]
+    assert [r[2] for r in hall] == [0, 1, 0] and hall[2][3] < 0.1
+    assert hall[0][1] == hall[1][1] == hall[2][1] and (hall[0][0] == hall[1][0]).all() and (hall[0][0] == hall[2][0]).all()
+
+
 def test_regeneration_render_kernel_gives_the_same_bytes(tmp_path):
     """k_render_regen (per-lane ray regeneration; measured, not shipped: it lives in the -DTMPT_EXPERIMENTS=1 build only)
     schedules the same per-lane arithmetic differently: frame and ray count equal the lockstep kernel's, one-shot and over

@@ -38,7 +38,7 @@ ABI_SYMBOLS = [
     "tmpt_camera_make", "tmpt_camera_for_scene", "tmpt_write_png", "tmpt_main", "tmpt_last_error",
     "tmpt_device_count", "tmpt_launch_count", "tmpt_render_stats", "tmpt_hit_scene_stats",
     "tmpt_frame_alloc", "tmpt_frame_open", "tmpt_frame_close", "tmpt_frame_free", "tmpt_render_multi",
-    "tmpt_scene_refit", "tmpt_progressive_begin", "tmpt_progressive_pass",
+    "tmpt_scene_refit", "tmpt_progressive_begin", "tmpt_progressive_pass", "tmpt_render_kernel_choice",
 ]
 
 
@@ -108,6 +108,7 @@ def lib() -> C.CDLL:
     L.tmpt_camera_for_scene.restype = None
     L.tmpt_write_png.argtypes = [C.c_char_p, i32, i32, vp, i32]
     L.tmpt_main.argtypes = [i32, C.POINTER(C.c_char_p)]
+    L.tmpt_render_kernel_choice.argtypes = [vp, vp, vp]
     L.tmpt_last_error.restype = C.c_char_p
     L.tmpt_launch_count.restype = C.c_uint64
     _lib = L
@@ -294,6 +295,12 @@ class Scene:
         rays, sec = C.c_uint64(0), C.c_double(0.0)
         _check(lib().tmpt_render(self._h, _ptr(cam), width, height, spp, HOST, host_ptr, C.byref(rays), C.byref(sec), None))
         return rays.value, sec.value
+
+    def render_kernel_choice(self):
+        """-> (kernel of the last frame: 0 k_render, 1 k_render_paths, -1 none yet; the probe's escape fraction)."""
+        k, e = C.c_int(-1), C.c_float(0.0)
+        _check(lib().tmpt_render_kernel_choice(self._h, C.byref(k), C.byref(e)))
+        return k.value, e.value
 
     def traversal_stats(self, camera, width: int, height: int, spp: int) -> dict:
         """Instrumented render pass -> mean box / triangle tests per ray (bench.py's roofline figures)."""

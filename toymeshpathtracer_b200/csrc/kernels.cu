@@ -112,6 +112,14 @@ struct tmpt_scene {
     char* h_stage = nullptr;
     size_t stageBytes = 0;
     std::mutex hostCallMutex;      // serialises the entry points that use per-scene scratch (staging, frame, accum, counters)
+    // render-kernel choice (k_render vs k_render_paths), cached per camera / frame size: see k_probe_paths
+    tmpt_camera probeCam{};
+    int probeW = 0, probeH = 0, probeUsePaths = -1;  // -1: no decision yet
+    int lastUsedPaths = -1;                           // what the last frame ran (tmpt_render_kernel_choice)
+    bool probePending = false;                        // a probe is in flight: h_probe is valid once probeDone has passed
+    float probeEscape = 0.0f;
+    unsigned int *d_probe = nullptr, *h_probe = nullptr;  // device counters / their pinned copy
+    cudaEvent_t probeDone = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     bvh::SceneView view{};
     tmpt_scene_info info{};
@@ -856,6 +864,146 @@ __global__ void __launch_bounds__(THREADS, MINB) k_render_regen(const RenderPara
 
 #endif  // TMPT_EXPERIMENTS
 
+// K4'': PATH-level regeneration.  k_render's lanes trace the samples of one tile in lockstep: when a lane's path leaves the scene
+// early (sky), the lane idles until the longest path of the warp has used up its ten bounces -- nothing in the closed Sponza hall,
+// most of the lane slots in open scenes (cube, suzanne, teapot: 2.6 rays per camera sample).  Here a lane whose path has ended takes
+// the next sample of its item, or the next (pixel, chunk) item from a global counter (warp-aggregated: ballot / popc / shfl), at the
+// next BOUNCE BOUNDARY, where the warp is synchronous anyway: the traversals themselves stay lockstep (per-ray regeneration inside a
+// traversal was measured twice and loses), the regeneration code runs when at least GATE lanes need it or nobody is
+// tracing.  Work item = one (pixel, chunk) per lane; consecutive items are the pixels of one 8x4 tile, so a warp starts with a
+// whole tile.  The per-lane arithmetic and its order are those of integ::render_chunk: the frame is byte-identical to k_render's.
+template <int THREADS, int MINB, int GATE>
+__global__ void __launch_bounds__(THREADS, MINB) k_render_paths(const RenderParams p) {
+    constexpr unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    bvh::LocalStack stack;
+    float kk[integ::kMaxDepth];
+    unsigned long long rays = 0;
+    bool havePath = false, done = false, exhausted = false;
+    uint32_t rng = 0;
+    int depth = 0, s = 0, sEnd = 0, x = 0, y = 0, xl = 0, rb = 0, chunk = 0;
+    ex::V3 sum = ex::v3(0.0f, 0.0f, 0.0f), o = sum, d = sum;
+    const float invW = ex::divf(1.0f, (float)p.width), invH = ex::divf(1.0f, (float)p.height);
+    const unsigned long long totalItems = (unsigned long long)p.numTiles * (unsigned long long)p.chunks * 32ull;
+    for (;;) {
+        // ---- regeneration: lanes without a path get their item's next sample, or a new item
+        const unsigned need = __ballot_sync(FULL, !havePath && !done);
+        const unsigned tracing = __ballot_sync(FULL, havePath);
+        if (need && (__popc(need) >= GATE || tracing == 0)) {
+            // (a) items that are finished: store the chunk sum, ask for a new item
+            const bool finished = !havePath && !done && s == sEnd;
+            if (finished && sEnd > 0) {  // (sEnd == 0: the lane has not had an item yet)
+                if (p.useAccum) {
+                    __stcs(&p.accum[((size_t)chunk * p.bandRows + rb) * p.localWidth + xl], make_float4(sum.x, sum.y, sum.z, 0.0f));
+                } else {
+                    const uchar4 px = integ::resolve_pixel(sum, ex::divf(1.0f, (float)p.spp));
+                    if (p.frame) p.frame[(size_t)y * p.width + x] = px;
+                    else p.outStripes[(size_t)(p.bandRow0 + rb) * p.localWidth + xl] = px;
+                }
+                s = 0; sEnd = 0;  // (no item: s == sEnd makes the lane ask for one below)
+            }
+            bool wantItem = !havePath && !done && s == sEnd;
+            while (__any_sync(FULL, wantItem)) {  // (a lane whose item fell outside the frame asks again)
+                const unsigned want = __ballot_sync(FULL, wantItem);
+                if (exhausted) { if (wantItem) { done = true; wantItem = false; } break; }
+                const int cnt = __popc(want);
+                unsigned long long base = 0;
+                if (lane == __ffs((int)want) - 1) base = atomicAdd(p.laneCounter, (unsigned long long)cnt);
+                base = __shfl_sync(FULL, base, __ffs((int)want) - 1);
+                exhausted = base + (unsigned long long)cnt >= totalItems;
+                if (wantItem) {
+                    const unsigned long long item = base + (unsigned long long)__popc(want & ((1u << lane) - 1u));
+                    if (item >= totalItems) { done = true; wantItem = false; }
+                    else {
+                        const uint32_t wi = (uint32_t)(item >> 5), li = (uint32_t)item & 31u;
+                        chunk = (int)(wi / (uint32_t)p.numTiles);
+                        const uint32_t tile = wi - (uint32_t)chunk * (uint32_t)p.numTiles;
+                        const int tx = (int)(tile % (uint32_t)p.tilesX), ty = (int)(tile / (uint32_t)p.tilesX);
+                        xl = tx * 8 + (int)(li & 7u); rb = ty * 4 + (int)(li >> 3);
+                        const int r = p.bandRow0 + rb;
+                        if (xl < p.localWidth && r < p.ownedRows && local_to_global(xl, r, p.stripeRows, p.rank, p.world, p.width, x, y)) {
+                            const int gchunk = p.chunk0 + chunk;
+                            rng = ex::chunk_seed((uint32_t)gchunk, (uint32_t)y * (uint32_t)p.width + (uint32_t)x, (uint32_t)p.width * (uint32_t)p.height);
+                            s = gchunk * p.chunkLen;
+                            sEnd = s + p.chunkLen < p.spp ? s + p.chunkLen : p.spp;
+                            sum = ex::v3(0.0f, 0.0f, 0.0f);
+                            wantItem = false;
+                        }
+                    }
+                }
+            }
+            // (b) the next camera ray of every lane that has an item and no path
+            if (!havePath && !done && s < sEnd) {
+                integ::primary_ray(p.cam, x, y, invW, invH, rng, o, d);
+                depth = 0;
+                havePath = true;
+            }
+        }
+        if (__all_sync(FULL, done)) break;
+        // ---- one bounce of every lane that has a path (lockstep traversals)
+        bool hit = false;
+        bvh::HitRec h;
+        h.id = -1;
+        if (havePath) {
+            ++rays;
+            h = bvh::traverse_with<false, false, false>(stack, p.sc, o, d, integ::kMinT, integ::kMaxT);
+            hit = h.id >= 0;
+        }
+        ex::V3 pos = ex::v3(0.0f, 0.0f, 0.0f), normal = pos;
+        bool shadowed = false;
+        if (hit) {
+            bvh::hit_payload(p.sc, h.id, h.u, h.v, pos, normal);
+            ++rays;
+            shadowed = bvh::traverse_with<true, false, false>(stack, p.sc, pos, p.lightDir, integ::kMinT, integ::kMaxT).id >= 0;
+        }
+        if (havePath) {
+            bool ended = false;
+            ex::V3 color = ex::v3(0.0f, 0.0f, 0.0f);
+            if (hit) {
+                kk[depth] = shadowed ? 0.0f : integ::sun_term(normal, d, p.lightDir);
+                d = integ::scatter_dir(pos, normal, rng);
+                o = pos;
+                ++depth;
+                ended = depth == integ::kMaxDepth;  // out of bounces: the path's colour starts at 0 (main.cpp:84, 112-116)
+            } else {
+                color = integ::sky(d);
+                ended = true;
+            }
+            if (ended) {
+                for (int i = depth - 1; i >= 0; --i) color = integ::unwind_step(kk[i], color);
+                sum = ex::add(sum, color);
+                ++s;
+                havePath = false;
+            }
+        }
+    }
+    for (int k = 16; k > 0; k >>= 1) rays += __shfl_xor_sync(FULL, rays, k);
+    if (lane == 0 && rays) atomicAdd(p.rayCount, rays);
+}
+
+// Which render kernel?  k_render_paths wins where paths leave the scene early (+13..25 % on cube / suzanne / teapot), k_render where
+// they do not (Sponza: +8 %).  The probe traces 4096 camera rays on a 64 x 64 grid over the frame and one diffuse bounce from each
+// hit: out[0] = camera rays that hit, out[1] = bounce rays traced, out[2] = bounce rays that escaped to the sky.  ~10 us; the
+// decision is cached with the scene for as long as camera and frame size stay the same (launch_render).
+__global__ void __launch_bounds__(128) k_probe_paths(bvh::SceneView sc, integ::Camera cam, int width, int height, unsigned int* __restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;  // 4096 lanes
+    const int gx = i & 63, gy = i >> 6;
+    const int x = (int)(((long long)gx * 2 + 1) * width / 128), y = (int)(((long long)gy * 2 + 1) * height / 128);
+    uint32_t rng = ex::pixel_seed(0x50524F42u + (uint32_t)i);  // "PROB": the probe's own streams, no relation to a frame's
+    ex::V3 o, d;
+    integ::primary_ray(cam, x, y, ex::divf(1.0f, (float)width), ex::divf(1.0f, (float)height), rng, o, d);
+    bvh::HitRec h = bvh::traverse<false>(sc, o, d, integ::kMinT, integ::kMaxT);
+    unsigned hit0 = h.id >= 0 ? 1u : 0u, esc = 0u;
+    if (hit0) {
+        ex::V3 pos, normal;
+        bvh::hit_payload(sc, h.id, h.u, h.v, pos, normal);
+        d = integ::scatter_dir(pos, normal, rng);
+        esc = bvh::traverse<false>(sc, pos, d, integ::kMinT, integ::kMaxT).id < 0 ? 1u : 0u;
+    }
+    const unsigned nHit = __popc(__ballot_sync(0xffffffffu, hit0 != 0u)), nEsc = __popc(__ballot_sync(0xffffffffu, esc != 0u));
+    if ((threadIdx.x & 31) == 0) { atomicAdd(&out[0], nHit); atomicAdd(&out[1], nHit); atomicAdd(&out[2], nEsc); }
+}
+
 // pixel = in-order sum of its chunk sums, then mean / sqrt / quantise (main.cpp:221-233)
 __global__ void k_resolve(const RenderParams p, int bandRows) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -1238,6 +1386,7 @@ extern "C" int tmpt_scene_refit(tmpt_scene* s, const float* tris9, int triCount,
         s->info.bounds_max[k] = bld::ordered_to_float(hb[3 + k]);
     }
     s->view.farLimit = bvh_far_limit(s->info);
+    s->probeW = 0;  // moved geometry: the next frame probes again (k_probe_paths)
     float ms = 0.0f;
     CU_TRY(cudaEventElapsedTime(&ms, s->ev0, s->ev1));
     if (seconds) *seconds = ms * 1e-3;
@@ -1251,6 +1400,9 @@ extern "C" void tmpt_scene_destroy(tmpt_scene* s) {
     cudaFree(s->d_tris9); cudaFree(s->d_nodes); cudaFree(s->d_qnodes); cudaFree(s->d_status);  // (d_tris, d_hitdata live inside d_nodes)
     cudaFree(s->d_tileCounter); cudaFree(s->d_rayCount); cudaFree(s->d_fetchCounter); cudaFree(s->d_frame); cudaFree(s->d_accum); cudaFree(s->d_sum);
     cudaFree(s->d_stage);
+    cudaFree(s->d_probe);
+    if (s->h_probe) cudaFreeHost(s->h_probe);
+    if (s->probeDone) cudaEventDestroy(s->probeDone);
     if (s->h_stage) cudaFreeHost(s->h_stage);
     if (s->ev0) cudaEventDestroy(s->ev0);
     if (s->ev1) cudaEventDestroy(s->ev1);
@@ -1407,6 +1559,48 @@ struct ProgressivePass {
     float4* sum;
 };
 
+// k_render or k_render_paths for this frame?  TMPT_RENDER_PATHS=0 / 1 forces the choice (tests, A/B).  Otherwise k_probe_paths
+// decides: a frame whose first diffuse bounce escapes to the sky more than kOpenFrame of the time is an "open" frame.  The probe
+// runs when camera or frame size change, on the frame's stream, WITHOUT stalling the host: its result is picked up by the first
+// later frame that finds it complete, so a moving camera renders with a decision that is a frame or two old (both kernels produce
+// the same bytes, the choice is about speed only).  Only the very first frame of a scene waits for its probe.
+static constexpr float kOpenFrame = 0.15f;
+static int choose_render_kernel(tmpt_scene* s, const tmpt_camera* camera, const integ::Camera& cam, int width, int height, cudaStream_t st,
+                                bool* usePaths) {
+    static const int pathsEnv = getenv("TMPT_RENDER_PATHS") ? atoi(getenv("TMPT_RENDER_PATHS")) : -1;
+    *usePaths = pathsEnv > 0;
+    if (pathsEnv >= 0 || s->triCount == 0) return TMPT_OK;
+    if (!s->d_probe) {
+        CU_TRY(cudaMalloc((void**)&s->d_probe, 4 * sizeof(unsigned int)));
+        CU_TRY(cudaMallocHost((void**)&s->h_probe, 4 * sizeof(unsigned int)));
+        CU_TRY(cudaEventCreateWithFlags(&s->probeDone, cudaEventDisableTiming));
+    }
+    auto consume = [&]() {
+        s->probeEscape = s->h_probe[1] ? (float)s->h_probe[2] / (float)s->h_probe[1] : 1.0f;  // (no camera ray hits anything: open)
+        s->probeUsePaths = s->probeEscape > kOpenFrame ? 1 : 0;
+        s->probePending = false;
+    };
+    if (s->probePending && cudaEventQuery(s->probeDone) == cudaSuccess) consume();
+    if (!s->probePending && (s->probeUsePaths < 0 || s->probeW != width || s->probeH != height || memcmp(&s->probeCam, camera, sizeof(tmpt_camera)) != 0)) {
+        CU_TRY(cudaMemsetAsync(s->d_probe, 0, 4 * sizeof(unsigned int), st));
+        LAUNCH(k_probe_paths, 32, 128, 0, st, s->view, cam, width, height, s->d_probe);
+        CU_TRY(cudaMemcpyAsync(s->h_probe, s->d_probe, 4 * sizeof(unsigned int), cudaMemcpyDeviceToHost, st));
+        CU_TRY(cudaEventRecord(s->probeDone, st));
+        s->probeCam = *camera; s->probeW = width; s->probeH = height;
+        s->probePending = true;
+        if (s->probeUsePaths < 0) { CU_TRY(cudaEventSynchronize(s->probeDone)); consume(); }
+    }
+    *usePaths = s->probeUsePaths == 1;
+    return TMPT_OK;
+}
+
+extern "C" int tmpt_render_kernel_choice(const tmpt_scene* s, int* kernel, float* escapeFraction) {
+    if (!s) return tmpt::fail(TMPT_ERR_ARG, "tmpt_render_kernel_choice: NULL scene");
+    if (kernel) *kernel = s->lastUsedPaths;
+    if (escapeFraction) *escapeFraction = s->probeEscape;
+    return TMPT_OK;
+}
+
 static int launch_render(const tmpt_scene* cs, const tmpt_camera* camera, int width, int height, int spp, int stripeRows, int rank, int world,
                          uint8_t* outStripes, uint8_t* frame, unsigned long long* rayCountDev, cudaStream_t st,
                          unsigned long long* statsDev = nullptr, const ProgressivePass* prog = nullptr) {
@@ -1465,6 +1659,17 @@ static int launch_render(const tmpt_scene* cs, const tmpt_camera* camera, int wi
             0.5f * s->view.farLimit;
     if (farCamera && smemPerThread * 256 > 48 * 1024)
         CU_TRY(cudaFuncSetAttribute(k_render<false, 256, 4, kSStack, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smemPerThread * 256)));
+    bool usePaths = false;  // (the instrumented pass and far cameras stay with k_render)
+    if (!statsDev && !farCamera && rk == 0 && cfgEnv == 0) {
+        const int rc = choose_render_kernel(s, camera, p.cam, width, height, st, &usePaths);
+        if (rc != TMPT_OK) return rc;
+    }
+    if (!statsDev) s->lastUsedPaths = usePaths ? 1 : 0;
+    int perSMp256 = 0, perSMp1024 = 0;
+    if (usePaths) {
+        CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSMp256, k_render_paths<256, 4, 8>, 256, 0));
+        CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSMp1024, k_render_paths<1024, 1, 8>, 1024, 0));
+    }
 #if TMPT_TUNE_CFG
     if (cfgEnv >= 4 && cfgEnv <= 8) {  // tuning only (-DTMPT_TUNE_CFG=1): other resident-warp / register-budget points
         for (p.bandRow0 = 0; p.bandRow0 < p.ownedRows; p.bandRow0 += bandRows) {
@@ -1510,10 +1715,25 @@ static int launch_render(const tmpt_scene* cs, const tmpt_camera* camera, int wi
             } else
             REGEN_CASE(1, 8, 4) REGEN_CASE(2, 4, 2) REGEN_CASE(3, 12, 6) REGEN_CASE(4, 16, 4)
 #undef REGEN_CASE
+#define PATHS_CASE(V, T, MB, GT)                                                                                       \
+            if (rk == V) {                                                                                           \
+                CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSMr, k_render_paths<T, MB, GT>, T, 0));     \
+                const int gridR = (int)std::min<long long>((long long)s->smCount * std::max(perSMr, 1), (items * 32 + T - 1) / T); \
+                LAUNCH((k_render_paths<T, MB, GT>), gridR, T, 0, st, p);                                              \
+            } else
+            PATHS_CASE(5, 256, 4, 1) PATHS_CASE(6, 256, 4, 8) PATHS_CASE(7, 256, 4, 16) PATHS_CASE(8, 1024, 1, 8) PATHS_CASE(9, 1024, 1, 16)
+#undef PATHS_CASE
             return tmpt::fail(TMPT_ERR_ARG, "TMPT_RENDER_KERNEL=%d: no such render kernel", rk);
         } else
 #endif
-        if (farCamera && !statsDev) LAUNCH((k_render<false, 256, 4, kSStack, true>), grid, 256, smemPerThread * 256, st, p);
+        if (usePaths) {  // one (pixel, chunk) item per lane, fetched from laneCounter
+            CU_TRY(cudaMemsetAsync(s->d_fetchCounter, 0, sizeof(unsigned long long), st));
+            const bool big = items >= (long long)s->smCount * 32 * 8 && perSMp1024 > 0;
+            const int t = big ? 1024 : 256;
+            const int gridP = (int)std::min<long long>((long long)s->smCount * std::max(big ? perSMp1024 : perSMp256, 1), (items * 32 + t - 1) / t);
+            if (big) LAUNCH((k_render_paths<1024, 1, 8>), gridP, 1024, 0, st, p);
+            else LAUNCH((k_render_paths<256, 4, 8>), gridP, 256, 0, st, p);
+        } else if (farCamera && !statsDev) LAUNCH((k_render<false, 256, 4, kSStack, true>), grid, 256, smemPerThread * 256, st, p);
         else if (statsDev) LAUNCH((k_render<true, 256, 4, kSStack>), grid, 256, smemPerThread * 256, st, p);
         else if (cfg == 3) LAUNCH((k_render<false, 1024, 1, kSStack>), grid, 1024, smemPerThread * 1024, st, p);
         else if (cfg == 2) LAUNCH((k_render<false, 512, 2, kSStack>), grid, 512, smemPerThread * 512, st, p);
