@@ -475,6 +475,24 @@ TMPT_HD uint32_t qnode_step(const SceneView& sc, uint32_t node, const RayCtx& r,
     const uint32_t nzw = r.sz ? qb.y : qb.x, fzw = r.sz ? qb.x : qb.y;
     const uint32_t one = qb.z;  // 0x3F800000, stored in the node so that it arrives in a register (see qbyte_f)
     float a[4], b[4];
+#if defined(__CUDA_ARCH__) && TMPT_FMA2
+    {  // the 24 plane distances as 12 FFMA2, like wide_node_step
+        float tn[3][4], tf[3][4];
+#define TMPT_QPAIR(T, W, A, C)                                                           \
+        fma2_bcast(qbyte_f<0>(W, one), qbyte_f<1>(W, one), A, C, T[0], T[1]);            \
+        fma2_bcast(qbyte_f<2>(W, one), qbyte_f<3>(W, one), A, C, T[2], T[3]);
+        TMPT_QPAIR(tn[0], nxw, ax, cx) TMPT_QPAIR(tn[1], nyw, ay, cy) TMPT_QPAIR(tn[2], nzw, az, cz)
+        TMPT_QPAIR(tf[0], fxw, ax, cx) TMPT_QPAIR(tf[1], fyw, ay, cy) TMPT_QPAIR(tf[2], fzw, az, cz)
+#undef TMPT_QPAIR
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            a[k] = fmaxf(fmaxf(tn[0][k], tn[1][k]), fmaxf(tn[2][k], tMin));
+            b[k] = fminf(fminf(tf[0][k], tf[1][k]), fminf(tf[2][k], bestT));
+        }
+    }
+    const uint32_t ref2[4] = {rf.x, rf.y, rf.z, rf.w};
+    if (true) return enter_and_push(a, b, ref2, stack, sp, anyRay);
+#endif
     qchild<0>(one, nxw, nyw, nzw, fxw, fyw, fzw, ax, ay, az, cx, cy, cz, tMin, bestT, a[0], b[0]);
     qchild<1>(one, nxw, nyw, nzw, fxw, fyw, fzw, ax, ay, az, cx, cy, cz, tMin, bestT, a[1], b[1]);
     qchild<2>(one, nxw, nyw, nzw, fxw, fyw, fzw, ax, ay, az, cx, cy, cz, tMin, bestT, a[2], b[2]);
