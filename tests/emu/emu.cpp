@@ -290,6 +290,21 @@ void emu_ray_iters(void* h, const float* rays6, long n, float tMin, float tMax, 
     }
 }
 
+// node visits per node index (development: how much of the walk happens in the top of the tree, tools/exp_top_levels.py)
+void emu_node_visits(void* h, const float* rays6, long n, float tMin, float tMax, int anyHit, unsigned long long* visitsPerNode) {
+    EmuScene* s = (EmuScene*)h;
+    for (long i = 0; i < n; ++i) {
+        const float* r = rays6 + i * 6;
+        bvh::LocalStack stack;
+        bvh::WalkState w;
+        bvh::walk_start(w, s->view, ex::v3(r[0], r[1], r[2]), ex::v3(r[3], r[4], r[5]), tMax, anyHit != 0);
+        for (;;) {
+            if (w.cur != bvh::NONE && !bvh::ref_is_leaf(w.cur)) ++visitsPerNode[w.cur];
+            if (bvh::walk_step<false>(w, s->view, tMin, tMax, stack, nullptr)) break;
+        }
+    }
+}
+
 void emu_sincos(float a, float* s, float* c) { ex::sincos_spec(a, *s, *c); }
 int emu_sah_must_halve(int depth, int count) { return bld::sah_must_halve(depth, count) ? 1 : 0; }
 int emu_max_tree_depth() { return bvh::MAX_TREE_DEPTH; }
