@@ -673,6 +673,35 @@ def test_path_regeneration_kernel_is_bit_exact_and_chosen_for_open_frames(tmp_pa
     assert hall[0][1] == hall[1][1] == hall[2][1] and (hall[0][0] == hall[1][0]).all() and (hall[0][0] == hall[2][0]).all()
 
 
+def test_render_kernel_choice_follows_the_camera_and_never_changes_the_bytes():
+    """The probe behind the k_render / k_render_paths choice runs when camera or frame size change and is picked up one frame
+    later (no host stall): a scene object rendering a SEQUENCE of cameras -- inside the hall (closed), far outside it looking
+    at the building (open), other frame sizes -- produces, frame by frame, the bytes a fresh scene produces for that camera
+    alone, whichever kernel the history made it use; and the choice does follow the camera."""
+    if os.environ.get("TMPT_RENDER_PATHS") or os.environ.get("TMPT_RENDER_CFG"):
+        pytest.skip("render kernel forced by the environment")
+    tris, mn, mx = _sponza_tris()
+    w, h, spp = 192, 108, 4
+    inside = tm.camera_for_scene("x/sponza.obj", mn, mx, w, h)
+    c = 0.5 * (mn + mx)
+    size = float(np.max(mx - mn))
+    outside = tm.camera_make(c + np.array([1.5, 1.2, 1.1], np.float32) * size, c, [0, 1, 0], 40.0, w / h, 0.0, 2.5 * size)
+    seq = [(inside, w, h), (outside, w, h), (outside, w, h), (outside, 96, 54), (inside, w, h), (inside, w, h), (inside, 96, 54)]
+    kernels = []
+    with tm.Scene(tris) as s:
+        assert s.render_kernel_choice()[0] == -1
+        for cam, fw, fh in seq:
+            img, rays, _ = s.render(cam, fw, fh, spp)
+            kernels.append(s.render_kernel_choice())
+            with tm.Scene(tris) as fresh:
+                fimg, frays, _ = fresh.render(cam, fw, fh, spp)
+                first = fresh.render_kernel_choice()
+            assert rays == frays and (img == fimg).all()
+            assert first[0] == (0 if cam is inside else 1), first  # (a scene's first frame waits for its probe)
+    ks = [k for k, _ in kernels]
+    assert ks[0] == 0 and ks[2] == 1 and ks[5] == 0, kernels  # the second frame of an unchanged camera has the new decision (render() is synchronous)
+
+
 def test_regeneration_render_kernel_gives_the_same_bytes(tmp_path):
     """k_render_regen (per-lane ray regeneration; measured, not shipped: it lives in the -DTMPT_EXPERIMENTS=1 build only)
     schedules the same per-lane arithmetic differently: frame and ray count equal the lockstep kernel's, one-shot and over
