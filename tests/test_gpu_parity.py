@@ -202,7 +202,9 @@ def test_edge_cases():
                                           ("cube", 70, 41, 20), ("suzanne", 48, 28, 9),  # several chunks per pixel (chunk length = spp/32 clamped to 1..8)
                                           ("cube", 640, 360, 8),   # 57 600 warp items: launch_render picks the 1024-thread instantiation the bench times
                                           ("cube", 640, 360, 4),   # BASELINE config 1 at its full size
-                                          ("suzanne", 640, 360, 4)])  # BASELINE config 2 at its full size (the oracle scans 970 triangles per ray: ~10 s)
+                                          ("suzanne", 640, 360, 4),  # BASELINE config 2 at its full size (the oracle scans 970 triangles per ray: ~10 s)
+                                          ("triangle", 40, 24, 1024),  # the reference's largest spp (main.cpp:275): 128 chunks of 8 samples per pixel
+                                          ("cube", 1, 1, 1), ("cube", 7, 3, 33)])  # the smallest frame; a frame smaller than one tile, ragged last chunk
 def test_frame_bit_exact_vs_oracle_pixel_mode(scenes, oracle, name, w, h, spp):
     sc = load_scene(name)
     cam = tm.camera_for_scene(f"{name}.obj", sc["bounds_min"], sc["bounds_max"], w, h)
@@ -211,6 +213,23 @@ def test_frame_bit_exact_vs_oracle_pixel_mode(scenes, oracle, name, w, h, spp):
     assert rays == orays
     assert (img == oimg).all()
     assert sec > 0
+
+
+def test_largest_frame_10000x10000_rows_bit_exact_vs_oracle(scenes, oracle):
+    """The reference's largest frame (main.cpp:263-270: width, height <= 10000) at 64 spp: 1e8 pixels, 32 chunk sums each, so the
+    frame is rendered in 12 bands of 838 rows (4 GB accumulation budget), 1.7e10 rays (the 64-bit counter).  Rows at the frame's
+    edges, in the middle and either side of a band boundary equal the oracle's rows bit for bit; two renders agree."""
+    name, w, h, spp = "cube", 10000, 10000, 64
+    sc = load_scene(name)
+    cam = tm.camera_for_scene(f"{name}.obj", sc["bounds_min"], sc["bounds_max"], w, h)
+    img, rays, sec = scenes(name).render(cam, w, h, spp)
+    assert rays > 2 ** 32 and img.shape == (h, w, 4)
+    print(f"10000x10000x64: {rays} rays in {sec:.2f} s = {rays / sec / 1e6:.0f} Mrays/s")
+    for row in (0, 837, 838, 5001, 9999):
+        oimg, _ = oracle.render(sc["tris"], cam, w, h, spp, rows=(row, row + 1))
+        assert (img[row] == oimg[row]).all(), row
+    img2, rays2, _ = scenes(name).render(cam, w, h, spp)
+    assert rays2 == rays and (img2 == img).all()
 
 
 def test_far_camera_frame_bit_exact_vs_oracle(scenes, oracle):
