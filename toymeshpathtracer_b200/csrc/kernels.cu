@@ -880,8 +880,11 @@ __global__ void __launch_bounds__(THREADS, MINB) k_render_paths(const RenderPara
     float kk[integ::kMaxDepth];
     unsigned long long rays = 0;
     bool havePath = false, done = false, exhausted = false;
-    uint32_t rng = 0;
-    int depth = 0, s = 0, sEnd = 0, x = 0, y = 0, xl = 0, rb = 0, chunk = 0;
+    // a lane's item, packed (the kernel lives at 64 registers): pixel x | y << 16 (both < 10000), packed position xl | rb << 16,
+    // chunk << 8 | samples left in the chunk (<= integ::kMaxChunkSamples); hasItem = the lane owes a store when `left` reaches 0
+    uint32_t rng = 0, pix = 0, loc = 0, cl = 0;
+    bool hasItem = false;
+    int depth = 0;
     ex::V3 sum = ex::v3(0.0f, 0.0f, 0.0f), o = sum, d = sum;
     const float invW = ex::divf(1.0f, (float)p.width), invH = ex::divf(1.0f, (float)p.height);
     const unsigned long long totalItems = (unsigned long long)p.numTiles * (unsigned long long)p.chunks * 32ull;
@@ -891,18 +894,18 @@ __global__ void __launch_bounds__(THREADS, MINB) k_render_paths(const RenderPara
         const unsigned tracing = __ballot_sync(FULL, havePath);
         if (need && (__popc(need) >= GATE || tracing == 0)) {
             // (a) items that are finished: store the chunk sum, ask for a new item
-            const bool finished = !havePath && !done && s == sEnd;
-            if (finished && sEnd > 0) {  // (sEnd == 0: the lane has not had an item yet)
+            bool wantItem = !havePath && !done && (cl & 0xFFu) == 0u;
+            if (wantItem && hasItem) {
+                const int xl = (int)(loc & 0xFFFFu), rb = (int)(loc >> 16);
                 if (p.useAccum) {
-                    __stcs(&p.accum[((size_t)chunk * p.bandRows + rb) * p.localWidth + xl], make_float4(sum.x, sum.y, sum.z, 0.0f));
+                    __stcs(&p.accum[((size_t)(cl >> 8) * p.bandRows + rb) * p.localWidth + xl], make_float4(sum.x, sum.y, sum.z, 0.0f));
                 } else {
                     const uchar4 px = integ::resolve_pixel(sum, ex::divf(1.0f, (float)p.spp));
-                    if (p.frame) p.frame[(size_t)y * p.width + x] = px;
+                    if (p.frame) p.frame[(size_t)(pix >> 16) * p.width + (pix & 0xFFFFu)] = px;
                     else p.outStripes[(size_t)(p.bandRow0 + rb) * p.localWidth + xl] = px;
                 }
-                s = 0; sEnd = 0;  // (no item: s == sEnd makes the lane ask for one below)
+                hasItem = false;
             }
-            bool wantItem = !havePath && !done && s == sEnd;
             while (__any_sync(FULL, wantItem)) {  // (a lane whose item fell outside the frame asks again)
                 const unsigned want = __ballot_sync(FULL, wantItem);
                 if (exhausted) { if (wantItem) { done = true; wantItem = false; } break; }
@@ -916,25 +919,30 @@ __global__ void __launch_bounds__(THREADS, MINB) k_render_paths(const RenderPara
                     if (item >= totalItems) { done = true; wantItem = false; }
                     else {
                         const uint32_t wi = (uint32_t)(item >> 5), li = (uint32_t)item & 31u;
-                        chunk = (int)(wi / (uint32_t)p.numTiles);
+                        const int chunk = (int)(wi / (uint32_t)p.numTiles);
                         const uint32_t tile = wi - (uint32_t)chunk * (uint32_t)p.numTiles;
                         const int tx = (int)(tile % (uint32_t)p.tilesX), ty = (int)(tile / (uint32_t)p.tilesX);
-                        xl = tx * 8 + (int)(li & 7u); rb = ty * 4 + (int)(li >> 3);
+                        const int xl = tx * 8 + (int)(li & 7u), rb = ty * 4 + (int)(li >> 3);
                         const int r = p.bandRow0 + rb;
+                        int x, y;
                         if (xl < p.localWidth && r < p.ownedRows && local_to_global(xl, r, p.stripeRows, p.rank, p.world, p.width, x, y)) {
                             const int gchunk = p.chunk0 + chunk;
                             rng = ex::chunk_seed((uint32_t)gchunk, (uint32_t)y * (uint32_t)p.width + (uint32_t)x, (uint32_t)p.width * (uint32_t)p.height);
-                            s = gchunk * p.chunkLen;
-                            sEnd = s + p.chunkLen < p.spp ? s + p.chunkLen : p.spp;
+                            const int s0 = gchunk * p.chunkLen;
+                            const int left = (s0 + p.chunkLen < p.spp ? s0 + p.chunkLen : p.spp) - s0;
+                            pix = (uint32_t)x | ((uint32_t)y << 16);
+                            loc = (uint32_t)xl | ((uint32_t)rb << 16);
+                            cl = ((uint32_t)chunk << 8) | (uint32_t)left;
                             sum = ex::v3(0.0f, 0.0f, 0.0f);
+                            hasItem = true;
                             wantItem = false;
                         }
                     }
                 }
             }
             // (b) the next camera ray of every lane that has an item and no path
-            if (!havePath && !done && s < sEnd) {
-                integ::primary_ray(p.cam, x, y, invW, invH, rng, o, d);
+            if (!havePath && !done && (cl & 0xFFu) != 0u) {
+                integ::primary_ray(p.cam, (int)(pix & 0xFFFFu), (int)(pix >> 16), invW, invH, rng, o, d);
                 depth = 0;
                 havePath = true;
             }
@@ -972,7 +980,7 @@ __global__ void __launch_bounds__(THREADS, MINB) k_render_paths(const RenderPara
             if (ended) {
                 for (int i = depth - 1; i >= 0; --i) color = integ::unwind_step(kk[i], color);
                 sum = ex::add(sum, color);
-                ++s;
+                --cl;  // one sample less to go (low byte)
                 havePath = false;
             }
         }
