@@ -342,7 +342,7 @@ def bench_reference(args, scene, w, h, spp, rank, world):
         "e2e": {"value": value, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    _emit(line)
     return 0
 
 
@@ -545,7 +545,7 @@ def bench_b200(args, scene, w, h, spp, rank, world, local_rank):
             "clocks": clk, "roofline": roofline, "cpu_baseline": cpu,
             "configs": extra_configs, "hit_scene": hit_scene,
         }
-        print(json.dumps(line), flush=True)
+        _emit(line)
     sc.close()
     if world > 1:
         dist.barrier()
@@ -575,9 +575,35 @@ def main():
                "--master-port", str(port), os.path.abspath(__file__)] + sys.argv[1:]
         return subprocess.call(cmd)
     scene, w, h, spp = WORKLOADS[args.workload]
-    if args.impl == "reference":
-        return bench_reference(args, scene, w, h, spp, rank, world)
-    return bench_b200(args, scene, w, h, spp, rank, world, local_rank)
+    # stdout carries ONE line, the JSON: whatever libraries print while the bench runs (NCCL's version banner, for one) goes to
+    # stderr -- file descriptor 1 points at stderr until the line is printed
+    global _STDOUT_FD
+    sys.stdout.flush()
+    _STDOUT_FD = os.dup(1)
+    os.dup2(2, 1)
+    try:
+        if args.impl == "reference":
+            return bench_reference(args, scene, w, h, spp, rank, world)
+        return bench_b200(args, scene, w, h, spp, rank, world, local_rank)
+    finally:
+        _restore_stdout()
+
+
+_STDOUT_FD = None
+
+
+def _restore_stdout():
+    global _STDOUT_FD
+    if _STDOUT_FD is not None:
+        sys.stdout.flush()
+        os.dup2(_STDOUT_FD, 1)
+        os.close(_STDOUT_FD)
+        _STDOUT_FD = None
+
+
+def _emit(line):
+    _restore_stdout()
+    print(json.dumps(line), flush=True)
 
 
 if __name__ == "__main__":
