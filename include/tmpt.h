@@ -59,6 +59,10 @@ typedef enum tmpt_mem { TMPT_HOST = 0, TMPT_DEVICE = 1 } tmpt_mem;
 #define TMPT_HIT_BRUTE 2   /* nearest hit by scanning every triangle on the GPU (upstream's
                               HitScene); used to cross-check the BVH at sizes the CPU oracle
                               cannot reach                                                  */
+#define TMPT_HIT_SUN 3     /* the integrator's own shadow query (main.cpp:59): any hit along
+                              the SUN direction (main.cpp:36) from each ray's origin, through
+                              the scene's sun grid; the rays' directions are not read.  outID
+                              is 1 / -1.  Equals TMPT_HIT_ANY with direction = the sun's.   */
 
 typedef struct tmpt_scene_info {
     int32_t abi_version;

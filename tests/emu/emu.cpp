@@ -29,7 +29,45 @@ struct EmuScene {
     float sah[2] = {0, 0};
     bvh::SceneView view;
     int n = 0;
+    std::vector<uint32_t> sunStart;
+    std::vector<uint2> sunEntries;
 };
+
+// kernels.cu: build_sun_grid, serially (count, prefix, fill, sort) with the same per-(triangle, cell) functions
+void build_sun_grid(EmuScene* s, int cellsForced) {
+    s->view.sun = sun::View{};
+    if (s->n == 0 || cellsForced == 0) return;
+    sun::View g;
+    if (!sun::setup_view(s->tris9.data(), s->n, ex::normalize(ex::v3(-0.7f, 1.0f, 0.5f)), g)) return;
+    sun::set_resolution(g, cellsForced > 0 ? cellsForced : sun::default_cells_per_side(s->n));
+    const size_t nCells = (size_t)g.n * g.n;
+    s->sunStart.assign(nCells + 1, 0u);
+    for (int pass = 0; pass < 2; ++pass) {
+        std::vector<uint32_t> cursor(nCells, 0u);
+        for (int slot = 0; slot < s->n; ++slot) {
+            const int id = (int)ex::f2u(s->tris[(size_t)slot * 3].w);
+            const sun::Tri2 t = sun::project_tri(g, s->tris9.data() + (size_t)id * 9);
+            int x0, x1, y0, y1;
+            sun::cell_range(g, t, x0, x1, y0, y1);
+            for (int cy = y0; cy <= y1; ++cy)
+                for (int cx = x0; cx <= x1; ++cx) {
+                    if (!sun::touches_cell(g, t, cx, cy)) continue;
+                    const size_t c = (size_t)cy * g.n + cx;
+                    if (pass == 0) ++s->sunStart[c + 1];
+                    else s->sunEntries[s->sunStart[c] + cursor[c]++] = make_uint2((uint32_t)slot, ex::f2u(sun::far_depth(g, t, cx, cy)));
+                }
+        }
+        if (pass == 0) {
+            for (size_t c = 0; c < nCells; ++c) s->sunStart[c + 1] += s->sunStart[c];
+            s->sunEntries.assign(std::max<size_t>(s->sunStart[nCells], 1), make_uint2(0, 0));
+        }
+    }
+    for (size_t c = 0; c < nCells; ++c)
+        std::sort(s->sunEntries.begin() + s->sunStart[c], s->sunEntries.begin() + s->sunStart[c + 1], sun::entry_before);
+    g.cellStart = s->sunStart.data();
+    g.entries = s->sunEntries.data();
+    s->view.sun = g;
+}
 }  // namespace
 
 extern "C" {
@@ -172,6 +210,7 @@ void* emu_scene_create2(const float* tris9, int n, int builder, float cInner, fl
     s->qnodes.assign((size_t)s->counters[0] * bvh::QNODE_STRIDE, make_uint4(0, 0, 0, 0));
     for (uint32_t i = 0; i < s->counters[0]; ++i) bld::quantize_node(s->nodes.data(), s->qnodes.data(), i);
     s->view.qnodes = s->qnodes.data();
+    build_sun_grid(s, -1);
     return s;
 }
 void* emu_scene_create(const float* tris9, int n) { return emu_scene_create2(tris9, n, 1, 1.0f, 1.0f, bvh::MAX_LEAF_TRIS); }
@@ -204,6 +243,7 @@ void emu_scene_refit(void* h, const float* tris9) {
         bld::refit_wide_node(s->nodes.data(), s->tris.data(), s->tris9.data(), i, maxAbs,
                              [nodes](uint32_t n, int row) { return nodes[(size_t)n * bvh::NODE_F4 + row]; });
     for (uint32_t i = 0; i < s->counters[0]; ++i) bld::quantize_node(s->nodes.data(), s->qnodes.data(), i);
+    build_sun_grid(s, s->view.sun.n > 0 ? s->view.sun.n : -1);
 }
 // the quantised nodes, in LOGICAL row order (the bank skew undone): 16 uint32 per node
 void emu_qnodes(void* h, uint32_t* out) {
@@ -303,6 +343,25 @@ void emu_node_visits(void* h, const float* rays6, long n, float tMin, float tMax
             if (bvh::walk_step<false>(w, s->view, tMin, tMax, stack, nullptr)) break;
         }
     }
+}
+
+// the sun grid: rebuild with n cells per side (0 = none: shadow rays walk the tree, -1 = default), counts, and the query itself
+void emu_sun_grid(void* h, int cells) { build_sun_grid((EmuScene*)h, cells); }
+void emu_sun_info(void* h, long long out[3]) {
+    EmuScene* s = (EmuScene*)h;
+    out[0] = s->view.sun.n;
+    out[1] = s->view.sun.n ? (long long)s->sunStart[(size_t)s->view.sun.n * s->view.sun.n] : 0;
+    long long longest = 0;
+    if (s->view.sun.n) for (size_t c = 0; c < (size_t)s->view.sun.n * s->view.sun.n; ++c) longest = std::max<long long>(longest, s->sunStart[c + 1] - s->sunStart[c]);
+    out[2] = longest;
+}
+void emu_sun_occluded(void* h, const float* origins3, long n, float tMin, float tMax, int* out, unsigned long long* triTests) {
+    EmuScene* s = (EmuScene*)h;
+    const ex::V3 l = ex::v3(s->view.sun.lx, s->view.sun.ly, s->view.sun.lz);
+    bvh::TravStats ts;
+    for (long i = 0; i < n; ++i)
+        out[i] = bvh::sun_occluded<true>(s->view, ex::v3(origins3[3 * i], origins3[3 * i + 1], origins3[3 * i + 2]), l, tMin, tMax, &ts) ? 1 : -1;
+    if (triTests) *triTests = ts.tris;
 }
 
 void emu_sincos(float a, float* s, float* c) { ex::sincos_spec(a, *s, *c); }

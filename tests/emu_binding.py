@@ -97,6 +97,21 @@ class EmuScene:
         self.L.emu_hit_scene(self.h, _p(rays), C.c_long(n), C.c_float(tmin), C.c_float(tmax), mode, _p(ids), _p(t), _p(pos), _p(nrm))
         return ids, t, pos, nrm
 
+    def sun_grid(self, cells=-1):
+        """Rebuild the shadow rays' grid (csrc/sungrid.cuh) with `cells` per side (-1: default, 0: none) -> info dict."""
+        self.L.emu_sun_grid(self.h, int(cells))
+        out = np.zeros(3, np.int64)
+        self.L.emu_sun_info(self.h, _p(out))
+        return {"n": int(out[0]), "entries": int(out[1]), "longest": int(out[2])}
+
+    def sun_occluded(self, origins, tmin=0.001, tmax=1.0e7):
+        """The integrator's shadow query through the grid: (1 / -1 per origin, exact triangle tests run)."""
+        o = np.ascontiguousarray(origins, np.float32).reshape(-1, 3)
+        out = np.zeros(o.shape[0], np.int32)
+        tests = C.c_ulonglong(0)
+        self.L.emu_sun_occluded(self.h, _p(o), C.c_long(o.shape[0]), C.c_float(tmin), C.c_float(tmax), _p(out), C.byref(tests))
+        return out, tests.value
+
     def render_stats(self, cam22, w, h, spp):
         cam22 = np.ascontiguousarray(cam22, np.float32)
         out = np.zeros(3, np.uint64)

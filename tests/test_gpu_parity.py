@@ -232,6 +232,39 @@ def test_largest_frame_10000x10000_rows_bit_exact_vs_oracle(scenes, oracle):
     assert rays2 == rays and (img2 == img).all()
 
 
+@pytest.mark.parametrize("name", SCENES + ["sponza"])
+def test_sun_grid_shadow_query_equals_tree_scan_and_reference(scenes, name):
+    """TMPT_HIT_SUN -- the integrator's shadow query through the grid in the sun's projection (csrc/sungrid.cuh) -- against the
+    reference's own hit flags on every shadow ray of a reference render, and against the tree's any-hit and the all-triangle scan
+    on 1.2 M origins: random points in and around the scene, points on triangles (crowded towards edges and vertices), a hair
+    below and above them, vertices, edge midpoints."""
+    g = load_rays(name)
+    sh = g["kind"] == 2
+    rays = np.ascontiguousarray(g["rays"][sh], np.float32)
+    l = rays[0, 3:6].copy()
+    s = scenes(name)
+    got = s.HitScene(rays, mode=tm.HIT_SUN)[0]
+    assert ((got >= 0) == (g["id"][sh] >= 0)).all()
+    tris = sponza_scene()[0] if name == "sponza" else load_scene(name)["tris"]
+    v = tris.reshape(-1, 3, 3)
+    mn, mx = v.reshape(-1, 3).min(0), v.reshape(-1, 3).max(0)
+    rng = np.random.default_rng(17)
+    n = 200000
+    pick = rng.integers(0, len(v), n)
+    bary = rng.dirichlet([0.3, 0.3, 0.3], n).astype(np.float32)
+    on = (v[pick] * bary[:, :, None]).sum(1).astype(np.float32)
+    o = np.concatenate([rng.uniform(mn - 0.5, mx + 0.5, (n, 3)).astype(np.float32), on, on - l * np.float32(2e-3), on + l * np.float32(1e-4),
+                        v[pick, 0], ((v[pick, 0] + v[pick, 1]) * np.float32(0.5))]).astype(np.float32)
+    q = np.concatenate([o, np.broadcast_to(l, o.shape)], 1).astype(np.float32)
+    for tmin, tmax in ((tm.K_MIN_T, tm.K_MAX_T), (0.0, 2.5)):
+        a = s.HitScene(q, tMin=tmin, tMax=tmax, mode=tm.HIT_SUN)[0] >= 0
+        b = s.HitScene(q, tMin=tmin, tMax=tmax, mode=tm.HIT_ANY)[0] >= 0
+        assert (a == b).all(), (name, tmin, int((a != b).sum()))
+    sub = q[:: 7 if name == "sponza" else 1][:300000]
+    assert ((s.HitScene(sub, mode=tm.HIT_SUN)[0] >= 0) == (s.HitScene(sub, mode=tm.HIT_BRUTE)[0] >= 0)).all()
+    assert 0.02 < a.mean() < 0.98
+
+
 def test_far_camera_frame_bit_exact_vs_oracle(scenes, oracle):
     """A camera 40 scene sizes away: its origin is beyond the far limit of the padded boxes (bvh.cuh: ray_is_far), so
     launch_render picks the render instantiation that answers such rays with the exact scan.  Still the oracle's bytes."""

@@ -27,7 +27,7 @@ CLI_PATH = os.path.join(HERE, "bin", "TrimeshTracer")
 
 TMPT_OK, TMPT_ERR_ARG, TMPT_ERR_CUDA, TMPT_ERR_IO, TMPT_ERR_OOM = 0, -1, -2, -3, -4
 HOST, DEVICE = 0, 1
-HIT_CLOSEST, HIT_ANY, HIT_BRUTE = 0, 1, 2
+HIT_CLOSEST, HIT_ANY, HIT_BRUTE, HIT_SUN = 0, 1, 2, 3
 BUILD_DEFAULT, BUILD_LBVH = 0, 1
 K_MIN_T, K_MAX_T = 0.001, 1.0e7  # main.cpp:30-31
 
@@ -253,7 +253,7 @@ class Scene:
         rays = _f32(rays).reshape(-1, 6)
         n = rays.shape[0]
         ids = np.full(n, -1, np.int32)
-        want = payload and mode != HIT_ANY
+        want = payload and mode not in (HIT_ANY, HIT_SUN)
         t = np.zeros(n, np.float32) if want else None
         pos = np.zeros((n, 3), np.float32) if want else None
         nrm = np.zeros((n, 3), np.float32) if want else None

@@ -30,6 +30,7 @@
 // float slab test below can never cull a triangle the exact test would accept.
 #pragma once
 #include "exact.cuh"
+#include "sungrid.cuh"
 
 
 #ifdef __CUDA_ARCH__
@@ -68,6 +69,7 @@ struct SceneView {
     uint32_t* status;     // device status word (STACK_OVERFLOW)
     const uint4* qnodes;  // QNODE_ROWS rows per node: the quantised form of `nodes` (only in a -DTMPT_QNODES=1 build)
     float farLimit;       // rays whose origin has a component beyond this are answered by the all-triangle scan (ray_is_far); <= 0: no limit
+    sun::View sun;        // the shadow rays' grid (sungrid.cuh); sun.n == 0: none, shadow rays walk the tree
 };
 
 struct HitRec {
@@ -555,6 +557,49 @@ TMPT_HD bool tri_step(const SceneView& sc, uint32_t slot, ex::V3 o, ex::V3 d, fl
         }
     }
     return false;
+}
+
+// Shadow query through the sun grid (sungrid.cuh): is the point p shadowed along the light direction l?  Walks the list of p's cell
+// from the sun side down to p's own depth, exact test on every entry.  The next entry is requested before the current one is tested.
+template <bool STATS>
+TMPT_HD bool sun_occluded(const SceneView& sc, ex::V3 p, ex::V3 l, float tMin, float tMax, TravStats* stats) {
+    const sun::View& g = sc.sun;
+    const float u = sun::proj_u(g, p), v = sun::proj_v(g, p), w = sun::proj_w(g, p);
+    if (!(u == u) || !(v == v) || !(w == w)) return false;  // NaN origin: a miss, as in the tree walk
+    const int cx = sun::cell_of(u, g.loU, g.invCell, g.n), cy = sun::cell_of(v, g.loV, g.invCell, g.n);
+    const uint32_t c = (uint32_t)cy * (uint32_t)g.n + (uint32_t)cx;
+#ifdef __CUDA_ARCH__
+    uint32_t e = __ldg(g.cellStart + c);
+    const uint32_t end = __ldg(g.cellStart + c + 1);
+#else
+    uint32_t e = g.cellStart[c];
+    const uint32_t end = g.cellStart[c + 1];
+#endif
+    if (e == end) return false;
+#ifdef __CUDA_ARCH__
+    uint2 cur = __ldg(g.entries + e);
+#else
+    uint2 cur = g.entries[e];
+#endif
+    for (;;) {
+        if (ex::u2f(cur.y) < w) return false;  // this and everything after it ends before the origin
+        ++e;
+        uint2 nxt = cur;
+        if (e < end) {
+#ifdef __CUDA_ARCH__
+            nxt = __ldg(g.entries + e);
+#else
+            nxt = g.entries[e];
+#endif
+        }
+        if (STATS) ++stats->tris;
+        const uint32_t row0 = cur.x * 3u;
+        const float4 a = ld_row_tri(sc.tris + row0), b = ld_row_tri(sc.tris + (row0 + 1u)), cc = ld_row_tri(sc.tris + (row0 + 2u));
+        float t, bu, bv;
+        if (mt_exact(p, l, ex::v3(a.x, a.y, a.z), ex::v3(b.x, b.y, b.z), ex::v3(cc.x, cc.y, cc.z), tMin, tMax, t, bu, bv)) return true;
+        if (e >= end) return false;
+        cur = nxt;
+    }
 }
 
 // Walk state of one ray in one lane.

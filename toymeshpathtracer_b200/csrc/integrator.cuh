@@ -94,8 +94,10 @@ TMPT_HD ex::V3 trace_path(Stack& stack, const Scene& sc, const Camera& cam, ex::
         ex::V3 pos, normal;
         bvh::hit_payload(sc, h.id, h.u, h.v, pos, normal);
         ++rays;
-        const bvh::HitRec sh = bvh::traverse_with<true, STATS, FAR>(stack, sc, pos, lightDir, kMinT, kMaxT, stats);
-        kk[depth] = sh.id < 0 ? sun_term(normal, d, lightDir) : 0.0f;
+        // the shadow ray (main.cpp:59): through the sun grid when the scene has one (sungrid.cuh), else through the tree
+        const bool shadowed = sc.sun.n > 0 ? bvh::sun_occluded<STATS>(sc, pos, lightDir, kMinT, kMaxT, stats)
+                                           : bvh::traverse_with<true, STATS, FAR>(stack, sc, pos, lightDir, kMinT, kMaxT, stats).id >= 0;
+        kk[depth] = shadowed ? 0.0f : sun_term(normal, d, lightDir);
         d = scatter_dir(pos, normal, rng);
         o = pos;
         ++depth;

@@ -112,6 +112,10 @@ struct tmpt_scene {
     char* h_stage = nullptr;
     size_t stageBytes = 0;
     std::mutex hostCallMutex;      // serialises the entry points that use per-scene scratch (staging, frame, accum, counters)
+    uint32_t *d_sunStart = nullptr, *d_sunCount = nullptr;  // sun grid (sungrid.cuh): cell offsets; counts / fill cursors + scan scratch
+    uint2* d_sunEntries = nullptr;
+    uint32_t sunEntriesCap = 0, sunEntries = 0;
+    uint64_t sunBytes = 0;
     // render-kernel choice (k_render vs k_render_paths), cached per camera / frame size: see k_probe_paths
     tmpt_camera probeCam{};
     int probeW = 0, probeH = 0, probeUsePaths = -1;  // -1: no decision yet
@@ -547,10 +551,13 @@ __global__ void __launch_bounds__(128) k_hit_scene(bvh::SceneView sc, const floa
         const ex::V3 o = ex::v3(r[0], r[1], r[2]), d = ex::v3(r[3], r[4], r[5]);
         bvh::HitRec h;
         if (MODE == TMPT_HIT_BRUTE) h = bvh::brute_force(sc, o, d, tMin, tMax);
-        else if (MODE == TMPT_HIT_ANY) h = bvh::traverse<true, STATS>(sc, o, d, tMin, tMax, &ts);
+        else if (MODE == TMPT_HIT_SUN) {  // the integrator's shadow query: the ray's own direction is NOT read, the sun's is used
+            h.id = bvh::sun_occluded<STATS>(sc, o, ex::v3(sc.sun.lx, sc.sun.ly, sc.sun.lz), tMin, tMax, &ts) ? 1 : -1;
+            h.t = 0.0f; h.u = 0.0f; h.v = 0.0f;
+        } else if (MODE == TMPT_HIT_ANY) h = bvh::traverse<true, STATS>(sc, o, d, tMin, tMax, &ts);
         else h = bvh::traverse<false, STATS>(sc, o, d, tMin, tMax, &ts);
         if (STATS) { ++nr; nh += h.id >= 0; }
-        if (MODE == TMPT_HIT_ANY) { outID[i] = h.id < 0 ? -1 : 1; continue; }
+        if (MODE == TMPT_HIT_ANY || MODE == TMPT_HIT_SUN) { outID[i] = h.id < 0 ? -1 : 1; continue; }
         outID[i] = h.id;
         if (h.id >= 0) {
             if (outT) outT[i] = h.t;
@@ -962,7 +969,8 @@ __global__ void __launch_bounds__(THREADS, MINB) k_render_paths(const RenderPara
         if (hit) {
             bvh::hit_payload(p.sc, h.id, h.u, h.v, pos, normal);
             ++rays;
-            shadowed = bvh::traverse_with<true, false, false>(stack, p.sc, pos, p.lightDir, integ::kMinT, integ::kMaxT).id >= 0;
+            shadowed = p.sc.sun.n > 0 ? bvh::sun_occluded<false>(p.sc, pos, p.lightDir, integ::kMinT, integ::kMaxT, nullptr)
+                                      : bvh::traverse_with<true, false, false>(stack, p.sc, pos, p.lightDir, integ::kMinT, integ::kMaxT).id >= 0;
         }
         if (havePath) {
             bool ended = false;
@@ -987,6 +995,117 @@ __global__ void __launch_bounds__(THREADS, MINB) k_render_paths(const RenderPara
     }
     for (int k = 16; k > 0; k >>= 1) rays += __shfl_xor_sync(FULL, rays, k);
     if (lane == 0 && rays) atomicAdd(p.rayCount, rays);
+}
+
+// ---- K7: the sun grid (sungrid.cuh), built on the device after the tree ---------------------------------------------------------
+// One WARP per triangle slot walks the cells of the triangle's padded bounding box (lanes stride over them) and, where the
+// projection touches the cell, counts (FILL = false) or writes (FILL = true) an entry.  A triangle whose box spans more than
+// kSunBigCells cells (the floor's two triangles cover every cell) is put on a list instead and binned by the whole grid of
+// k_sun_bin_big: one warp walking a million cells, an atomic's round trip per step, took 25 ms.
+constexpr long long kSunBigCells = 2048;
+__device__ __forceinline__ void sun_bin_cell(const sun::View& g, const sun::Tri2& t, int slot, int cx, int cy, bool fill, uint32_t* cellCount,
+                                             const uint32_t* cellStart, uint2* entries) {
+    if (!sun::touches_cell(g, t, cx, cy)) return;
+    const uint32_t c = (uint32_t)cy * (uint32_t)g.n + (uint32_t)cx;
+    const uint32_t k = atomicAdd(&cellCount[c], 1u);
+    if (fill) entries[cellStart[c] + k] = make_uint2((uint32_t)slot, ex::f2u(sun::far_depth(g, t, cx, cy)));
+}
+template <bool FILL>
+__global__ void __launch_bounds__(256) k_sun_bin(sun::View g, const float4* __restrict__ tris, const float* __restrict__ tris9, int nSlots,
+                                                 uint32_t* __restrict__ cellCount, const uint32_t* __restrict__ cellStart, uint2* __restrict__ entries,
+                                                 uint32_t* __restrict__ bigList, uint32_t* __restrict__ bigCount) {
+    const int slot = (int)(((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
+    if (slot >= nSlots) return;
+    const int id = (int)ex::f2u(__ldg(&tris[(size_t)slot * 3]).w);
+    const sun::Tri2 t = sun::project_tri(g, tris9 + (size_t)id * 9);
+    int x0, x1, y0, y1;
+    sun::cell_range(g, t, x0, x1, y0, y1);
+    const int wx = x1 - x0 + 1;
+    const long long cells = (long long)wx * (y1 - y0 + 1);
+    if (cells > kSunBigCells) {
+        if (!FILL && lane == 0) bigList[atomicAdd(bigCount, 1u)] = (uint32_t)slot;  // (the fill pass reads the list the count pass made)
+        return;
+    }
+    for (long long i = lane; i < cells; i += 32) sun_bin_cell(g, t, slot, x0 + (int)(i % wx), y0 + (int)(i / wx), FILL, cellCount, cellStart, entries);
+}
+template <bool FILL>
+__global__ void __launch_bounds__(256) k_sun_bin_big(sun::View g, const float4* __restrict__ tris, const float* __restrict__ tris9,
+                                                     uint32_t* __restrict__ cellCount, const uint32_t* __restrict__ cellStart, uint2* __restrict__ entries,
+                                                     const uint32_t* __restrict__ bigList, const uint32_t* __restrict__ bigCount) {
+    const uint32_t nBig = *bigCount;
+    const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x, stride = (long long)gridDim.x * blockDim.x;
+    for (uint32_t j = 0; j < nBig; ++j) {
+        const int slot = (int)bigList[j];
+        const int id = (int)ex::f2u(__ldg(&tris[(size_t)slot * 3]).w);
+        const sun::Tri2 t = sun::project_tri(g, tris9 + (size_t)id * 9);
+        int x0, x1, y0, y1;
+        sun::cell_range(g, t, x0, x1, y0, y1);
+        const int wx = x1 - x0 + 1;
+        const long long cells = (long long)wx * (y1 - y0 + 1);
+        for (long long i = tid; i < cells; i += stride) sun_bin_cell(g, t, slot, x0 + (int)(i % wx), y0 + (int)(i / wx), FILL, cellCount, cellStart, entries);
+    }
+}
+
+// exclusive scan of the cell counts, three small kernels: per-block totals, scan of the totals (one block), per-block scan + offset
+constexpr int kScanBlock = 1024;
+__global__ void __launch_bounds__(kScanBlock) k_scan_totals(const uint32_t* __restrict__ in, long long n, uint32_t* __restrict__ totals) {
+    __shared__ uint32_t sh[kScanBlock / 32];
+    const long long i = (long long)blockIdx.x * kScanBlock + threadIdx.x;
+    uint32_t v = i < n ? in[i] : 0u;
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        uint32_t w = sh[threadIdx.x];
+        for (int o = 16; o > 0; o >>= 1) w += __shfl_xor_sync(0xffffffffu, w, o);
+        if (threadIdx.x == 0) totals[blockIdx.x] = w;
+    }
+}
+__global__ void __launch_bounds__(kScanBlock) k_scan_of_totals(uint32_t* __restrict__ totals, int nBlocks, uint32_t* __restrict__ grandTotal) {
+    // one block; every thread owns a contiguous run of the totals
+    __shared__ uint32_t sh[kScanBlock];
+    const int per = (nBlocks + kScanBlock - 1) / kScanBlock, b0 = threadIdx.x * per, b1 = min(nBlocks, b0 + per);
+    uint32_t sum = 0;
+    for (int b = b0; b < b1; ++b) sum += totals[b];
+    sh[threadIdx.x] = sum;
+    __syncthreads();
+    for (int o = 1; o < kScanBlock; o <<= 1) {  // Hillis-Steele inclusive scan
+        const uint32_t add = threadIdx.x >= o ? sh[threadIdx.x - o] : 0u;
+        __syncthreads();
+        sh[threadIdx.x] += add;
+        __syncthreads();
+    }
+    uint32_t run = sh[threadIdx.x] - sum;  // exclusive prefix of this thread's run
+    for (int b = b0; b < b1; ++b) { const uint32_t tot = totals[b]; totals[b] = run; run += tot; }
+    if (threadIdx.x == kScanBlock - 1) *grandTotal = sh[threadIdx.x];
+}
+__global__ void __launch_bounds__(kScanBlock) k_scan_apply(const uint32_t* __restrict__ in, long long n, const uint32_t* __restrict__ totals,
+                                                            const uint32_t* __restrict__ grandTotal, uint32_t* __restrict__ out) {
+    __shared__ uint32_t sh[kScanBlock];
+    const long long i = (long long)blockIdx.x * kScanBlock + threadIdx.x;
+    const uint32_t v = i < n ? in[i] : 0u;
+    sh[threadIdx.x] = v;
+    __syncthreads();
+    for (int o = 1; o < kScanBlock; o <<= 1) {
+        const uint32_t add = threadIdx.x >= o ? sh[threadIdx.x - o] : 0u;
+        __syncthreads();
+        sh[threadIdx.x] += add;
+        __syncthreads();
+    }
+    if (i < n) out[i] = totals[blockIdx.x] + sh[threadIdx.x] - v;
+    if (i == n - 1) out[n] = *grandTotal;
+}
+// every cell's list into its order (sun::entry_before): one thread per cell, insertion sort in place (lists are short)
+__global__ void __launch_bounds__(128) k_sun_sort(const uint32_t* __restrict__ cellStart, long long nCells, uint2* __restrict__ entries) {
+    const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= nCells) return;
+    const uint32_t b = cellStart[c], e = cellStart[c + 1];
+    for (uint32_t i = b + 1; i < e; ++i) {
+        const uint2 x = entries[i];
+        uint32_t j = i;
+        while (j > b && sun::entry_before(x, entries[j - 1])) { entries[j] = entries[j - 1]; --j; }
+        entries[j] = x;
+    }
 }
 
 // Which render kernel?  k_render_paths wins where paths leave the scene early (+13..25 % on cube / suzanne / teapot), k_render where
@@ -1287,6 +1406,63 @@ int build_bvh(tmpt_scene* s, unsigned flags) {
     return TMPT_OK;
 }
 
+// The sun grid of a scene (sungrid.cuh): basis and projected bounds on the host (doubles, from the caller's triangles), binning on the
+// device.  TMPT_SUN_GRID=0 turns it off (shadow rays walk the tree), =n forces n cells per side.  If the lists would need more
+// than kSunMaxEntries entries (a scene of huge overlapping triangles) the grid is halved, and dropped below 32 cells per side.
+constexpr unsigned long long kSunMaxEntries = 256ull << 20;
+static ex::V3 host_light_dir() { return ex::normalize(ex::v3(-0.7f, 1.0f, 0.5f)); }  // main.cpp:36
+static int build_sun_grid(tmpt_scene* s, const float* tris9, int n, cudaStream_t st) {
+    static const int forced = getenv("TMPT_SUN_GRID") ? atoi(getenv("TMPT_SUN_GRID")) : -1;
+    s->view.sun = sun::View{};
+    s->info.device_bytes -= s->sunBytes;
+    s->sunBytes = 0; s->sunEntries = 0;
+    if (forced == 0 || n <= 0) return TMPT_OK;
+    sun::View g;
+    if (!sun::setup_view(tris9, n, host_light_dir(), g)) return TMPT_OK;  // NaN / infinite vertices: no grid, the tree copes
+    int cells = forced > 0 ? std::min(std::max(forced, 1), 8192) : sun::default_cells_per_side(n);
+    for (;; cells /= 2) {
+        if (cells < (forced > 0 ? 1 : 32)) return TMPT_OK;  // (no grid)
+        sun::set_resolution(g, cells);
+        const long long nCells = (long long)cells * cells;
+        const int nBlocks = (int)((nCells + kScanBlock - 1) / kScanBlock);
+        cudaFree(s->d_sunStart); s->d_sunStart = nullptr;
+        cudaFree(s->d_sunCount); s->d_sunCount = nullptr;
+        CU_TRY(cudaMalloc((void**)&s->d_sunStart, (size_t)(nCells + 1) * sizeof(uint32_t)));
+        CU_TRY(cudaMalloc((void**)&s->d_sunCount, (size_t)(nCells + nBlocks + 2 + n) * sizeof(uint32_t)));
+        uint32_t* totals = s->d_sunCount + nCells;
+        uint32_t* grand = totals + nBlocks;
+        uint32_t* bigCount = grand + 1;
+        uint32_t* bigList = bigCount + 1;  // up to n slots
+        CU_TRY(cudaMemsetAsync(s->d_sunCount, 0, (size_t)(nCells + nBlocks + 2) * sizeof(uint32_t), st));
+        const int binGrid = (int)(((long long)n * 32 + 255) / 256), bigGrid = s->smCount * 8;
+        LAUNCH((k_sun_bin<false>), binGrid, 256, 0, st, g, s->d_tris, s->d_tris9, n, s->d_sunCount, nullptr, nullptr, bigList, bigCount);
+        LAUNCH((k_sun_bin_big<false>), bigGrid, 256, 0, st, g, s->d_tris, s->d_tris9, s->d_sunCount, nullptr, nullptr, bigList, bigCount);
+        LAUNCH(k_scan_totals, nBlocks, kScanBlock, 0, st, s->d_sunCount, nCells, totals);
+        LAUNCH(k_scan_of_totals, 1, kScanBlock, 0, st, totals, nBlocks, grand);
+        LAUNCH(k_scan_apply, nBlocks, kScanBlock, 0, st, s->d_sunCount, nCells, totals, grand, s->d_sunStart);
+        uint32_t total = 0;
+        CU_TRY(cudaMemcpyAsync(&total, grand, sizeof total, cudaMemcpyDeviceToHost, st));
+        CU_TRY(cudaStreamSynchronize(st));
+        if ((unsigned long long)total > kSunMaxEntries) continue;  // halve the grid
+        if (s->sunEntriesCap < total) {
+            cudaFree(s->d_sunEntries); s->d_sunEntries = nullptr; s->sunEntriesCap = 0;
+            CU_TRY(cudaMalloc((void**)&s->d_sunEntries, (size_t)std::max<uint32_t>(total, 1u) * sizeof(uint2)));
+            s->sunEntriesCap = std::max<uint32_t>(total, 1u);
+        }
+        CU_TRY(cudaMemsetAsync(s->d_sunCount, 0, (size_t)nCells * sizeof(uint32_t), st));
+        LAUNCH((k_sun_bin<true>), binGrid, 256, 0, st, g, s->d_tris, s->d_tris9, n, s->d_sunCount, s->d_sunStart, s->d_sunEntries, bigList, bigCount);
+        LAUNCH((k_sun_bin_big<true>), bigGrid, 256, 0, st, g, s->d_tris, s->d_tris9, s->d_sunCount, s->d_sunStart, s->d_sunEntries, bigList, bigCount);
+        LAUNCH(k_sun_sort, (int)((nCells + 127) / 128), 128, 0, st, s->d_sunStart, nCells, s->d_sunEntries);
+        g.cellStart = s->d_sunStart;
+        g.entries = s->d_sunEntries;
+        s->view.sun = g;
+        s->sunBytes = (uint64_t)(nCells + 1) * 4 + (uint64_t)total * 8;
+        s->info.device_bytes += s->sunBytes;
+        s->sunEntries = total;
+        return TMPT_OK;
+    }
+}
+
 struct DeviceGuard {
     int prev = -1;
     bool ok = false;
@@ -1345,6 +1521,8 @@ extern "C" int tmpt_scene_create(const float* tris9, int triCount, int device, u
                 brc = build_bvh(s, flags & ~(unsigned)TMPT_BUILD_LBVH);
             }
             if (brc != TMPT_OK) return brc == kTreeTooDeep ? TMPT_ERR_ARG : brc;
+            brc = build_sun_grid(s, tris9, triCount, s->stream);
+            if (brc != TMPT_OK) return brc;
         } else {
             s->view = bvh::SceneView{nullptr, nullptr, nullptr, nullptr, bvh::NONE, 0, s->d_status, nullptr, 0.0f};
         }
@@ -1386,6 +1564,10 @@ extern "C" int tmpt_scene_refit(tmpt_scene* s, const float* tris9, int triCount,
 #endif
     uint32_t hb[6];
     CU_TRY(cudaMemcpyAsync(hb, s->d_bounds, sizeof hb, cudaMemcpyDeviceToHost, st));
+    {  // the shadow rays' grid is rebuilt for the new positions (inside the timed window)
+        const int grc = build_sun_grid(s, tris9, n, st);
+        if (grc != TMPT_OK) return grc;
+    }
     CU_TRY(cudaEventRecord(s->ev1, st));
     CU_TRY(cudaStreamSynchronize(st));
     CU_TRY(cudaGetLastError());
@@ -1409,6 +1591,7 @@ extern "C" void tmpt_scene_destroy(tmpt_scene* s) {
     cudaFree(s->d_tileCounter); cudaFree(s->d_rayCount); cudaFree(s->d_fetchCounter); cudaFree(s->d_frame); cudaFree(s->d_accum); cudaFree(s->d_sum);
     cudaFree(s->d_stage);
     cudaFree(s->d_probe);
+    cudaFree(s->d_sunStart); cudaFree(s->d_sunCount); cudaFree(s->d_sunEntries);
     if (s->h_probe) cudaFreeHost(s->h_probe);
     if (s->probeDone) cudaEventDestroy(s->probeDone);
     if (s->h_stage) cudaFreeHost(s->h_stage);
@@ -1438,7 +1621,8 @@ static int check_status(const tmpt_scene* s, cudaStream_t st) {
 extern "C" int tmpt_hit_scene(const tmpt_scene* s, const float* rays6, int64_t nRays, float tMin, float tMax, int mode, int mem,
                               int32_t* outID, float* outT, float* outPos3, float* outNormal3, void* stream) {
     if (!s || nRays < 0 || (nRays > 0 && (!rays6 || !outID))) return tmpt::fail(TMPT_ERR_ARG, "tmpt_hit_scene: NULL scene / rays / outID");
-    if (mode != TMPT_HIT_CLOSEST && mode != TMPT_HIT_ANY && mode != TMPT_HIT_BRUTE) return tmpt::fail(TMPT_ERR_ARG, "tmpt_hit_scene: mode %d", mode);
+    if (mode != TMPT_HIT_CLOSEST && mode != TMPT_HIT_ANY && mode != TMPT_HIT_BRUTE && mode != TMPT_HIT_SUN) return tmpt::fail(TMPT_ERR_ARG, "tmpt_hit_scene: mode %d", mode);
+    if (mode == TMPT_HIT_SUN && s->triCount > 0 && s->view.sun.n == 0) return tmpt::fail(TMPT_ERR_ARG, "tmpt_hit_scene: TMPT_HIT_SUN, but this scene has no sun grid");
     if (mem != TMPT_HOST && mem != TMPT_DEVICE) return tmpt::fail(TMPT_ERR_ARG, "tmpt_hit_scene: mem %d", mem);
     if (nRays == 0) return TMPT_OK;
     DeviceGuard guard(s->device);
@@ -1498,6 +1682,7 @@ extern "C" int tmpt_hit_scene(const tmpt_scene* s, const float* rays6, int64_t n
 #endif
     if (mode == TMPT_HIT_CLOSEST) LAUNCH((k_hit_scene<TMPT_HIT_CLOSEST, false>), G, B, 0, st, s->view, dRays, (long long)nRays, tMin, tMax, dID, dT, dPos, dNrm, nullptr);
     else if (mode == TMPT_HIT_ANY) LAUNCH((k_hit_scene<TMPT_HIT_ANY, false>), G, B, 0, st, s->view, dRays, (long long)nRays, tMin, tMax, dID, dT, dPos, dNrm, nullptr);
+    else if (mode == TMPT_HIT_SUN) LAUNCH((k_hit_scene<TMPT_HIT_SUN, false>), G, B, 0, st, s->view, dRays, (long long)nRays, tMin, tMax, dID, dT, dPos, dNrm, nullptr);
     else LAUNCH((k_hit_scene<TMPT_HIT_BRUTE, false>), G, B, 0, st, s->view, dRays, (long long)nRays, tMin, tMax, dID, dT, dPos, dNrm, nullptr);
     CU_TRY(cudaGetLastError());
     if (mem == TMPT_HOST) {
@@ -1529,7 +1714,6 @@ extern "C" int tmpt_stripe_rows(int height, int stripeRows, int rank, int worldS
     return rows;
 }
 
-static ex::V3 host_light_dir() { return ex::normalize(ex::v3(-0.7f, 1.0f, 0.5f)); }  // main.cpp:36
 
 // Chunk sums go to an accumulation buffer when a pixel has more than one chunk; the frame is rendered in bands of
 // owned rows so that the buffer stays within a fixed budget (a whole 1080p x 64 spp frame, 32 chunks per pixel, is 1.06 GB; the budget is 4 GB).  Allocation
@@ -2008,7 +2192,8 @@ extern "C" int tmpt_render_stats(const tmpt_scene* cs, const tmpt_camera* camera
 }
 
 extern "C" int tmpt_hit_scene_stats(const tmpt_scene* s, const float* rays6Dev, int64_t nRays, float tMin, float tMax, int mode, uint64_t outStats[TMPT_STATS_COUNT]) {
-    if (!s || !rays6Dev || nRays <= 0 || !outStats || (mode != TMPT_HIT_CLOSEST && mode != TMPT_HIT_ANY))
+    if (!s || !rays6Dev || nRays <= 0 || !outStats || (mode != TMPT_HIT_CLOSEST && mode != TMPT_HIT_ANY && mode != TMPT_HIT_SUN) ||
+        (mode == TMPT_HIT_SUN && s->view.sun.n == 0))
         return tmpt::fail(TMPT_ERR_ARG, "tmpt_hit_scene_stats: bad arguments");
     DeviceGuard guard(s->device);
     if (!guard.ok) return tmpt::fail(TMPT_ERR_CUDA, "tmpt_hit_scene_stats: cudaSetDevice(%d) failed", s->device);
@@ -2021,6 +2206,7 @@ extern "C" int tmpt_hit_scene_stats(const tmpt_scene* s, const float* rays6Dev, 
     const int B = 128;
     const int G = (int)std::min<long long>(div_up(nRays, B), (long long)s->smCount * 64);
     if (mode == TMPT_HIT_CLOSEST) LAUNCH((k_hit_scene<TMPT_HIT_CLOSEST, true>), G, B, 0, st, s->view, rays6Dev, (long long)nRays, tMin, tMax, ids.p, nullptr, nullptr, nullptr, stats.p);
+    else if (mode == TMPT_HIT_SUN) LAUNCH((k_hit_scene<TMPT_HIT_SUN, true>), G, B, 0, st, s->view, rays6Dev, (long long)nRays, tMin, tMax, ids.p, nullptr, nullptr, nullptr, stats.p);
     else LAUNCH((k_hit_scene<TMPT_HIT_ANY, true>), G, B, 0, st, s->view, rays6Dev, (long long)nRays, tMin, tMax, ids.p, nullptr, nullptr, nullptr, stats.p);
     CU_TRY(cudaGetLastError());
     CU_TRY(cudaMemcpyAsync(outStats, stats.p, TMPT_STATS_COUNT * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
