@@ -116,6 +116,7 @@ struct tmpt_scene {
     uint2* d_sunEntries = nullptr;
     uint32_t sunEntriesCap = 0, sunEntries = 0;
     uint64_t sunBytes = 0;
+    size_t sunStartCap = 0, sunCountCap = 0;
     // render-kernel choice (k_render vs k_render_paths), cached per camera / frame size: see k_probe_paths
     tmpt_camera probeCam{};
     int probeW = 0, probeH = 0, probeUsePaths = -1;  // -1: no decision yet
@@ -1425,10 +1426,17 @@ static int build_sun_grid(tmpt_scene* s, const float* tris9, int n, cudaStream_t
         sun::set_resolution(g, cells);
         const long long nCells = (long long)cells * cells;
         const int nBlocks = (int)((nCells + kScanBlock - 1) / kScanBlock);
-        cudaFree(s->d_sunStart); s->d_sunStart = nullptr;
-        cudaFree(s->d_sunCount); s->d_sunCount = nullptr;
-        CU_TRY(cudaMalloc((void**)&s->d_sunStart, (size_t)(nCells + 1) * sizeof(uint32_t)));
-        CU_TRY(cudaMalloc((void**)&s->d_sunCount, (size_t)(nCells + nBlocks + 2 + n) * sizeof(uint32_t)));
+        const size_t needStart = (size_t)nCells + 1, needCount = (size_t)nCells + nBlocks + 2 + n;
+        if (s->sunStartCap < needStart) {  // (a refit finds its buffers in place)
+            cudaFree(s->d_sunStart); s->d_sunStart = nullptr; s->sunStartCap = 0;
+            CU_TRY(cudaMalloc((void**)&s->d_sunStart, needStart * sizeof(uint32_t)));
+            s->sunStartCap = needStart;
+        }
+        if (s->sunCountCap < needCount) {
+            cudaFree(s->d_sunCount); s->d_sunCount = nullptr; s->sunCountCap = 0;
+            CU_TRY(cudaMalloc((void**)&s->d_sunCount, needCount * sizeof(uint32_t)));
+            s->sunCountCap = needCount;
+        }
         uint32_t* totals = s->d_sunCount + nCells;
         uint32_t* grand = totals + nBlocks;
         uint32_t* bigCount = grand + 1;
