@@ -309,7 +309,12 @@ def measure_hit_scene(tm, torch, sc, cam, w, h, dev):
     hit = ids >= 0
     pos, nrm = pos[hit], nrm[hit]
     shadow = torch.cat([pos, light.expand_as(pos)], 1).contiguous()
-    _, _, _, out["shadow_any"] = timed(shadow, tm.HIT_ANY)
+    ids_any, _, _, out["shadow_any"] = timed(shadow, tm.HIT_ANY)
+    try:  # the same shadow rays through the sun grid (what the render kernels do): must agree ray by ray
+        ids_sun, _, _, out["shadow_sun_grid"] = timed(shadow, tm.HIT_SUN)
+        out["shadow_sun_grid"]["agrees_with_shadow_any"] = bool(((ids_any >= 0) == (ids_sun >= 0)).all().item())
+    except Exception as e:  # noqa: BLE001 -- a scene without a grid (TMPT_SUN_GRID=0)
+        out["shadow_sun_grid"] = {"unavailable": repr(e)}
     r = torch.randn(pos.shape, device=dev, generator=g)
     r = r / r.norm(dim=1, keepdim=True)
     nd = nrm + r
@@ -491,10 +496,10 @@ def bench_b200(args, scene, w, h, spp, rank, world, local_rank):
         traffic, traffic_source = None, None
         try:  # dram__bytes_read + dram__bytes_write of this kernel on this workload: NOT measured in this run (ncu cannot run inside a
             # timed bench), read from the committed ncu --set full capture of the same instantiation and labelled as such
-            tj = json.load(open(os.path.join(ROOT, "profiles", "r2_traffic.json")))["k_render"]
+            tj = json.load(open(os.path.join(ROOT, "profiles", "r2g_traffic.json")))["k_render"]
             if args.workload == "sponza_1080p_64spp" and world == 1:
                 traffic = tj["dram_bytes_read"] + tj["dram_bytes_write"]
-                traffic_source = "from file profiles/r2_traffic.json (" + tj["source"] + "), not measured in this run"
+                traffic_source = "from file profiles/r2g_traffic.json (" + tj["source"] + "), not measured in this run"
         except (OSError, KeyError, ValueError):
             pass
         achieved = (value / world) * 1e6 * flops_per_ray / 1e12 if flops_per_ray else None
@@ -506,7 +511,7 @@ def bench_b200(args, scene, w, h, spp, rank, world, local_rank):
             "hbm_context": {"algorithmic_bytes_per_frame": int(tris.size * 4 + w * h * 4), "hbm_peak_gbs_measured": peaks.get("hbm_gbs"),
                             "hbm_frac": (tris.size * 4 + w * h * 4) / (kernel_ms * 1e-3) / 1e9 / peaks["hbm_gbs"] if peaks.get("hbm_gbs") else None},
             "kernel": "k_render", "kernel_ms": kernel_ms,
-            "limiter": "L1 data stage (l1tex__data_pipe_lsu_wavefronts 84 % of peak) and issue slots (69 %), profiles/r2c_k_render_ncu_summary.txt",
+            "limiter": "L1 data stage (l1tex__data_pipe_lsu_wavefronts 88 % of peak) and issue slots (65 %), profiles/r2g_k_render_ncu_summary.txt",
         }
         if stats:
             # the limiter in the kernel's own units: 16-byte rows gathered per clock and SM (7 per node step, 3 per triangle test), against
@@ -514,8 +519,9 @@ def bench_b200(args, scene, w, h, spp, rank, world, local_rank):
             rows_per_ray = 7.0 * stats["node_visits_per_ray"] + 3.0 * stats["tri_tests_per_ray"]
             rows_rate = (value / world) * 1e6 * rows_per_ray / (sm_count * sm_mhz * 1e6)
             roofline["l1_gather"] = {"rows_per_ray": rows_per_ray, "rows_per_clk_per_sm": rows_rate, "peak_rows_per_clk_per_sm_all_l1_hits": 2.9,
-                                     "frac": rows_rate / 2.9, "l1_hit_rate_ncu": 0.70,
-                                     "note": "misses cost about twice a hit in the data stage (1.3-1.5 rows/clk): ncu puts the stage at 84 % of its wavefront peak"}
+                                     "frac": rows_rate / 2.9, "l1_hit_rate_ncu": 0.64,
+                                     "note": "rows of node steps and triangle tests (the sun grid's list entries, ~1 row per shadow ray, not counted); misses cost about "
+                                             "twice a hit in the data stage (1.3-1.5 rows/clk): ncu puts the stage at 88 % of its wavefront peak"}
         cw, ch, cspp = CPU_SAMPLE[scene]
         try:
             mr, crays, csec, kind, cores = run_reference_cpu(scene, cw, ch, cspp)

@@ -38,7 +38,12 @@ void build_sun_grid(EmuScene* s, int cellsForced) {
     s->view.sun = sun::View{};
     if (s->n == 0 || cellsForced == 0) return;
     sun::View g;
-    if (!sun::setup_view(s->tris9.data(), s->n, ex::normalize(ex::v3(-0.7f, 1.0f, 0.5f)), g)) return;
+    float bmin[3] = {3.0e38f, 3.0e38f, 3.0e38f}, bmax[3] = {-3.0e38f, -3.0e38f, -3.0e38f};  // kernels.cu: k_prim_bounds
+    for (size_t i = 0; i < (size_t)s->n * 9; ++i) {
+        bmin[i % 3] = std::min(bmin[i % 3], s->tris9[i]);
+        bmax[i % 3] = std::max(bmax[i % 3], s->tris9[i]);
+    }
+    if (!sun::setup_view(bmin, bmax, ex::normalize(ex::v3(-0.7f, 1.0f, 0.5f)), g)) return;
     sun::set_resolution(g, cellsForced > 0 ? cellsForced : sun::default_cells_per_side(s->n));
     const size_t nCells = (size_t)g.n * g.n;
     s->sunStart.assign(nCells + 1, 0u);

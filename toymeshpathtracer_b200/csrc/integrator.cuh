@@ -95,8 +95,12 @@ TMPT_HD ex::V3 trace_path(Stack& stack, const Scene& sc, const Camera& cam, ex::
         bvh::hit_payload(sc, h.id, h.u, h.v, pos, normal);
         ++rays;
         // the shadow ray (main.cpp:59): through the sun grid when the scene has one (sungrid.cuh), else through the tree
+#if defined(TMPT_SUN_ONLY) && TMPT_SUN_ONLY  // (experiment: what the tree fallback in the same kernel costs)
+        const bool shadowed = bvh::sun_occluded<STATS>(sc, pos, lightDir, kMinT, kMaxT, stats);
+#else
         const bool shadowed = sc.sun.n > 0 ? bvh::sun_occluded<STATS>(sc, pos, lightDir, kMinT, kMaxT, stats)
                                            : bvh::traverse_with<true, STATS, FAR>(stack, sc, pos, lightDir, kMinT, kMaxT, stats).id >= 0;
+#endif
         kk[depth] = shadowed ? 0.0f : sun_term(normal, d, lightDir);
         d = scatter_dir(pos, normal, rng);
         o = pos;

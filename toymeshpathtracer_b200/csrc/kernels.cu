@@ -1412,14 +1412,18 @@ int build_bvh(tmpt_scene* s, unsigned flags) {
 // than kSunMaxEntries entries (a scene of huge overlapping triangles) the grid is halved, and dropped below 32 cells per side.
 constexpr unsigned long long kSunMaxEntries = 256ull << 20;
 static ex::V3 host_light_dir() { return ex::normalize(ex::v3(-0.7f, 1.0f, 0.5f)); }  // main.cpp:36
-static int build_sun_grid(tmpt_scene* s, const float* tris9, int n, cudaStream_t st) {
+static int build_sun_grid(tmpt_scene* s, int n, cudaStream_t st) {  // (after the tree: needs s->info.bounds_min / max)
     static const int forced = getenv("TMPT_SUN_GRID") ? atoi(getenv("TMPT_SUN_GRID")) : -1;
     s->view.sun = sun::View{};
     s->info.device_bytes -= s->sunBytes;
     s->sunBytes = 0; s->sunEntries = 0;
     if (forced == 0 || n <= 0) return TMPT_OK;
+    static const bool trace = getenv("TMPT_SUN_TRACE") != nullptr;
+    auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    const double t0 = now();
     sun::View g;
-    if (!sun::setup_view(tris9, n, host_light_dir(), g)) return TMPT_OK;  // NaN / infinite vertices: no grid, the tree copes
+    if (!sun::setup_view(s->info.bounds_min, s->info.bounds_max, host_light_dir(), g)) return TMPT_OK;  // NaN / infinite vertices: no grid, the tree copes
+    const double t1 = now();
     int cells = forced > 0 ? std::min(std::max(forced, 1), 8192) : sun::default_cells_per_side(n);
     for (;; cells /= 2) {
         if (cells < (forced > 0 ? 1 : 32)) return TMPT_OK;  // (no grid)
@@ -1449,8 +1453,10 @@ static int build_sun_grid(tmpt_scene* s, const float* tris9, int n, cudaStream_t
         LAUNCH(k_scan_of_totals, 1, kScanBlock, 0, st, totals, nBlocks, grand);
         LAUNCH(k_scan_apply, nBlocks, kScanBlock, 0, st, s->d_sunCount, nCells, totals, grand, s->d_sunStart);
         uint32_t total = 0;
+        const double t2 = now();
         CU_TRY(cudaMemcpyAsync(&total, grand, sizeof total, cudaMemcpyDeviceToHost, st));
         CU_TRY(cudaStreamSynchronize(st));
+        const double t3 = now();
         if ((unsigned long long)total > kSunMaxEntries) continue;  // halve the grid
         if (s->sunEntriesCap < total) {
             cudaFree(s->d_sunEntries); s->d_sunEntries = nullptr; s->sunEntriesCap = 0;
@@ -1461,6 +1467,11 @@ static int build_sun_grid(tmpt_scene* s, const float* tris9, int n, cudaStream_t
         LAUNCH((k_sun_bin<true>), binGrid, 256, 0, st, g, s->d_tris, s->d_tris9, n, s->d_sunCount, s->d_sunStart, s->d_sunEntries, bigList, bigCount);
         LAUNCH((k_sun_bin_big<true>), bigGrid, 256, 0, st, g, s->d_tris, s->d_tris9, s->d_sunCount, s->d_sunStart, s->d_sunEntries, bigList, bigCount);
         LAUNCH(k_sun_sort, (int)((nCells + 127) / 128), 128, 0, st, s->d_sunStart, nCells, s->d_sunEntries);
+        if (trace) {
+            CU_TRY(cudaStreamSynchronize(st));
+            fprintf(stderr, "[sun grid] n %d entries %u: host setup %.2f ms, alloc + count launches %.2f ms, wait for the stream %.2f ms, alloc + fill + sort %.2f ms\n",
+                    cells, total, t1 - t0, t2 - t1, t3 - t2, now() - t3);
+        }
         g.cellStart = s->d_sunStart;
         g.entries = s->d_sunEntries;
         s->view.sun = g;
@@ -1529,7 +1540,7 @@ extern "C" int tmpt_scene_create(const float* tris9, int triCount, int device, u
                 brc = build_bvh(s, flags & ~(unsigned)TMPT_BUILD_LBVH);
             }
             if (brc != TMPT_OK) return brc == kTreeTooDeep ? TMPT_ERR_ARG : brc;
-            brc = build_sun_grid(s, tris9, triCount, s->stream);
+            brc = build_sun_grid(s, triCount, s->stream);
             if (brc != TMPT_OK) return brc;
         } else {
             s->view = bvh::SceneView{nullptr, nullptr, nullptr, nullptr, bvh::NONE, 0, s->d_status, nullptr, 0.0f};
@@ -1572,17 +1583,19 @@ extern "C" int tmpt_scene_refit(tmpt_scene* s, const float* tris9, int triCount,
 #endif
     uint32_t hb[6];
     CU_TRY(cudaMemcpyAsync(hb, s->d_bounds, sizeof hb, cudaMemcpyDeviceToHost, st));
-    {  // the shadow rays' grid is rebuilt for the new positions (inside the timed window)
-        const int grc = build_sun_grid(s, tris9, n, st);
-        if (grc != TMPT_OK) return grc;
-    }
-    CU_TRY(cudaEventRecord(s->ev1, st));
     CU_TRY(cudaStreamSynchronize(st));
     CU_TRY(cudaGetLastError());
     for (int k = 0; k < 3; ++k) {
         s->info.bounds_min[k] = bld::ordered_to_float(hb[k]);
         s->info.bounds_max[k] = bld::ordered_to_float(hb[3 + k]);
     }
+    {  // the shadow rays' grid is rebuilt for the new positions and bounds (inside the timed window)
+        const int grc = build_sun_grid(s, n, st);
+        if (grc != TMPT_OK) return grc;
+    }
+    CU_TRY(cudaEventRecord(s->ev1, st));
+    CU_TRY(cudaStreamSynchronize(st));
+    CU_TRY(cudaGetLastError());
     s->view.farLimit = bvh_far_limit(s->info);
     s->probeW = 0;  // moved geometry: the next frame probes again (k_probe_paths)
     float ms = 0.0f;

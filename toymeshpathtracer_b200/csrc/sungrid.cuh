@@ -126,8 +126,9 @@ TMPT_HD bool entry_before(uint2 a, uint2 b) {
 }
 
 // ---- host side of the build (the product's tmpt_scene_create and the tests' host emulation share it) -------------------------
-// Basis, projected bounds and pads of a scene for light direction l.  false: the scene has non-finite vertices (no grid).
-inline bool setup_view(const float* tris9, int triCount, ex::V3 l, View& g) {
+// Basis, projected bounds and pads of a scene with bounding box [bmin, bmax] for light direction l (the eight corners of the box
+// bound every vertex's projection).  false: the box is not finite (no grid).
+inline bool setup_view(const float bmin[3], const float bmax[3], ex::V3 l, View& g) {
     g = View{};
     const double L[3] = {l.x, l.y, l.z};
     const bool xAxis = (L[0] < 0 ? -L[0] : L[0]) < 0.9;
@@ -140,8 +141,8 @@ inline bool setup_view(const float* tris9, int triCount, ex::V3 l, View& g) {
     g.vx = (float)V[0]; g.vy = (float)V[1]; g.vz = (float)V[2];
     g.lx = l.x; g.ly = l.y; g.lz = l.z;
     float lo[3] = {3.0e38f, 3.0e38f, 3.0e38f}, hi[3] = {-3.0e38f, -3.0e38f, -3.0e38f};
-    for (size_t i = 0; i < (size_t)triCount * 3; ++i) {
-        const ex::V3 p = ex::v3(tris9[3 * i], tris9[3 * i + 1], tris9[3 * i + 2]);
+    for (int corner = 0; corner < 8; ++corner) {
+        const ex::V3 p = ex::v3((corner & 1) ? bmax[0] : bmin[0], (corner & 2) ? bmax[1] : bmin[1], (corner & 4) ? bmax[2] : bmin[2]);
         const float c[3] = {proj_u(g, p), proj_v(g, p), proj_w(g, p)};
         for (int k = 0; k < 3; ++k) {
             if (!(c[k] == c[k]) || fabsf(c[k]) > 1.0e30f) return false;
