@@ -754,6 +754,29 @@ def test_render_kernel_choice_follows_the_camera_and_never_changes_the_bytes():
     assert ks[0] == 0 and ks[2] == 1 and ks[5] == 0, kernels  # the second frame of an unchanged camera has the new decision (render() is synchronous)
 
 
+def test_frames_do_not_depend_on_the_sun_grid(tmp_path):
+    """TMPT_SUN_GRID=0 (shadow rays walk the tree, the fallback of a scene without a grid), a coarse grid and the default grid:
+    the same bytes and ray counts, through both render kernels (suzanne: k_render_paths, sponza: k_render) and progressive passes."""
+    import sys
+
+    def run(name, w, h, spp, grid, extra=()):
+        out = str(tmp_path / f"{name}_{grid}_{len(extra)}.npz")
+        env = dict(os.environ)
+        env.pop("TMPT_SUN_GRID", None)
+        if grid is not None:
+            env["TMPT_SUN_GRID"] = grid
+        r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "render_probe.py"), name, str(w), str(h), str(spp), out, *extra],
+                           env=env, capture_output=True, text=True, timeout=900)
+        assert r.returncode == 0, r.stderr[-2000:]
+        z = np.load(out)
+        return z["img"].tobytes(), int(z["rays"])
+
+    for name, w, h, spp, extra in (("suzanne", 200, 120, 6, ()), ("sponza", 240, 136, 4, ()), ("suzanne", 101, 57, 20, ("2", "1", "3"))):
+        base = run(name, w, h, spp, None, extra)
+        for grid in ("0", "5", "300"):
+            assert run(name, w, h, spp, grid, extra) == base, (name, grid)
+
+
 def test_regeneration_render_kernel_gives_the_same_bytes(tmp_path):
     """k_render_regen (per-lane ray regeneration; measured, not shipped: it lives in the -DTMPT_EXPERIMENTS=1 build only)
     schedules the same per-lane arithmetic differently: frame and ray count equal the lockstep kernel's, one-shot and over

@@ -1,5 +1,5 @@
 """Scene build times inside a process that has torch's CUDA context up (as bench.py does): cold and warm (development)."""
-import sys, time; sys.path.insert(0, '/root/repo')
+import sys, time; sys.path.insert(0, __import__('os').path.dirname(__import__('os').path.dirname(__import__('os').path.abspath(__file__))))
 import torch
 torch.cuda.init(); x = torch.zeros(1 << 20, device="cuda"); torch.cuda.synchronize()
 import toymeshpathtracer_b200 as tm
