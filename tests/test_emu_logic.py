@@ -433,3 +433,24 @@ def test_sun_grid_lists_are_sorted_and_conservative(emu):
     rays = np.concatenate([below, np.broadcast_to(l, below.shape)], 1).astype(np.float32)
     assert ((got > 0) == (s.hit(rays, mode=2)[0] >= 0)).all()
     assert (got[facing] > 0).mean() > 0.999
+
+
+@pytest.mark.parametrize("scale,shift", [(1e-3, 0.0), (1e4, 0.0), (1.0, 5e3), (1e-2, 1e2), (1e3, -7e5)])
+def test_sun_grid_pads_scale_with_the_scene(emu, scale, shift):
+    """The pads are relative (2^-14 of the projected extent, 2^-16 of the largest coordinate): a scene a thousand times smaller or
+    ten thousand times larger, or far from the origin (where float coordinates are coarse), still answers like the scan."""
+    sc = load_scene("suzanne")
+    l = np.ascontiguousarray(load_rays("suzanne")["rays"][load_rays("suzanne")["kind"] == 2][0, 3:6], np.float32)
+    tris = (sc["tris"].reshape(-1, 3) * np.float32(scale) + np.float32(shift)).astype(np.float32).reshape(-1, 9)
+    v = tris.reshape(-1, 3, 3)
+    mn, mx = v.reshape(-1, 3).min(0), v.reshape(-1, 3).max(0)
+    ext = float((mx - mn).max())
+    rng = np.random.default_rng(3)
+    pick = rng.integers(0, len(v), 3000)
+    bary = rng.dirichlet([0.3, 0.3, 0.3], 3000).astype(np.float32)
+    on = (v[pick] * bary[:, :, None]).sum(1).astype(np.float32)
+    o = np.concatenate([rng.uniform(mn - 0.1 * ext, mx + 0.1 * ext, (3000, 3)).astype(np.float32), on, on - l * np.float32(2e-3 * ext), v[pick, 0]]).astype(np.float32)
+    rays = np.concatenate([o, np.broadcast_to(l, o.shape)], 1).astype(np.float32)
+    s = emu.scene(tris)
+    for tmin in (0.001, 0.0):
+        assert ((s.sun_occluded(o, tmin=tmin)[0] > 0) == (s.hit(rays, tmin=tmin, mode=2)[0] >= 0)).all()
