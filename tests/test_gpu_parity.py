@@ -186,6 +186,7 @@ def test_edge_cases():
         ids, *_ = s.HitScene(ray)
         assert ids[0] == -1
         assert s.HitScene(np.zeros((0, 6), np.float32))[0].shape == (0,)
+        assert s.HitScene(ray, mode=tm.HIT_SUN)[0][0] == -1 and s.HitScene(ray, mode=tm.HIT_ANY)[0][0] == -1
     tri = np.array([[0, 0, 0, 1, 0, 0, 0, 1, 0]], np.float32)
     with tm.Scene(tri) as s:
         ids, t, pos, nrm = s.HitScene(ray)
