@@ -67,8 +67,13 @@ void build_sun_grid(EmuScene* s, int cellsForced) {
             s->sunEntries.assign(std::max<size_t>(s->sunStart[nCells], 1), make_uint2(0, 0));
         }
     }
-    for (size_t c = 0; c < nCells; ++c)
+    for (size_t c = 0; c < nCells; ++c) {
+        if (s->sunStart[c + 1] - s->sunStart[c] > sun::kSortMax) {  // k_sun_sort: long lists are not sorted and have no early exit
+            for (uint32_t i = s->sunStart[c]; i < s->sunStart[c + 1]; ++i) s->sunEntries[i].y = ex::f2u(sun::kFarthest);
+            continue;
+        }
         std::sort(s->sunEntries.begin() + s->sunStart[c], s->sunEntries.begin() + s->sunStart[c + 1], sun::entry_before);
+    }
     g.cellStart = s->sunStart.data();
     g.entries = s->sunEntries.data();
     s->view.sun = g;

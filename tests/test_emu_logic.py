@@ -454,3 +454,20 @@ def test_sun_grid_pads_scale_with_the_scene(emu, scale, shift):
     s = emu.scene(tris)
     for tmin in (0.001, 0.0):
         assert ((s.sun_occluded(o, tmin=tmin)[0] > 0) == (s.hit(rays, tmin=tmin, mode=2)[0] >= 0)).all()
+
+
+def test_sun_grid_with_thousands_of_triangles_over_one_cell(emu):
+    """3000 nearly coincident triangles: every cell they cover has a list longer than sun::kSortMax, which is left unsorted with
+    "infinitely far" entries (no early exit): grid == scan."""
+    rng = np.random.default_rng(21)
+    base = np.array([[0, 0, 0], [1, 0, 0.2], [0.3, 0.1, 1]], np.float32)
+    stack = (base[None] + rng.normal(scale=1e-3, size=(3000, 3, 3))).astype(np.float32).reshape(-1, 9)
+    far = (rng.uniform(-2, 2, (50, 1, 3)) + rng.normal(scale=0.2, size=(50, 3, 3))).astype(np.float32).reshape(-1, 9)
+    tris = np.concatenate([stack, far]).astype(np.float32)
+    l = np.ascontiguousarray(load_rays("cube")["rays"][load_rays("cube")["kind"] == 2][0, 3:6], np.float32)
+    s = emu.scene(tris)
+    assert s.sun_grid(-1)["longest"] > 1024
+    o = rng.uniform(-2.5, 2.5, (4000, 3)).astype(np.float32)
+    rays = np.concatenate([o, np.broadcast_to(l, o.shape)], 1).astype(np.float32)
+    got, scan = s.sun_occluded(o)[0] > 0, s.hit(rays, mode=2)[0] >= 0
+    assert (got == scan).all() and 0.02 < got.mean() < 0.98

@@ -266,6 +266,22 @@ def test_sun_grid_shadow_query_equals_tree_scan_and_reference(scenes, name):
     assert 0.02 < a.mean() < 0.98
 
 
+def test_sun_grid_with_thousands_of_triangles_over_one_cell():
+    """3000 nearly coincident triangles: lists longer than sun::kSortMax are left unsorted and without an early exit; the shadow
+    query still equals the tree's any-hit and the scan."""
+    rng = np.random.default_rng(21)
+    base = np.array([[0, 0, 0], [1, 0, 0.2], [0.3, 0.1, 1]], np.float32)
+    stack = (base[None] + rng.normal(scale=1e-3, size=(3000, 3, 3))).astype(np.float32).reshape(-1, 9)
+    far = (rng.uniform(-2, 2, (50, 1, 3)) + rng.normal(scale=0.2, size=(50, 3, 3))).astype(np.float32).reshape(-1, 9)
+    tris = np.concatenate([stack, far]).astype(np.float32)
+    l = load_rays("cube")["rays"][load_rays("cube")["kind"] == 2][0, 3:6].astype(np.float32)
+    o = rng.uniform(-2.5, 2.5, (20000, 3)).astype(np.float32)
+    q = np.concatenate([o, np.broadcast_to(l, o.shape)], 1).astype(np.float32)
+    with tm.Scene(tris) as s:
+        a, b, c = (s.HitScene(q, mode=m)[0] >= 0 for m in (tm.HIT_SUN, tm.HIT_ANY, tm.HIT_BRUTE))
+        assert (a == b).all() and (a == c).all() and 0.02 < a.mean() < 0.98
+
+
 def test_far_camera_frame_bit_exact_vs_oracle(scenes, oracle):
     """A camera 40 scene sizes away: its origin is beyond the far limit of the padded boxes (bvh.cuh: ray_is_far), so
     launch_render picks the render instantiation that answers such rays with the exact scan.  Still the oracle's bytes."""

@@ -1101,6 +1101,10 @@ __global__ void __launch_bounds__(128) k_sun_sort(const uint32_t* __restrict__ c
     const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= nCells) return;
     const uint32_t b = cellStart[c], e = cellStart[c + 1];
+    if (e - b > sun::kSortMax) {  // (thousands of triangles over one cell: no order, no early exit)
+        for (uint32_t i = b; i < e; ++i) entries[i].y = ex::f2u(sun::kFarthest);
+        return;
+    }
     for (uint32_t i = b + 1; i < e; ++i) {
         const uint2 x = entries[i];
         uint32_t j = i;

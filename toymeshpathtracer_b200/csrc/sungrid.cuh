@@ -119,6 +119,11 @@ TMPT_HD int default_cells_per_side(int triCount) {
     return n;
 }
 
+// Lists longer than this are not sorted (one thread sorts a list by insertion): their entries get the far depth "infinitely far"
+// instead, so a query tests all of them -- what a scan would do -- and the early exit never fires on an unsorted list.
+constexpr uint32_t kSortMax = 1024;
+constexpr float kFarthest = 3.0e38f;
+
 // entry order inside a cell: far depth descending, then slot ascending (a total order: the build is deterministic)
 TMPT_HD bool entry_before(uint2 a, uint2 b) {
     const float za = ex::u2f(a.y), zb = ex::u2f(b.y);
