@@ -367,10 +367,9 @@ void emu_sun_info(void* h, long long out[3]) {
 }
 void emu_sun_occluded(void* h, const float* origins3, long n, float tMin, float tMax, int* out, unsigned long long* triTests) {
     EmuScene* s = (EmuScene*)h;
-    const ex::V3 l = ex::v3(s->view.sun.lx, s->view.sun.ly, s->view.sun.lz);
     bvh::TravStats ts;
-    for (long i = 0; i < n; ++i)
-        out[i] = s->view.sun.n > 0 && bvh::sun_occluded<true>(s->view, ex::v3(origins3[3 * i], origins3[3 * i + 1], origins3[3 * i + 2]), l, tMin, tMax, &ts) ? 1 : -1;
+    for (long i = 0; i < n; ++i)  // as k_hit_scene<TMPT_HIT_SUN> answers it: far origins by the scan
+        out[i] = s->view.sun.n > 0 && bvh::sun_query<true>(s->view, ex::v3(origins3[3 * i], origins3[3 * i + 1], origins3[3 * i + 2]), tMin, tMax, &ts) ? 1 : -1;
     if (triTests) *triTests = ts.tris;
 }
 

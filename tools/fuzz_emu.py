@@ -1,0 +1,190 @@
+#!/usr/bin/env python
+"""Fuzz the product's structures on the CPU -- TEST TOOLING (runs the host emulation, tests/emu: the product's own
+__host__ __device__ headers compiled with g++; never part of the product path).
+
+    python tools/fuzz_emu.py [first_seed] [last_seed]        # default 0 400, all cores
+
+A seed makes one random scene -- 1 .. 2000 triangles of one of eight kinds (blobs, sizes over five decades, coplanar overlapping
+pieces, slivers, triangles edge-on to the sun, duplicates, a height-field mesh with shared vertices under three giants, triangles
+flat in the sun's depth), scaled by 1e-4 .. 1e5 and sometimes shifted far off the origin -- and 21 000 query origins on, a hair
+above / below, at vertices and edge midpoints of, around and far below its triangles.  Per seed, for both builders:
+
+  tree closest hit  == all-triangle scan   (id, t bits; rays along the sun and in random / axis-parallel directions)
+  tree any hit      == scan
+  sun grid          == scan                 (bvh::sun_query, what k_hit_scene<TMPT_HIT_SUN> runs)
+
+at tMin = 0.001 (the integrator's) and tMin = 0 (a caller's choice: rays that START on a surface hit it at t = +-0).
+
+What it found (round 2, both fixed, regression tests in tests/test_emu_logic.py and tests/test_zz_gpu_fuzz_regressions.py):
+  * pop-time cull with the child slot still in the key's low bits (bvh.cuh: walk_step) -- with tMin = 0 a ray starting on a shared
+    vertex lost the lower-index triangles of the tie;
+  * TMPT_HIT_SUN for origins a million scene sizes away (bvh.cuh: sun_query now takes the scan beyond the far limit).
+What it documents: ZERO-AREA triangles -- the scan can accept a garbage "hit" of such a triangle anywhere along a
+ray; the tree finds it only for rays that cross the triangle's padded box (the reference: only for rays that cross its octree leaf).
+`scene_kinds(degenerate=False)` leaves them out; with them the tool reports the mismatches and checks that they involve nothing else.
+"""
+from __future__ import annotations
+
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+sys.path.insert(0, ROOT)
+
+_EMU = None
+_L = None
+
+
+def _emu():
+    global _EMU
+    if _EMU is None:
+        from emu_binding import Emu
+        _EMU = Emu()
+    return _EMU
+
+
+def light_dir():
+    """kLightDir as the reference computes it (main.cpp:36): read from a golden shadow ray."""
+    global _L
+    if _L is None:
+        g = np.load(os.path.join(ROOT, "tests", "golden", "rays", "cube.npz"))
+        _L = np.ascontiguousarray(g["rays"][g["kind"] == 2][0, 3:6], np.float32)
+    return _L
+
+
+def bits(a):
+    return np.ascontiguousarray(a, np.float32).view(np.uint32)
+
+
+KINDS = ("blobs", "log-sizes", "coplanar", "slivers", "edge-on", "duplicates+degenerate", "mesh+giants", "flat-in-depth")
+
+
+def make_scene(rng, kind=None, degenerate=True):
+    """-> (tris9 float32 [n, 9], scale, kind)"""
+    L = light_dir().astype(np.float64)
+    n = int(rng.choice([1, 2, 5, 17, 64, 300, 2000]))
+    scale = float(10 ** rng.uniform(-4, 5))
+    shift = rng.uniform(-1, 1, 3) * scale * float(10 ** rng.uniform(-2, 3)) * (rng.random() < 0.5)
+    if kind is None:
+        kind = int(rng.integers(0, 8))
+    c = rng.uniform(-1, 1, (n, 1, 3))
+    if kind == 0:
+        t = c + rng.normal(scale=0.1, size=(n, 3, 3))
+    elif kind == 1:
+        t = c + rng.normal(size=(n, 3, 3)) * (10 ** rng.uniform(-5, 0.5, (n, 1, 1)))
+    elif kind == 2:
+        t = c + rng.normal(scale=0.3, size=(n, 3, 3))
+        ax = rng.integers(0, 3)
+        t[:, :, ax] = np.round(c[:, :, ax] * 3) / 3
+    elif kind == 3:
+        a = c + rng.normal(scale=0.2, size=(n, 1, 3))
+        b = a + rng.normal(scale=0.5, size=(n, 1, 3))
+        t = np.concatenate([a, b, (a + b) / 2 + rng.normal(size=(n, 1, 3)) * 1e-6], 1)
+    elif kind == 4:
+        a = c + rng.normal(scale=0.2, size=(n, 1, 3))
+        t = np.concatenate([a, a + L[None, None, :] * rng.uniform(0.01, 1, (n, 1, 1)), a + rng.normal(scale=0.2, size=(n, 1, 3))], 1)
+    elif kind == 5:
+        base = c[: max(1, n // 4)] + rng.normal(scale=0.2, size=(max(1, n // 4), 3, 3))
+        t = base[rng.integers(0, len(base), n)]
+        z1, z2 = rng.random(n) < 0.2, rng.random(n) < 0.1
+        if degenerate:
+            t[z1, 2] = t[z1, 1]
+            t[z2, 1] = t[z2, 0]
+            t[z2, 2] = t[z2, 0]
+    elif kind == 6:
+        m = int(np.sqrt(n / 2)) + 1
+        xs, ys = np.meshgrid(np.linspace(-1, 1, m + 1), np.linspace(-1, 1, m + 1))
+        P = np.stack([xs, 0.1 * np.sin(3 * xs) * np.cos(2 * ys), ys], -1)
+        q = []
+        for i in range(m):
+            for j in range(m):
+                q.append([P[i, j], P[i + 1, j], P[i, j + 1]])
+                q.append([P[i + 1, j], P[i + 1, j + 1], P[i, j + 1]])
+        t = np.concatenate([np.array(q), rng.normal(size=(3, 3, 3)) * 30])
+    else:
+        t = c + rng.normal(scale=0.2, size=(n, 3, 3))
+        w = (t * L).sum(-1, keepdims=True)
+        t = t - w * L * (1 - 10 ** rng.uniform(-8, 0, (n, 1, 1)))
+    return np.ascontiguousarray((t * scale + shift).reshape(-1, 9), np.float32), scale, kind
+
+
+def make_origins(rng, tris, scale, k=3000):
+    L = light_dir().astype(np.float64)
+    v = tris.reshape(-1, 3, 3).astype(np.float64)
+    pick = rng.integers(0, len(v), k)
+    on = (v[pick] * rng.dirichlet([0.4, 0.4, 0.4], k)[:, :, None]).sum(1)
+    mn, mx = v.reshape(-1, 3).min(0), v.reshape(-1, 3).max(0)
+    ext = np.maximum(mx - mn, 1e-30)
+    o = np.concatenate([on, on - L * scale * 1e-3, on + L * scale * 1e-5, v[pick, 0], (v[pick, 0] + v[pick, 1]) / 2,
+                        rng.uniform(mn - 0.3 * ext, mx + 0.3 * ext, (k, 3)), on - L * ext.max() * rng.uniform(0, 3, (k, 1))])
+    return np.ascontiguousarray(o, np.float32)
+
+
+def zero_area(tris):
+    v = tris.reshape(-1, 3, 3).astype(np.float64)
+    return np.linalg.norm(np.cross(v[:, 1] - v[:, 0], v[:, 2] - v[:, 0]), axis=1) == 0.0
+
+
+def run_seed(seed, degenerate=True, kind=None):
+    """-> (seed, kind, triangles, scale, failures, documented): `failures` must be empty; `documented` counts the closest-hit
+    differences that involve a zero-area triangle (see the module docstring)."""
+    rng = np.random.default_rng(seed)
+    tris, scale, kind = make_scene(rng, kind, degenerate)
+    o = make_origins(rng, tris, scale)
+    L = light_dir()
+    flat = zero_area(tris)
+    bad, documented = [], 0
+    for builder in (0, 1):
+        s = _emu().scene(tris, builder=builder)
+        if s.info()["status"] != 0:
+            bad.append(("status", builder, s.info()))
+            continue
+        d = rng.normal(size=o.shape)
+        d /= np.linalg.norm(d, axis=1, keepdims=True)
+        ax = rng.random(len(d)) < 0.1
+        d[ax] = np.eye(3)[rng.integers(0, 3, ax.sum())] * rng.choice([-1, 1], (ax.sum(), 1))
+        for label, rays in (("sun", np.concatenate([o, np.broadcast_to(L, o.shape)], 1).astype(np.float32)),
+                            ("random", np.concatenate([o, d], 1).astype(np.float32))):
+            for tmin in (0.001, 0.0):
+                scan = s.hit(rays, tmin=tmin, mode=2)
+                tree = s.hit(rays, tmin=tmin, mode=0)
+                anyh = s.hit(rays, tmin=tmin, mode=1)[0] >= 0
+                hit = scan[0] >= 0
+                if label == "sun" and builder == 0:
+                    got = s.sun_occluded(o, tmin=tmin)[0] > 0
+                    if (got != hit).any():
+                        bad.append(("sun-grid", tmin, int((got != hit).sum())))
+                if (anyh != hit).any():
+                    bad.append(("any-hit", label, builder, tmin, int((anyh != hit).sum())))
+                m = (tree[0] != scan[0]) | (hit & (bits(tree[1]) != bits(scan[1])))
+                if m.any():
+                    # a difference is "documented" when the scan's winner is a zero-area triangle (its garbage hit is off the triangle)
+                    known = m & hit & flat[np.maximum(scan[0], 0)]
+                    documented += int(known.sum())
+                    if (m & ~known).any():
+                        bad.append(("closest", label, builder, tmin, int((m & ~known).sum())))
+        s.close()
+    return seed, KINDS[kind], len(tris), scale, bad, documented
+
+
+def _run(seed):
+    return run_seed(seed)
+
+
+if __name__ == "__main__":
+    from multiprocessing import Pool
+    a = int(sys.argv[1]) if len(sys.argv) > 1 else 0
+    b = int(sys.argv[2]) if len(sys.argv) > 2 else 400
+    _emu()  # build once, before the workers start
+    fails = docs = 0
+    with Pool(os.cpu_count()) as p:
+        for seed, kind, n, scale, bad, documented in p.imap_unordered(_run, range(a, b)):
+            docs += documented
+            if bad:
+                fails += 1
+                print(f"FAIL seed {seed} ({kind}, {n} triangles, scale {scale:.3g}): {bad}", flush=True)
+    print(f"seeds {a}..{b - 1}: {fails} failing, {docs} closest-hit differences on zero-area triangles (documented)")
+    sys.exit(1 if fails else 0)

@@ -682,7 +682,10 @@ TMPT_HD bool walk_step(WalkState& w, const SceneView& sc, float tMin, float tMax
     // lane, with its stack latency exposed to the whole warp: +3.3 % without it.)
     if (popping) {
         --w.sp;
-        if (ex::u2f((uint32_t)(top >> 32)) <= w.best.t) w.cur = (uint32_t)top;
+        // (the child slot in the key's two low bits is masked off: WITH it the key can exceed the entry distance by up to three
+        // ulps, and an entry clamped to tMin = 0 -- key = slot, a denormal -- compared greater than a best t of +-0: a ray that starts
+        // ON a vertex shared by several triangles lost the lower-index ones.  Found by tools/fuzz_emu.py.)
+        if (ex::u2f((uint32_t)(top >> 32) & ~3u) <= w.best.t) w.cur = (uint32_t)top;
         else if (STATS) ++stats->culledPops;
     }
     const bool done = w.cur == NONE && w.triPos == w.triEnd && w.sp == 0;
@@ -718,6 +721,17 @@ HitRec scan_all(const float4* tris, int triCount, ex::V3 o, ex::V3 d, float tMin
     return best;
 }
 TMPT_HD HitRec brute_force(const SceneView& sc, ex::V3 o, ex::V3 d, float tMin, float tMax) { return scan_all(sc.tris, sc.triCount, o, d, tMin, tMax); }
+
+// The shadow query for a CALLER's origin (tmpt_hit_scene, TMPT_HIT_SUN): the grid's pads, like the boxes', are sized for origins
+// near the scene -- the rounding of an origin's projection and the drift of the ray's own projection along its length both grow
+// with |origin| (at 1e6 scene sizes a query lands in a neighbouring cell) -- so an origin beyond the far limit is answered by the
+// scan, as in traverse().  The integrator's own shadow rays start on a triangle and call sun_occluded directly.
+template <bool STATS>
+TMPT_HD bool sun_query(const SceneView& sc, ex::V3 o, float tMin, float tMax, TravStats* stats) {
+    const ex::V3 l = ex::v3(sc.sun.lx, sc.sun.ly, sc.sun.lz);
+    if (ray_is_far(sc, o)) return scan_all(sc.tris, sc.triCount, o, l, tMin, tMax).id >= 0;
+    return sun_occluded<STATS>(sc, o, l, tMin, tMax, stats);
+}
 
 template <bool ANY, bool STATS = false>
 TMPT_HD HitRec traverse(const SceneView& sc, ex::V3 o, ex::V3 d, float tMin, float tMax, TravStats* stats = nullptr) {

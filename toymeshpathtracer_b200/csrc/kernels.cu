@@ -553,7 +553,7 @@ __global__ void __launch_bounds__(128) k_hit_scene(bvh::SceneView sc, const floa
         bvh::HitRec h;
         if (MODE == TMPT_HIT_BRUTE) h = bvh::brute_force(sc, o, d, tMin, tMax);
         else if (MODE == TMPT_HIT_SUN) {  // the integrator's shadow query: the ray's own direction is NOT read, the sun's is used
-            h.id = sc.sun.n > 0 && bvh::sun_occluded<STATS>(sc, o, ex::v3(sc.sun.lx, sc.sun.ly, sc.sun.lz), tMin, tMax, &ts) ? 1 : -1;  // (no grid: an empty scene)
+            h.id = sc.sun.n > 0 && bvh::sun_query<STATS>(sc, o, tMin, tMax, &ts) ? 1 : -1;  // (no grid: an empty scene)
             h.t = 0.0f; h.u = 0.0f; h.v = 0.0f;
         } else if (MODE == TMPT_HIT_ANY) h = bvh::traverse<true, STATS>(sc, o, d, tMin, tMax, &ts);
         else h = bvh::traverse<false, STATS>(sc, o, d, tMin, tMax, &ts);
