@@ -2,7 +2,8 @@
 """Fuzz the product's structures on the CPU -- TEST TOOLING (runs the host emulation, tests/emu: the product's own
 __host__ __device__ headers compiled with g++; never part of the product path).
 
-    python tools/fuzz_emu.py [first_seed] [last_seed]        # default 0 400, all cores
+    python tools/fuzz_emu.py [first_seed] [last_seed]             # default 0 400, all cores
+    python tools/fuzz_emu.py --render [first_seed] [last_seed]    # small frames of random scenes: emulation == oracle, bytes and ray count
 
 A seed makes one random scene -- 1 .. 2000 triangles of one of eight kinds (blobs, sizes over five decades, coplanar overlapping
 pieces, slivers, triangles edge-on to the sun, duplicates, a height-field mesh with shared vertices under three giants, triangles
@@ -21,7 +22,7 @@ What it found (round 2, both fixed, regression tests in tests/test_emu_logic.py 
   * TMPT_HIT_SUN for origins a million scene sizes away (bvh.cuh: sun_query now takes the scan beyond the far limit).
 What it documents: ZERO-AREA triangles -- the scan can accept a garbage "hit" of such a triangle anywhere along a
 ray; the tree finds it only for rays that cross the triangle's padded box (the reference: only for rays that cross its octree leaf).
-`scene_kinds(degenerate=False)` leaves them out; with them the tool reports the mismatches and checks that they involve nothing else.
+`make_scene(degenerate=False)` leaves them out; with them the tool reports the mismatches and checks that they involve nothing else.
 """
 from __future__ import annotations
 
@@ -170,18 +171,51 @@ def run_seed(seed, degenerate=True, kind=None):
     return seed, KINDS[kind], len(tris), scale, bad, documented
 
 
+_ORC = None
+
+
+def render_seed(seed):
+    """Integrator level: a small frame of a random scene (no zero-area triangles; at most 400 triangles: the oracle scans them all)
+    through the host emulation of the product's path -- tree, sun grid, per-pixel RNG streams -- against the oracle in the same RNG
+    mode: the frame's bytes and the ray count must be equal.  -> (seed, kind, triangles, scale, failures)"""
+    global _ORC
+    if _ORC is None:
+        from oracle.pyoracle import Oracle
+        _ORC = Oracle()
+    rng = np.random.default_rng(seed)
+    tris, scale, kind = make_scene(rng, degenerate=False)
+    tris = tris[:400]
+    v = tris.reshape(-1, 3)
+    w, h, spp = 24, 16, int(rng.choice([1, 3, 8]))
+    cam = _ORC.camera_for_scene(v.min(0), v.max(0), w, h)
+    oimg, orays = _ORC.render(tris, cam, w, h, spp, threads=1)
+    bad = []
+    for builder in (0, 1):
+        s = _emu().scene(tris, builder=builder)
+        img, rays = s.render(cam, w, h, spp)
+        if rays != orays or (img != oimg).any():
+            bad.append(("frame", builder, rays, orays, int((img != oimg).any(-1).sum())))
+        s.close()
+    return seed, KINDS[kind], len(tris), scale, bad
+
+
 def _run(seed):
     return run_seed(seed)
 
 
+def _run_render(seed):
+    return render_seed(seed) + (0,)
+
+
 if __name__ == "__main__":
     from multiprocessing import Pool
-    a = int(sys.argv[1]) if len(sys.argv) > 1 else 0
-    b = int(sys.argv[2]) if len(sys.argv) > 2 else 400
+    args = [x for x in sys.argv[1:] if x != "--render"]
+    a = int(args[0]) if len(args) > 0 else 0
+    b = int(args[1]) if len(args) > 1 else 400
     _emu()  # build once, before the workers start
     fails = docs = 0
     with Pool(os.cpu_count()) as p:
-        for seed, kind, n, scale, bad, documented in p.imap_unordered(_run, range(a, b)):
+        for seed, kind, n, scale, bad, documented in p.imap_unordered(_run_render if "--render" in sys.argv else _run, range(a, b)):
             docs += documented
             if bad:
                 fails += 1
