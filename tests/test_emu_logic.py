@@ -543,15 +543,16 @@ def test_sun_query_from_distant_origins_takes_the_scan(emu):
                 assert ((s.sun_occluded(o, tmax=tmax)[0] > 0) == (s.hit(rays, tmax=tmax, mode=2)[0] >= 0)).all(), (name, k, tmax)
 
 
-@pytest.mark.parametrize("seed", [0, 2, 5, 7, 9, 12, 15, 20, 226])
+@pytest.mark.parametrize("seed", [0, 2, 7, 12, 13, 15, 20, 37, 41, 280])
 def test_fuzz_seeds_tree_and_sun_grid_equal_the_scan(seed):
-    """tools/fuzz_emu.py on the seeds that failed before the two fixes above (and two that never did): random scenes of eight
-    kinds at scales 1e-4 .. 1e5; tree closest / any hit and the sun grid against the all-triangle scan at tMin = 0.001 and 0.
-    The only differences allowed are the documented ones: the scan's garbage hits on ZERO-AREA triangles."""
+    """tools/fuzz_emu.py on the seeds that failed before the two fixes above, and two scenes of grazing slivers: random scenes of
+    nine kinds at scales 1e-4 .. 1e5; tree closest / any hit and the sun grid against the all-triangle scan at tMin = 0.001 and 0.
+    The only differences allowed are the documented ones: the scan's GARBAGE hits -- rounding noise that passed
+    the reference's determinant test, at a point outside the triangle's padded box / outside its footprint in the sun's projection."""
     fz = _fuzz()
     _, kind, n, scale, bad, documented = fz.run_seed(seed)
     assert not bad, (kind, n, scale, bad)
-    if kind != "duplicates+degenerate":
+    if kind not in ("duplicates+degenerate", "grazing-slivers", "edge-on", "slivers"):
         assert documented == 0
 
 

@@ -69,27 +69,30 @@ def test_sun_query_from_distant_origins(fz):
                     assert (a == b).all(), (name, k, tmax, int((a != b).sum()))
 
 
-@pytest.mark.parametrize("seed", [0, 2, 5, 7, 12, 15, 20, 226])
+@pytest.mark.parametrize("seed", [0, 2, 7, 12, 15, 20, 37, 41])
 def test_fuzz_scenes_tree_and_sun_grid_equal_the_scan(fz, seed):
-    """The fuzzer's random scenes (eight kinds, scales 1e-4 .. 1e5, some far off the origin) on the GPU: tree closest / any hit
+    """The fuzzer's random scenes (nine kinds, scales 1e-4 .. 1e5, some far off the origin) on the GPU: tree closest / any hit
     and the sun grid against the all-triangle scan at tMin = 0.001 and 0.  Differences are allowed only where the scan's winner is
-    a ZERO-AREA triangle (its "hit" is rounding noise and lies off the triangle)."""
+    a GARBAGE hit (rounding noise that passed the determinant test, at a point outside the triangle's padded box,
+    or -- for the grid -- from an origin outside the triangle's footprint in the sun's projection)."""
     rng = np.random.default_rng(seed)
     tris, scale, kind = fz.make_scene(rng)
     o = fz.make_origins(rng, tris, scale)
-    flat = fz.zero_area(tris)
     d = rng.normal(size=o.shape)
     d = (d / np.linalg.norm(d, axis=1, keepdims=True)).astype(np.float32)
     for flags in (0, tm.BUILD_LBVH):
         with tm.Scene(tris, flags=flags) as s:
             for label, rays in (("sun", _sun_rays(fz, o)), ("random", np.concatenate([o, d], 1).astype(np.float32))):
                 for tmin in (0.001, 0.0):
+                    what = (fz.KINDS[kind], label, tmin)
                     scan = s.HitScene(rays, tMin=tmin, mode=tm.HIT_BRUTE)
                     tree = s.HitScene(rays, tMin=tmin)
                     hit = scan[0] >= 0
-                    assert ((s.HitScene(rays, tMin=tmin, mode=tm.HIT_ANY)[0] == 1) == hit).all(), (fz.KINDS[kind], label, tmin)
+                    noise = fz.garbage_hits(tris, rays, scan[0], scan[1])
+                    anyh = s.HitScene(rays, tMin=tmin, mode=tm.HIT_ANY)[0] == 1
+                    assert not ((anyh != hit) & ~noise).any(), what
                     if label == "sun" and flags == 0:
-                        assert ((s.HitScene(rays, tMin=tmin, mode=tm.HIT_SUN)[0] == 1) == hit).all(), (fz.KINDS[kind], tmin)
+                        sun = s.HitScene(rays, tMin=tmin, mode=tm.HIT_SUN)[0] == 1
+                        assert not ((sun != hit) & ~fz.off_footprint(tris, o, scan[0])).any(), what
                     m = (tree[0] != scan[0]) | (hit & (bits(tree[1]) != bits(scan[1])))
-                    known = m & hit & flat[np.maximum(scan[0], 0)]
-                    assert not (m & ~known).any(), (fz.KINDS[kind], label, tmin, int((m & ~known).sum()))
+                    assert not (m & ~noise).any(), what + (int((m & ~noise).sum()),)

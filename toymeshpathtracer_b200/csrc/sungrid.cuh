@@ -76,7 +76,10 @@ TMPT_HD void cell_range(const View& g, const Tri2& t, int& x0, int& x1, int& y0,
 
 // Does the projected triangle touch cell (cx, cy) grown by pad?  Separating axes: the square's own axes are the bounding-box test
 // (cell_range); the triangle's three edge normals are tested here.  A degenerate projection (a segment or a point) has no interior
-// side to orient a normal by: it is kept wherever its bounding box reaches.
+// side to orient a normal by: it is kept wherever its bounding box reaches.  (For a sliver the SIGN of `side` can be rounding noise
+// -- only for an edge whose line passes within ~1e-7 of the triangle's size of the opposite vertex, and then every point of the
+// triangle lies that close to the line: a grown cell that touches the triangle straddles it, and passes whichever way the normal
+// points.  tools/fuzz_emu.py, kinds "slivers" / "edge-on" / "grazing-slivers".)
 TMPT_HD bool touches_cell(const View& g, const Tri2& t, int cx, int cy) {
     const float c0x = g.loU + (float)cx * g.cell - g.pad, c0y = g.loV + (float)cy * g.cell - g.pad;
     const float c1x = g.loU + (float)(cx + 1) * g.cell + g.pad, c1y = g.loV + (float)(cy + 1) * g.cell + g.pad;
