@@ -4,6 +4,7 @@ __host__ __device__ headers compiled with g++; never part of the product path).
 
     python tools/fuzz_emu.py [first_seed] [last_seed]             # default 0 400, all cores
     python tools/fuzz_emu.py --render [first_seed] [last_seed]    # small frames of random scenes: emulation == oracle, bytes and ray count
+    python tools/fuzz_emu.py --refit [first_seed] [last_seed]     # scenes moved three times and refitted: tree and grid == scan of the moved triangles
 
 A seed makes one random scene -- 1 .. 2000 triangles of one of nine kinds (blobs, sizes over five decades, coplanar overlapping
 pieces, slivers, triangles edge-on to the sun, duplicates, a height-field mesh with shared vertices under three giants, triangles
@@ -256,8 +257,58 @@ def render_seed(seed):
     return seed, KINDS[kind], len(tris), scale, bad
 
 
+def refit_seed(seed):
+    """tmpt_scene_refit's logic: a random scene (no zero-area triangles) moved three times -- every vertex on its own, whole
+    triangles, an anisotropic scale + shift of everything; amplitudes from 1e-4 to 2 scene sizes -- and refitted in place (tree
+    boxes recomputed bottom-up, sun grid rebuilt); after each move tree and grid must equal the scan over the MOVED triangles.
+    -> (seed, kind, triangles, scale, failures)"""
+    rng = np.random.default_rng(seed)
+    tris, scale, kind = make_scene(rng, degenerate=False)
+    L = light_dir()
+    bad = []
+    for builder in (0, 1):
+        s = _emu().scene(tris, builder=builder)
+        cur = tris
+        for step in range(3):
+            amp = scale * 10 ** rng.uniform(-4, 0.3)
+            mode = int(rng.integers(0, 3))
+            v = cur.reshape(-1, 3, 3).astype(np.float64)
+            if mode == 0:
+                v = v + rng.normal(scale=amp, size=v.shape)
+            elif mode == 1:
+                v = v + rng.normal(scale=amp, size=(len(v), 1, 3))
+            else:
+                v = (v - v.mean((0, 1))) * rng.uniform(0.2, 3.0, 3) + v.mean((0, 1)) + rng.normal(scale=amp, size=3)
+            cur = np.ascontiguousarray(v.reshape(-1, 9), np.float32)
+            s.refit(cur)
+            o = make_origins(rng, cur, scale, k=1000)
+            d = rng.normal(size=o.shape)
+            d /= np.linalg.norm(d, axis=1, keepdims=True)
+            for label, rays in (("sun", np.concatenate([o, np.broadcast_to(L, o.shape)], 1).astype(np.float32)),
+                                ("random", np.concatenate([o, d], 1).astype(np.float32))):
+                scan, tree = s.hit(rays, mode=2), s.hit(rays, mode=0)
+                anyh, hit = s.hit(rays, mode=1)[0] >= 0, scan[0] >= 0
+                noise = garbage_hits(cur, rays, scan[0], scan[1])
+                m = (tree[0] != scan[0]) | (hit & (bits(tree[1]) != bits(scan[1])))
+                if (m & ~noise).any():
+                    bad.append(("closest", builder, step, label, int((m & ~noise).sum())))
+                if ((anyh != hit) & ~noise).any():
+                    bad.append(("any-hit", builder, step, label))
+                if label == "sun" and builder == 0:
+                    got = s.sun_occluded(o)[0] > 0
+                    wrong = (got != hit) & ~off_footprint(cur, o, scan[0])
+                    if wrong.any():
+                        bad.append(("sun-grid", step, int(wrong.sum())))
+        s.close()
+    return seed, KINDS[kind], len(tris), scale, bad
+
+
 def _run(seed):
     return run_seed(seed)
+
+
+def _run_refit(seed):
+    return refit_seed(seed) + (0,)
 
 
 def _run_render(seed):
@@ -266,13 +317,13 @@ def _run_render(seed):
 
 if __name__ == "__main__":
     from multiprocessing import Pool
-    args = [x for x in sys.argv[1:] if x != "--render"]
+    args = [x for x in sys.argv[1:] if not x.startswith("--")]
     a = int(args[0]) if len(args) > 0 else 0
     b = int(args[1]) if len(args) > 1 else 400
     _emu()  # build once, before the workers start
     fails = docs = 0
     with Pool(os.cpu_count()) as p:
-        for seed, kind, n, scale, bad, documented in p.imap_unordered(_run_render if "--render" in sys.argv else _run, range(a, b)):
+        for seed, kind, n, scale, bad, documented in p.imap_unordered(_run_render if "--render" in sys.argv else _run_refit if "--refit" in sys.argv else _run, range(a, b)):
             docs += documented
             if bad:
                 fails += 1
