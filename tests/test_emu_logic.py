@@ -571,3 +571,29 @@ def test_fuzz_seeds_refit(seed):
     (200 seeds were run once, none differed)."""
     _, kind, n, scale, bad = _fuzz().refit_seed(seed)
     assert not bad, (kind, n, scale, bad)
+
+
+@pytest.mark.parametrize("poison", [np.nan, np.inf, -np.inf])
+def test_nan_and_infinite_vertices(emu, poison):
+    """A mesh with a few NaN / infinite coordinates (2 % of its triangles): the exact test can never accept such a triangle (its t
+    is NaN or the comparison fails), the builders must not lose the others: tree == scan, grid == scan (an infinite scene box
+    gets no grid: shadow rays walk the tree)."""
+    fz = _fuzz()
+    rng = np.random.default_rng(3)
+    tris, scale, _ = fz.make_scene(rng, kind=0)
+    tris = tris.copy()
+    k = rng.integers(0, len(tris), max(1, len(tris) // 50))
+    tris[k, rng.integers(0, 9, len(k))] = poison
+    o = fz.make_origins(rng, np.nan_to_num(tris, nan=0.0, posinf=0.0, neginf=0.0), scale, k=500)
+    d = rng.normal(size=o.shape)
+    d = (d / np.linalg.norm(d, axis=1, keepdims=True)).astype(np.float32)
+    for builder in (0, 1):
+        s = emu.scene(tris, builder=builder)
+        for rays in (np.concatenate([o, d], 1).astype(np.float32), np.concatenate([o, np.broadcast_to(fz.light_dir(), o.shape)], 1).astype(np.float32)):
+            scan, tree = s.hit(rays, mode=2), s.hit(rays, mode=0)
+            assert (scan[0] >= 0).sum() > 50 and (tree[0] == scan[0]).all() and (bits(tree[1])[scan[0] >= 0] == bits(scan[1])[scan[0] >= 0]).all()
+            assert ((s.hit(rays, mode=1)[0] >= 0) == (scan[0] >= 0)).all()
+        if s.sun_grid(-1)["n"] > 0:
+            assert ((s.sun_occluded(o)[0] > 0) == (s.hit(rays, mode=2)[0] >= 0)).all()
+        else:
+            assert not np.isnan(poison)
