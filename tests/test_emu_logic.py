@@ -476,16 +476,24 @@ def test_sun_grid_with_thousands_of_triangles_over_one_cell(emu):
 
 
 # ---- found by tools/fuzz_emu.py (round 2) ------------------------------------------------------------------------------------
-def _fuzz():
+def _fuzz(fma=False):
     import importlib.util
     spec = importlib.util.spec_from_file_location("fuzz_emu", os.path.join(ROOT, "tools", "fuzz_emu.py"))
     m = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(m)
+    m.FMA = fma  # the slab distances with one fused multiply-add, as the device rounds them (bvh.cuh: fmaf_), or as a * b + c
     return m
 
 
+@pytest.fixture(scope="module")
+def emu_fma():
+    """The emulation with the slab distances rounded as the device rounds them (bvh.cuh: fmaf_ -> one fused multiply-add)."""
+    return Emu(defines=["-DTMPT_EMU_FMA=1"], tag="fma")
+
+
+@pytest.mark.parametrize("fused", [False, True], ids=["mul-add", "fma"])
 @pytest.mark.parametrize("builder", [0, 1], ids=["sah", "lbvh"])
-def test_rays_that_start_on_shared_vertices_with_tmin_zero(emu, builder):
+def test_rays_that_start_on_shared_vertices_with_tmin_zero(emu, emu_fma, builder, fused):
     """tMin = 0 and an origin ON a vertex of a mesh: every triangle around the vertex is hit at t = +-0 and the contract's tie rule
     (lowest original index) decides.  The pop-time cull compared the stack key WITH the child slot in its low bits -- slot 1..3 is
     a denormal > +-0 -- and dropped the children that held the lower indices (582 of 3000 vertex origins on a 75-triangle mesh)."""
@@ -496,7 +504,7 @@ def test_rays_that_start_on_shared_vertices_with_tmin_zero(emu, builder):
     o = np.concatenate([v[:, 0], v[:, 1], v[:, 2], (v[:, 0] + v[:, 1]) * np.float32(0.5)]).astype(np.float32)
     d = rng.normal(size=o.shape)
     d = (d / np.linalg.norm(d, axis=1, keepdims=True)).astype(np.float32)
-    s = emu.scene(tris, builder=builder)
+    s = (emu_fma if fused else emu).scene(tris, builder=builder)
     for rays in (np.concatenate([o, np.broadcast_to(fz.light_dir(), o.shape)], 1).astype(np.float32), np.concatenate([o, d], 1).astype(np.float32)):
         scan, tree = s.hit(rays, tmin=0.0, mode=2), s.hit(rays, tmin=0.0, mode=0)
         zero = (scan[0] >= 0) & (scan[1] == 0.0)
@@ -543,13 +551,15 @@ def test_sun_query_from_distant_origins_takes_the_scan(emu):
                 assert ((s.sun_occluded(o, tmax=tmax)[0] > 0) == (s.hit(rays, tmax=tmax, mode=2)[0] >= 0)).all(), (name, k, tmax)
 
 
+@pytest.mark.parametrize("fma", [False, True], ids=["mul-add", "fma"])
 @pytest.mark.parametrize("seed", [0, 2, 7, 12, 13, 15, 20, 37, 41, 280])
-def test_fuzz_seeds_tree_and_sun_grid_equal_the_scan(seed):
+def test_fuzz_seeds_tree_and_sun_grid_equal_the_scan(seed, fma):
     """tools/fuzz_emu.py on the seeds that failed before the two fixes above, and two scenes of grazing slivers: random scenes of
     nine kinds at scales 1e-4 .. 1e5; tree closest / any hit and the sun grid against the all-triangle scan at tMin = 0.001 and 0.
+    Both with the slab distances rounded as the device rounds them (one fma) and as a * b + c.
     The only differences allowed are the documented ones: the scan's GARBAGE hits -- rounding noise that passed
     the reference's determinant test, at a point outside the triangle's padded box / outside its footprint in the sun's projection."""
-    fz = _fuzz()
+    fz = _fuzz(fma)
     _, kind, n, scale, bad, documented = fz.run_seed(seed)
     assert not bad, (kind, n, scale, bad)
     if kind not in ("duplicates+degenerate", "grazing-slivers", "edge-on", "slivers"):

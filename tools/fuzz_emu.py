@@ -5,6 +5,7 @@ __host__ __device__ headers compiled with g++; never part of the product path).
     python tools/fuzz_emu.py [first_seed] [last_seed]             # default 0 400, all cores
     python tools/fuzz_emu.py --render [first_seed] [last_seed]    # small frames of random scenes: emulation == oracle, bytes and ray count
     python tools/fuzz_emu.py --refit [first_seed] [last_seed]     # scenes moved three times and refitted: tree and grid == scan of the moved triangles
+    (any of them with --fma: the emulation rounds the slab test's distances with one fused multiply-add, as the device does)
 
 A seed makes one random scene -- 1 .. 2000 triangles of one of nine kinds (blobs, sizes over five decades, coplanar overlapping
 pieces, slivers, triangles edge-on to the sun, duplicates, a height-field mesh with shared vertices under three giants, triangles
@@ -49,8 +50,13 @@ def _emu():
     global _EMU
     if _EMU is None:
         from emu_binding import Emu
-        _EMU = Emu()
+        # --fma: the slab distances rounded as the device rounds them (one fused multiply-add; bvh.cuh: fmaf_).  The plain build
+        # uses a * b + c -- the walk's answers must not depend on which.
+        _EMU = Emu(defines=["-DTMPT_EMU_FMA=1"], tag="fma") if FMA else Emu()
     return _EMU
+
+
+FMA = "--fma" in sys.argv
 
 
 def light_dir():

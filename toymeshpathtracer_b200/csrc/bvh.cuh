@@ -269,6 +269,8 @@ TMPT_HD float f4c(const float4& v, int k) { return k == 0 ? v.x : k == 1 ? v.y :
 TMPT_HD float fmaf_(float a, float b, float c) {
 #ifdef __CUDA_ARCH__
     return __fmaf_rn(a, b, c);
+#elif defined(TMPT_EMU_FMA)
+    return fmaf(a, b, c);  // host emulation built to round the slab distances exactly as the device does (tests/emu, tag "fma")
 #else
     return a * b + c;  // conservativeness does not depend on fusing
 #endif
