@@ -326,6 +326,7 @@ if __name__ == "__main__":
     args = [x for x in sys.argv[1:] if not x.startswith("--")]
     a = int(args[0]) if len(args) > 0 else 0
     b = int(args[1]) if len(args) > 1 else 400
+    os.environ.setdefault("OMP_NUM_THREADS", "1")  # one process per core already: the emulation's own OpenMP loops would oversubscribe
     _emu()  # build once, before the workers start
     fails = docs = 0
     with Pool(os.cpu_count()) as p:
