@@ -239,7 +239,8 @@ _ORC = None
 
 
 def render_seed(seed):
-    """Integrator level: a small frame of a random scene (no zero-area triangles; at most 400 triangles: the oracle scans them all)
+    """Integrator level: a small frame of a random scene + the loader's floor (no zero-area triangles, no grazing slivers; at most 400
+    triangles: the oracle scans them all; 2.2 rays per camera sample on average)
     through the host emulation of the product's path -- tree, sun grid, per-pixel RNG streams -- against the oracle in the same RNG
     mode: the frame's bytes and the ray count must be equal.  -> (seed, kind, triangles, scale, failures)"""
     global _ORC
@@ -248,10 +249,11 @@ def render_seed(seed):
         _ORC = Oracle()
     rng = np.random.default_rng(seed)
     tris, scale, kind = make_scene(rng, degenerate=False)
-    tris = tris[:400]
-    v = tris.reshape(-1, 3)
+    if KINDS[kind] == "grazing-slivers":  # (made to provoke garbage hits, which the oracle's scan reports and the tree does not)
+        tris, scale, kind = make_scene(rng, kind=3)
+    tris, mn, mx = _ORC.add_floor(tris[:400])  # the two floor triangles of LoadScene (main.cpp:150-162): paths bounce, shadow rays get shot
     w, h, spp = 24, 16, int(rng.choice([1, 3, 8]))
-    cam = _ORC.camera_for_scene(v.min(0), v.max(0), w, h)
+    cam = _ORC.camera_for_scene(mn, mx, w, h)
     oimg, orays = _ORC.render(tris, cam, w, h, spp, threads=1)
     bad = []
     for builder in (0, 1):
@@ -260,6 +262,7 @@ def render_seed(seed):
         if rays != orays or (img != oimg).any():
             bad.append(("frame", builder, rays, orays, int((img != oimg).any(-1).sum())))
         s.close()
+    render_seed.rays_per_sample = orays / (w * h * spp)
     return seed, KINDS[kind], len(tris), scale, bad
 
 
