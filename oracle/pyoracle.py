@@ -2,6 +2,7 @@
 
 ``Oracle``  -> oracle/liboracle.so   (plain-C restatement, oracle/oracle.c)
 ``Ref``     -> oracle/_ref/libref.so (the unmodified reference's own functions)
+``build_dropin`` -> oracle/_ref/TrimeshTracer_dropin (the reference program with `struct Scene` implemented over the C ABI)
 
 Only tests/, ``__graft_entry__.smoke()`` and ``bench.py``'s cpu_baseline /
 ``--impl reference`` legs may import this module.  The product package
@@ -19,6 +20,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ORACLE_SO = os.path.join(HERE, "liboracle.so")
 REF_SO = os.path.join(HERE, "_ref", "libref.so")
 REF_BIN = os.path.join(HERE, "_ref", "TrimeshTracer")
+DROPIN_BIN = os.path.join(HERE, "_ref", "TrimeshTracer_dropin")
 REF_ROOT = os.environ.get("TMPT_REF", "/root/reference")
 
 RNG_ROW, RNG_PIXEL = 0, 1
@@ -45,6 +47,16 @@ def build_ref() -> str | None:
         return REF_SO if os.path.exists(REF_SO) else None
     subprocess.run(["make", "-s", "-C", HERE, "ref", f"REF={REF_ROOT}"], check=True)
     return REF_SO
+
+
+def build_dropin() -> str | None:
+    """The reference program with its scene.cpp swapped for oracle/dropin/scene_tmpt.cpp (struct Scene over the C ABI), linked
+    against the product's libtmpt.so -- needs the reference sources (this container only) and a built product library."""
+    lib = os.path.join(os.path.dirname(HERE), "toymeshpathtracer_b200", "libtmpt.so")
+    if not os.path.isdir(os.path.join(REF_ROOT, "source")) or not os.path.exists(lib):
+        return DROPIN_BIN if os.path.exists(DROPIN_BIN) else None
+    subprocess.run(["make", "-s", "-C", HERE, "dropin", f"REF={REF_ROOT}"], check=True)
+    return DROPIN_BIN
 
 
 class Oracle:

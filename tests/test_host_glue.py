@@ -286,3 +286,27 @@ def test_build_staleness_is_by_content_and_safe_under_concurrency(tmp_path):
     assert not tb._stale(tb.LIB)
     with open(tb._stamp(tb.LIB)) as f:
         assert f.read().strip() == tb._source_hash()
+
+
+@pytest.mark.ref
+@pytest.mark.skipif(tm.device_count() > 0, reason="a GPU is present (tests/test_zz_gpu_fuzz_regressions.py runs the program there)")
+def test_reference_program_links_against_the_library_through_its_scene_class(tmp_path):
+    """INTEGRATION.md B, compiled for real: the reference's own main.cpp / maths.cpp / objparser.cpp and its UNMODIFIED scene.h, with
+    scene.cpp replaced by oracle/dropin/scene_tmpt.cpp (struct Scene's members over tmpt_scene_create / tmpt_hit_scene).  Here, without
+    a GPU: it builds, links libtmpt.so, contains no octree, keeps the reference's command line, loads the .obj with the reference's
+    own loader -- and then fails loudly, because the library has no CPU path."""
+    from oracle.pyoracle import build_dropin
+    exe = build_dropin()
+    assert exe and os.path.exists(exe)
+    assert "libtmpt.so" in subprocess.run(["ldd", exe], capture_output=True, text=True).stdout
+    syms = subprocess.run(["nm", "-C", exe], capture_output=True, text=True).stdout
+    assert "HitSceneInternal" not in syms and "OctreeNode::Subdivide" not in syms and "OctreeNode::InternalDivide" not in syms  # scene.cpp is not in it
+    assert "U tmpt_hit_scene" in syms and "U tmpt_scene_create" in syms and "Scene::HitScene" in syms
+    r = subprocess.run([exe], capture_output=True, text=True)
+    assert (r.returncode, r.stdout) == (1, "Usage: TrimeshTracer.exe [width] [height] [samplesPerPixel] [objFile]\n")
+    obj = tmp_path / "t.obj"
+    obj.write_text("v 0 0 0\nv 1 0 0\nv 0 1 0\nf 1 2 3\n")
+    r = subprocess.run([exe, "8", "8", "1", str(obj)], capture_output=True, text=True, cwd=tmp_path)
+    lines = r.stdout.strip().split("\n")
+    assert r.returncode == 1 and lines[0].startswith(f"Initialized scene '{obj}' (3 tris) in ")
+    assert lines[1].startswith("ERROR: tmpt_scene_create") and "no CPU path" in lines[1]

@@ -96,3 +96,30 @@ def test_fuzz_scenes_tree_and_sun_grid_equal_the_scan(fz, seed):
                         assert not ((sun != hit) & ~fz.off_footprint(tris, o, scan[0])).any(), what
                     m = (tree[0] != scan[0]) | (hit & (bits(tree[1]) != bits(scan[1])))
                     assert not (m & ~noise).any(), what + (int((m & ~noise).sum()),)
+
+
+@pytest.mark.parametrize("name,w,h,spp", [("suzanne", 64, 36, 2), ("cube", 96, 54, 2), ("teapot", 48, 27, 1)])
+def test_reference_program_with_the_scene_class_swapped(tmp_path, name, w, h, spp):
+    """The drop-in boundary at its narrowest (oracle/dropin/scene_tmpt.cpp): the reference's OWN program -- its
+    main.cpp, loader, camera, Trace / Scatter, per-row RNG streams, TBB row loop, stb PNG writer, and its unmodified scene.h --
+    with only scene.cpp replaced, so that every Scene::HitScene is answered by libtmpt.so on the GPU (one ray per call).  Because
+    flag, Hit.pos and Hit.normal come back bit for bit, the reference's integrator walks the same paths: output.png is the
+    reference binary's output.png byte for byte, and the ray count is the same.  (Both binaries are built in the build container,
+    oracle/Makefile, and travel in oracle/_ref/.)"""
+    import subprocess
+    import bench
+    from oracle.pyoracle import DROPIN_BIN, REF_BIN
+    if not (os.path.exists(DROPIN_BIN) and os.path.exists(REF_BIN)):
+        pytest.skip("oracle/_ref binaries not built (they are built where the reference sources are)")
+    obj = bench.scene_obj_path(name)
+    out = {}
+    for label, exe in (("reference", REF_BIN), ("dropin", DROPIN_BIN)):
+        d = tmp_path / label
+        d.mkdir()
+        r = subprocess.run([exe, str(w), str(h), str(spp), obj], cwd=d, capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, (label, r.stdout, r.stderr)
+        lines = r.stdout.strip().split("\n")
+        assert lines[1].startswith(f"Rendered scene at {w}x{h},{spp}spp in ")
+        out[label] = ((d / "output.png").read_bytes(), lines[2].split()[1])  # the PNG, and "- <n> K Rays"
+    assert out["dropin"][1] == out["reference"][1]
+    assert out["dropin"][0] == out["reference"][0]
