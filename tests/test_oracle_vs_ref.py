@@ -101,3 +101,32 @@ def test_fuzz_scenes_restatement_equals_the_reference_triangle_test(oracle, ref,
         ref.scene_free(h)
     if first == 260:
         assert lost > 0  # (seed 269)
+
+
+def test_fuzz_scenes_render_equals_reference_functor(oracle, ref):
+    """The integrator restatement on random scenes: 24x16 frames (1 / 3 / 8 spp) of the fuzzer's scenes + the loader's floor through
+    the reference's own TraceImageBody (row RNG streams, libm, its octree) and through oracle.c in the same mode: same bytes, same
+    ray count.  Scene kinds on which the reference's octree loses hits of its own triangle test (flat axis-aligned pieces:
+    "coplanar", "flat-in-depth") or meets garbage hits ("grazing-slivers") are left out -- in 400 frames the two differed on 25,
+    all of those kinds, and on none of the other 375 (see the previous test for what the octree does there)."""
+    import importlib.util
+    from conftest import ROOT
+    spec = importlib.util.spec_from_file_location("fuzz_emu", os.path.join(ROOT, "tools", "fuzz_emu.py"))
+    fz = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(fz)
+    compared = 0
+    for seed in range(60):
+        rng = np.random.default_rng(seed)
+        tris, scale, kind = fz.make_scene(rng, degenerate=False)
+        if fz.KINDS[kind] in ("coplanar", "flat-in-depth", "grazing-slivers"):
+            continue
+        tris, mn, mx = oracle.add_floor(tris[:400])
+        w, h, spp = 24, 16, int(rng.choice([1, 3, 8]))
+        cam = oracle.camera_for_scene(mn, mx, w, h)
+        hdl = ref.scene_from_tris(tris, mn, mx)
+        rimg, rrc = ref.render(hdl, cam, w, h, spp)
+        ref.scene_free(hdl)
+        img, rc = oracle.render(tris, cam, w, h, spp, RNG_ROW, TRIG_LIBM)
+        assert rc == rrc and (img == rimg).all(), (seed, fz.KINDS[kind])
+        compared += 1
+    assert compared >= 30
