@@ -219,7 +219,9 @@ def test_sponza_camera_special_case(oracle):
 def test_png_writer_round_trip(tmp_path):
     from PIL import Image
     rng = np.random.default_rng(3)
-    for (w, h) in [(1, 1), (7, 5), (640, 360), (300, 70)]:  # the last two span >1 stored deflate block
+    # (640x360 and 300x70 span several stored deflate blocks; 16383 / 16384 / 16385 pixels put a row at, one under and one over the
+    #  65535-byte block limit; 10000 is the reference's largest width / height, main.cpp:263-275)
+    for (w, h) in [(1, 1), (7, 5), (640, 360), (300, 70), (16383, 1), (16384, 2), (16385, 3), (10000, 3), (3, 10000)]:
         img = rng.integers(0, 256, (h, w, 4), dtype=np.uint8)
         p = str(tmp_path / f"o_{w}x{h}.png")
         tm.write_png(p, img, flip_vertically=True)
