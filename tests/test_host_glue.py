@@ -252,6 +252,30 @@ def test_cli_argument_errors():
     assert run("10", "10", "1", "/nonexistent/x.obj") == (1, "ERROR: failed to load .obj file\n")
 
 
+@pytest.mark.ref
+def test_cli_rejects_arguments_exactly_like_the_reference_binary(tmp_path):
+    """main.cpp:258-291: atoi semantics ("12abc" is 12, " 7" is 7, "1e3" is 1, "abc" and "" are 0, 99999999999 overflows), the range
+    checks, their order and wording, the exit codes -- 120 random argument lists through oracle/_ref/TrimeshTracer and through the
+    product's command line, compared wherever the reference stops before it renders."""
+    from oracle.pyoracle import REF_BIN, build_ref
+    build_ref()
+    obj = tmp_path / "t.obj"
+    obj.write_text("v 0 0 0\nv 1 0 0\nv 0 1 0\nf 1 2 3\n")
+    toks = ["0", "1", "-1", "10000", "10001", "1024", "1025", "abc", "12abc", " 7", "+3", "1e3", "99999999999", "", "2.9"]
+    rng = np.random.default_rng(1)
+    cases = [[], ["1"], ["1", "2"], ["1", "2", "3"]]
+    cases += [[toks[rng.integers(0, 15)], toks[rng.integers(0, 15)], toks[rng.integers(0, 15)], str(obj) if rng.random() < 0.8 else "/nonexistent.obj"]
+              for _ in range(120)]
+    compared = 0
+    for args in cases:
+        a = subprocess.run([REF_BIN, *args], cwd=tmp_path, capture_output=True, text=True)
+        if a.returncode == 1 and not a.stdout.startswith("Initialized"):
+            b = subprocess.run([tm.CLI_PATH, *args], cwd=tmp_path, capture_output=True, text=True)
+            assert (b.returncode, b.stdout) == (a.returncode, a.stdout), args
+            compared += 1
+    assert compared > 60
+
+
 def test_real_sponza_override(tmp_path, monkeypatch):
     """TMPT_SPONZA_OBJ (the reference's own data/sponza.obj, absent from this environment): when it names a file, bench.py
     and the tools use it instead of the procedural stand-in, and every results line says which one it was."""
