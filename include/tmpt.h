@@ -108,7 +108,12 @@ int tmpt_scene_refit(tmpt_scene* scene, const float* tris9, int triCount, double
  *   mem        TMPT_HOST: all pointers are host memory (copies are made inside the call);
  *              TMPT_DEVICE: all are device pointers on the scene's device.
  *   stream     a cudaStream_t (NULL = the scene's own stream); with TMPT_DEVICE the call is
- *              asynchronous on that stream. */
+ *              asynchronous on that stream.
+ *   tMin may be 0 (a ray that starts ON a surface then hits it at t = +-0; ties between the triangles around a vertex go
+ *   to the lowest index) or negative.  Origins beyond 16 x the scene's largest |coordinate| are answered by the all-triangle
+ *   scan (same answers, slower).  The one case in which the answer differs from a scan over all triangles -- and from the
+ *   reference's octree, and the octree from the scan -- is a "hit" that is rounding noise of maths.cpp:350's determinant test
+ *   (a ray in the plane of a zero-area or very long thin triangle), reported far from the triangle itself: DESIGN.md 2.1. */
 int tmpt_hit_scene(const tmpt_scene* scene, const float* rays6, int64_t nRays, float tMin, float tMax,
                    int mode, int mem, int32_t* outID, float* outT, float* outPos3, float* outNormal3,
                    void* stream);
