@@ -116,7 +116,10 @@ def test_reference_program_with_the_scene_class_swapped(tmp_path, name, w, h, sp
     for label, exe in (("reference", REF_BIN), ("dropin", DROPIN_BIN)):
         d = tmp_path / label
         d.mkdir()
-        r = subprocess.run([exe, str(w), str(h), str(spp), obj], cwd=d, capture_output=True, text=True, timeout=600)
+        # (two worker threads for the patched program: concurrent callers of one scene take turns inside tmpt_hit_scene(TMPT_HOST);
+        #  the image does not depend on the thread count -- every row seeds its own stream, main.cpp:204)
+        env = dict(os.environ, TBB_SHIM_THREADS="2") if label == "dropin" else None
+        r = subprocess.run([exe, str(w), str(h), str(spp), obj], cwd=d, capture_output=True, text=True, timeout=600, env=env)
         assert r.returncode == 0, (label, r.stdout, r.stderr)
         lines = r.stdout.strip().split("\n")
         assert lines[1].startswith(f"Rendered scene at {w}x{h},{spp}spp in ")
