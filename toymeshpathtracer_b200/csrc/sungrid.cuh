@@ -115,7 +115,7 @@ TMPT_HD float far_depth(const View& g, const Tri2& t, int cx, int cy) {
 }
 
 // Grid resolution for a scene: about 32 cells per triangle, a power of two in [32, 4096].  Headline scene (66 k triangles), Mrays/s
-// of the whole frame at 512 / 1024 / 2048 / 4096 cells per side: 7110 / 7575 / 7790 / 7875 (tree: 5255); 2048 = 53 MB of lists.
+// of the whole frame at 512 / 1024 / 2048 / 4096 cells per side: 7110 / 7575 / 7790 / 7875 (tree: 5255); 2048 = 17 MB of offsets + 30 MB of lists.
 TMPT_HD int default_cells_per_side(int triCount) {
     int n = 32;
     while (n < 4096 && 2ll * n * n < 32ll * triCount) n *= 2;  // (nearest power of two, geometrically)
