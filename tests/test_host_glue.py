@@ -121,15 +121,17 @@ def test_float_parser_matches_reference_semantics(tmp_path):
 
 
 def _random_obj_number(rng):
-    k = int(rng.integers(0, 12))
+    k = int(rng.integers(0, 13))
     x = rng.normal() * 10 ** rng.uniform(-6, 6)
     return ["%.9g" % x, "%.3f" % x, "%e" % x, "%E" % x, "%d" % int(x), "%d." % int(x), ("%.6f" % abs(x % 1))[1:], "+%.5g" % abs(x), "%.17g" % x,
-            "%.25f" % x, "%de%d" % (rng.integers(-999, 999), rng.integers(-30, 30)), "%.4fe+%d" % (x, rng.integers(0, 25))][k]
+            "%.25f" % x, "%de%d" % (rng.integers(-999, 999), rng.integers(-30, 30)), "%.4fe+%d" % (x, rng.integers(0, 25)),
+            # an exponent of 10-13 digits: the reference accumulates it in an int that wraps (objparser.cpp:113-117); so must this
+            "%de%s%d" % (rng.integers(1, 99), rng.choice(["", "-", "+"]), rng.integers(2 ** 31, 2 ** 42))][k]
 
 
 def _random_obj_text(rng):
     """OBJ text over the whole grammar objparser.cpp accepts: every number syntax (no integer / fraction part, exponents that take
-    the pow() branch, 25 decimals), records with too few or too many numbers, trailing garbage, tabs, CRLF, vt / vn / g / s /
+    the pow() branch or overflow an int, 25 decimals), records with too few or too many numbers, trailing garbage, tabs, CRLF, vt / vn / g / s /
     usemtl records, 'v' not followed by a blank, faces as v, v/vt, v//vn, v/vt/vn with positive, '+' and relative indices, polygons
     (fans), a 0 index (ends the face), one- and two-corner faces, vertices declared after faces, no final newline."""
     num = lambda: _random_obj_number(rng)

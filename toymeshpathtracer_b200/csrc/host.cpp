@@ -30,7 +30,7 @@ int parse_int(const char* s, const char** end) {
     unsigned value = 0;
     while (*s >= '0' && *s <= '9') value = value * 10u + unsigned(*s++ - '0');
     *end = s;
-    return negative ? -int(value) : int(value);
+    return negative ? int(0u - value) : int(value);  // (the reference writes -int(result): the same bits, without the overflow at 2^31)
 }
 
 // objparser.cpp:62-131: mantissa digits accumulated in a double, decimal exponent applied by
@@ -55,9 +55,9 @@ float parse_float(const char* s, const char** end) {
         ++s;
         const int esign = *s == '-' ? -1 : 1;
         if (*s == '-' || *s == '+') ++s;
-        int e = 0;
-        while (*s >= '0' && *s <= '9') e = e * 10 + (*s++ - '0');
-        exp10 += esign * e;
+        unsigned e = 0;  // wraps like the reference's int does in practice (objparser.cpp:113-117), without signed overflow
+        while (*s >= '0' && *s <= '9') e = e * 10u + unsigned(*s++ - '0');
+        exp10 = int(unsigned(exp10) + unsigned(esign) * e);
     }
     *end = s;
     if (exp10 <= 0 && exp10 >= -22) return float(sign * mantissa / kPow10[-exp10]);
