@@ -338,3 +338,42 @@ def test_reference_program_links_against_the_library_through_its_scene_class(tmp
     lines = r.stdout.strip().split("\n")
     assert r.returncode == 1 and lines[0].startswith(f"Initialized scene '{obj}' (3 tris) in ")
     assert lines[1].startswith("ERROR: tmpt_scene_create") and "no CPU path" in lines[1]
+
+
+def test_every_entry_point_survives_null_and_out_of_range_arguments(tmp_path):
+    """The C ABI's error behaviour (status codes and tmpt_last_error, never a crash, never an exception across the
+    boundary): each entry point called with NULL pointers / negative sizes returns an error status (or 0 rows / 0 pixels for the two
+    size helpers, nothing for the two destructors) and leaves a message."""
+    L = tm.lib()
+    N = None
+    buf, out = (C.c_uint8 * 64)(), C.c_void_p()
+    f0, f1, one = C.c_float(0), C.c_float(1), C.c_int64(1)
+    failing = {
+        "tmpt_scene_create (NULL out)": lambda: L.tmpt_scene_create(N, 0, 0, 0, N),
+        "tmpt_scene_create (negative count)": lambda: L.tmpt_scene_create(N, -1, 0, 0, C.byref(out)),
+        "tmpt_scene_create (NULL triangles)": lambda: L.tmpt_scene_create(N, 5, 0, 0, C.byref(out)),
+        "tmpt_scene_get_info": lambda: L.tmpt_scene_get_info(N, N),
+        "tmpt_scene_refit": lambda: L.tmpt_scene_refit(N, N, 0, N),
+        "tmpt_hit_scene": lambda: L.tmpt_hit_scene(N, N, one, f0, f1, 0, 0, N, N, N, N, N),
+        "tmpt_render": lambda: L.tmpt_render(N, N, 1, 1, 1, 0, N, N, N, N),
+        "tmpt_progressive_begin": lambda: L.tmpt_progressive_begin(N, 1, 1),
+        "tmpt_progressive_pass": lambda: L.tmpt_progressive_pass(N, N, 1, 0, N, N, N, N, N),
+        "tmpt_render_stripes": lambda: L.tmpt_render_stripes(N, N, 1, 1, 1, 0, 0, 1, 0, N, N, N, N, N),
+        "tmpt_render_multi": lambda: L.tmpt_render_multi(N, 0, N, 1, 1, 1, N, N, N),
+        "tmpt_frame_alloc": lambda: L.tmpt_frame_alloc(0, C.c_size_t(0), N, N),
+        "tmpt_frame_open": lambda: L.tmpt_frame_open(0, N, N),
+        "tmpt_render_stats": lambda: L.tmpt_render_stats(N, N, 1, 1, 1, N),
+        "tmpt_hit_scene_stats": lambda: L.tmpt_hit_scene_stats(N, N, one, f0, f1, 0, N),
+        "tmpt_load_obj": lambda: L.tmpt_load_obj(N, N, N, N, N),
+        "tmpt_write_png (NULL)": lambda: L.tmpt_write_png(N, 1, 1, N, 0),
+        "tmpt_write_png (size)": lambda: L.tmpt_write_png(os.fsencode(tmp_path / "x.png"), 0, -1, buf, 0),
+        "tmpt_render_kernel_choice": lambda: L.tmpt_render_kernel_choice(N, N, N),
+    }
+    L.tmpt_last_error.restype = C.c_char_p
+    for name, call in failing.items():
+        assert call() != tm.TMPT_OK and L.tmpt_last_error(), name
+    assert L.tmpt_stripe_rows(-1, 0, 0, 0) == 0 and L.tmpt_local_width(-1, -1, 0) == 0
+    L.tmpt_scene_destroy(N)
+    L.tmpt_free(N)
+    assert L.tmpt_frame_close(0, N) == tm.TMPT_OK and L.tmpt_frame_free(0, N) == tm.TMPT_OK  # nothing to release
+    assert L.tmpt_main(0, N) == 1  # the usage line
